@@ -1,0 +1,95 @@
+"""The CPU oracle (oracle/) against the golden vectors recorded from the unmodified reference
+(oracle/make_golden.py -> tests/golden/).  Bit-exact on values and autograd gradients: the
+restatement keeps the reference's torch op sequence."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from oracle import planner as P
+
+OPS = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+
+
+@pytest.fixture(scope='module')
+def single(golden_dir):
+    return np.load(os.path.join(golden_dir, 'single_ops.npz'))
+
+
+@pytest.fixture(scope='module')
+def chains(golden_dir):
+    return np.load(os.path.join(golden_dir, 'chains.npz'))
+
+
+@pytest.mark.parametrize('op', OPS)
+@pytest.mark.parametrize('variant', ['n_none', 'n_m1', 'n_m3', 'w_none'])
+def test_single_op_matches_reference(single, op, variant):
+    key = 'op%d_%s' % (op, variant)
+    img = torch.from_numpy(single['img']).requires_grad_()
+    p = torch.from_numpy(single[key + '_param']).requires_grad_()
+    mask = {'none': None, 'm1': 'mask1', 'm3': 'mask3'}[variant.split('_')[1]]
+    mask = None if mask is None else torch.from_numpy(single[mask])
+    out = O.execute(op, img, p, mask)
+    (out * torch.from_numpy(single['wgt'])).sum().backward()
+    l1 = (out - torch.from_numpy(single['target'])).abs().flatten(1).sum(1)
+    assert np.array_equal(out.detach().numpy(), single[key + '_out'])
+    assert np.array_equal(l1.detach().numpy(), single[key + '_l1sum'])
+    assert np.array_equal(img.grad.numpy(), single[key + '_gimg'])
+    gp = p.grad.numpy() if p.grad is not None else np.zeros_like(single[key + '_gparam'])
+    assert np.array_equal(gp, single[key + '_gparam'])
+
+
+@pytest.mark.parametrize('name', ['c6', 'c6r', 'c3', 'c2'])
+def test_chain_matches_reference(chains, name):
+    ops = [int(v) for v in chains[name + '_ops']]
+    img = torch.from_numpy(chains['img']).requires_grad_()
+    params = [torch.from_numpy(chains['%s_param%d' % (name, k)]).requires_grad_() for k in range(len(ops))]
+    out = O.chain(img, ops, params)
+    target = torch.from_numpy(chains[name + '_target'])
+    l1 = O.l1_mean(out, target)
+    l1.backward()
+    assert np.array_equal(out.detach().numpy(), chains[name + '_out'])
+    assert np.float32(l1.item()) == chains[name + '_l1mean']
+    assert np.float32(O.l1_dist(out.detach(), target).item()) == chains[name + '_l1dist']
+    assert np.array_equal(img.grad.numpy(), chains[name + '_gimg'])
+    for k, p in enumerate(params):
+        assert np.array_equal(p.grad.numpy(), chains['%s_gparam%d' % (name, k)])
+
+
+def test_planner_fits_match_reference(golden_dir):
+    pair = np.load(os.path.join(golden_dir, 'planner_pair.npz'))
+    tr = json.load(open(os.path.join(golden_dir, 'planner_transcripts.json')))
+    I0, Igt = torch.from_numpy(pair['I0']), torch.from_numpy(pair['Igt'])
+    ex = O.OracleExecutor()
+    assert P.get_dist(I0, Igt).item() == tr['init_dist']
+    for op in [0, 1, 2, 5, 6]:          # op 3 (24 params, 4800 evaluations) is covered by the beam test
+        cnt = [0]
+        param, ok = P.get_param(I0, Igt, op, ex, 'Nelder-Mead', cnt)
+        ref = tr['nm_fits'][str(op)]
+        assert cnt[0] == ref['nfev'] and bool(ok) == ref['success']
+        assert param[0].tolist() == ref['param']
+        assert P.get_dist(P.execute(I0, op, param, ex), Igt).item() == ref['dist']
+
+
+def test_planner_fixed_order_matches_reference(golden_dir):
+    pair = np.load(os.path.join(golden_dir, 'planner_pair.npz'))
+    tr = json.load(open(os.path.join(golden_dir, 'planner_transcripts.json')))
+    I0, Igt = torch.from_numpy(pair['I0']), torch.from_numpy(pair['Igt'])
+    actions, Is = P.beam_search(I0, Igt, None, O.OracleExecutor(), None, 1, [0, 1, 2, 3, 5, 6], O.ACTION_NAMES, 3,
+                                1e-2, 'L1', 'Nelder-Mead', variant='fixed_order')
+    got = [[[a[0], a[1], a[2]] for a in seq] for seq in actions]
+    assert got == tr['fixed']['actions']
+    assert len(Is) == 1 and len(Is[0]) == 3 and tuple(Is[0][0].shape) == (1, 3, 16, 16)
+
+
+def test_planner_beam_matches_reference(golden_dir):
+    pair = np.load(os.path.join(golden_dir, 'planner_pair.npz'))
+    tr = json.load(open(os.path.join(golden_dir, 'planner_transcripts.json')))
+    I0, Igt = torch.from_numpy(pair['I0']), torch.from_numpy(pair['Igt'])
+    actions, _ = P.beam_search(I0, Igt, None, O.OracleExecutor(), None, 2, [0, 1, 2, 3, 5, 6], O.ACTION_NAMES, 3,
+                               1e-2, 'L1', 'Nelder-Mead')
+    got = [[[a[0], a[1], a[2]] for a in seq] for seq in actions]
+    assert got == tr['beam2']['actions']
