@@ -1,0 +1,141 @@
+/*
+ * t2o.h -- C-ABI of the B200-native T2ONet operator / planner hot path.
+ *
+ * The reference (jshi31/T2ONet) has no FFI: its operator API is a Python class surface
+ * (models/operators.py, executors/executor.py, utils/beam_search.py).  The entry points
+ * below are what a binding for that surface calls instead of the chain of eager PyTorch
+ * kernels; t2onet_b200/ binds them with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its comment says "host"
+ *   - images are float32, NCHW planar, contiguous: (B, 3, H, W), values nominally in [0, 1]
+ *   - masks are float32 (B, 1|3, H, W) or NULL (= all ones, models/operators.py:123)
+ *   - parameters are float32 rows: op k of image b reads
+ *         params[b * param_stride + param_off[k] + i],  i < t2o_num_params(op_ids[k])
+ *     with the reference's layouts (tone: (L,), color: (3, L) index c*L+i, models/operators.py:578,608)
+ *   - all work is enqueued on `stream`; nothing synchronises the device
+ *   - `workspace` is caller-owned device scratch of >= t2o_workspace_bytes(...) bytes that must
+ *     be ZERO before its first use (the library leaves it zeroed again after every call)
+ *   - every function returns a t2o_status (0 = ok) and never throws; inputs are never modified
+ */
+#ifndef T2O_H_
+#define T2O_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2O_VERSION 100          /* major*100 + minor */
+#define T2O_MAX_CHAIN 8          /* operators fused in one launch */
+#define T2O_MAX_CURVE_STEPS 8    /* cfg.curve_steps (options/fiveK_base_options.py:50) */
+#define T2O_MAX_OP_PARAMS 24     /* color: 3 * curve_steps */
+
+/* flags of t2o_chain_forward */
+#define T2O_FLAG_RAW_PROCESS 1   /* n_ops == 1 only: write Operator.process(img, param) itself
+                                    (models/operators.py:128), without the mask blend and clamp */
+
+/* Operator ids = reference Executor indices (executors/executor.py:30) + extension ids for the
+ * operator classes that exist without an Executor slot (models/operators.py:186,527). */
+enum t2o_op {
+    T2O_OP_IDENTITY = -1,     /* executors/executor.py:44-46 (op_ind < 0): passthrough, no clamp */
+    T2O_OP_BRIGHTNESS = 0,    /* models/operators.py:277-283 */
+    T2O_OP_CONTRAST = 1,      /* models/operators.py:240-245 */
+    T2O_OP_SATURATION = 2,    /* models/operators.py:473-479 */
+    T2O_OP_COLOR = 3,         /* models/operators.py:607-616 */
+    T2O_OP_INPAINT = 4,       /* models/operators.py:680-682 -- NOT implemented (deep CNN, out of scope) */
+    T2O_OP_TONE = 5,          /* models/operators.py:571-585 */
+    T2O_OP_SHARPNESS = 6,     /* models/operators.py:351-358 */
+    T2O_OP_WHITE = 7,         /* models/operators.py:510-512 */
+    T2O_OP_EXPOSURE = 8,      /* models/operators.py:209-210 */
+    T2O_OP_WHITEBALANCE = 9   /* models/operators.py:548-549 */
+};
+
+enum t2o_status {
+    T2O_OK = 0,
+    T2O_ERR_INVALID_ARG = 1,      /* NULL where required, bad sizes, bad op id */
+    T2O_ERR_UNSUPPORTED = 2,      /* inpaint, curve_steps > 8, more than one sharpen per launch, ... */
+    T2O_ERR_WORKSPACE = 3,        /* workspace too small */
+    T2O_ERR_CUDA = 4,             /* a CUDA runtime call failed (see t2o_last_cuda_error) */
+    T2O_ERR_NO_DEVICE = 5         /* no sm_100 device / driver entry point missing */
+};
+
+typedef struct CUstream_st *t2o_stream_t;   /* == cudaStream_t */
+
+int t2o_version(void);
+const char *t2o_status_string(int status);
+const char *t2o_last_cuda_error(void);
+/* number of parameters of one operator (num_op_param of each class in models/operators.py) */
+int t2o_num_params(int op_id, int curve_steps);
+
+/* Scratch needed by the chain entry points for a (B, 3, H, W) batch with `param_stride` floats per row. */
+size_t t2o_workspace_bytes(int B, int H, int W, int param_stride);
+/* Scratch needed by t2o_score_candidates for S states and C candidates on (H, W) images. */
+size_t t2o_score_workspace_bytes(int S, int C, int H, int W);
+
+/*
+ * K fused Operator.execute steps (models/operators.py:112-131: process -> out*mask + img*(1-mask)
+ * -> clamp(0,1)), i.e. K successive Executor.execute calls with specified parameters
+ * (executors/executor.py:33-55), in ONE pass over HBM.  K == 1 is a single Operator.execute.
+ *   out      (B,3,H,W) or NULL      edited image
+ *   target   (B,3,H,W) or NULL      with l1_sum: per-image sum |out - target| (the numerator of
+ *   l1_sum   (B,)      or NULL      get_dist 'L1', utils/beam_search.py:170-173, and of the training L1)
+ * At most one sharpness operator per launch (the binding splits longer chains).
+ */
+int t2o_chain_forward(int n_ops, const int *op_ids /*host*/, const int *param_off /*host*/,
+                      const float *img, const float *mask, int mask_ch,
+                      const float *params, int param_stride,
+                      const float *target, float *out, float *l1_sum,
+                      int B, int H, int W, int curve_steps, int flags,
+                      void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
+ * Backward of t2o_chain_forward with the forward RECOMPUTED in the same pass (no stored
+ * intermediates; replaces autograd through the ~50 saved planes per operator).
+ * Upstream gradient, one of:
+ *   grad_out (B,3,H,W)                         dLoss/d(out), or
+ *   grad_out == NULL, target + grad_l1 (B,)    dLoss/d(out) = grad_l1[b] * sign(out - target)
+ *                                              (the fused L1; grad_l1[b] = dLoss/d(l1_sum[b]))
+ * Outputs:
+ *   grad_params (B, param_stride)   every column of the row is written (0 outside the used slots)
+ *   grad_img    (B,3,H,W) or NULL   dLoss/d(img)
+ *   out, l1_sum           or NULL   the forward results, for a fused forward+backward step
+ * Gradient conventions follow torch autograd on the reference graph: clamp passes the gradient on
+ * the closed interval, the contrast luminance clamp splits ties 0.5/0.5, HSV max/min route to the
+ * first tied channel (exact for gray pixels; two-channel ties see DESIGN.md).
+ */
+int t2o_chain_backward(int n_ops, const int *op_ids /*host*/, const int *param_off /*host*/,
+                       const float *img, const float *mask, int mask_ch,
+                       const float *params, int param_stride,
+                       const float *grad_out, const float *target, const float *grad_l1,
+                       float *grad_params, float *grad_img, float *out, float *l1_sum,
+                       int B, int H, int W, int curve_steps,
+                       void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/* Per-image sum |a - b| over n floats per image: get_dist(x1, x2, 'L1') * numel, utils/beam_search.py:170-173. */
+int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_per_image,
+               void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
+ * Planner candidate scoring (the inner loop of get_param_naive / beam_search,
+ * utils/beam_search.py:77-87,229-237): candidate c applies operator cand_op[c] with parameters
+ * cand_param[c*24 ..] to state image cand_state[c] and is scored against that state's target,
+ *     l1_sum[c] = sum |clamp(op(state; param)) - target|      (no image is written).
+ * Candidates MUST be sorted by cand_state (ascending); cand_begin[s] .. cand_begin[s+1] are the
+ * candidates of state s (S + 1 ints).  state_target[s] selects the target image of state s
+ * (NULL: target s % T).  Each (state, target) tile is staged once in shared memory by TMA and
+ * every candidate of that state is evaluated from there.
+ */
+int t2o_score_candidates(const float *states, int S, const float *targets, int T,
+                         const int32_t *state_target, const int32_t *cand_begin,
+                         const int32_t *cand_op, const float *cand_param, int C,
+                         float *l1_sum, int H, int W, int curve_steps,
+                         void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2O_H_ */

@@ -1,0 +1,88 @@
+// t2o_cabi.cu -- the extern "C" boundary declared in include/t2o.h.  Plain pointers and sizes
+// only; every entry point validates its arguments and returns a t2o_status.
+#include <cuda_runtime.h>
+
+#include "../../include/t2o.h"
+#include "t2o_math.cuh"
+
+namespace t2o {
+size_t chain_workspace_bytes(int B, int H, int W, int pstride);
+int chain_forward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
+                  const float *params, int pstride, const float *target, float *out, float *l1_sum,
+                  int B, int H, int W, int L, int flags, void *ws, size_t ws_bytes, cudaStream_t stream);
+int chain_backward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
+                   const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
+                   float *grad_params, float *grad_img, float *out, float *l1_sum,
+                   int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long long n, void *ws, size_t ws_bytes,
+                  cudaStream_t stream);
+size_t score_workspace_bytes(int S, int C, int H, int W);
+int score_candidates(const float *states, int S, const float *targets, int T, const int *state_target,
+                     const int *cand_begin, const int *cand_op, const float *cand_param, int C, float *l1_sum,
+                     int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+const char *last_cuda_error();
+}  // namespace t2o
+
+extern "C" {
+
+int t2o_version(void) { return T2O_VERSION; }
+
+const char *t2o_status_string(int status) {
+    switch (status) {
+        case T2O_OK: return "ok";
+        case T2O_ERR_INVALID_ARG: return "invalid argument";
+        case T2O_ERR_UNSUPPORTED: return "unsupported configuration";
+        case T2O_ERR_WORKSPACE: return "workspace missing or too small";
+        case T2O_ERR_CUDA: return "CUDA runtime error";
+        case T2O_ERR_NO_DEVICE: return "no usable device / driver entry point";
+        default: return "unknown status";
+    }
+}
+
+const char *t2o_last_cuda_error(void) { return t2o::last_cuda_error(); }
+
+int t2o_num_params(int op_id, int curve_steps) {
+    if (op_id < t2o::OP_IDENTITY || op_id >= t2o::OP_COUNT) return -1;
+    return t2o::op_num_params(op_id, curve_steps);
+}
+
+size_t t2o_workspace_bytes(int B, int H, int W, int param_stride) {
+    if (B < 1 || H < 1 || W < 1) return 0;
+    return t2o::chain_workspace_bytes(B, H, W, param_stride);
+}
+
+size_t t2o_score_workspace_bytes(int S, int C, int H, int W) {
+    if (H < 1 || W < 1) return 0;
+    return t2o::score_workspace_bytes(S, C, H, W);
+}
+
+int t2o_chain_forward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
+                      const float *params, int param_stride, const float *target, float *out, float *l1_sum,
+                      int B, int H, int W, int curve_steps, int flags, void *workspace, size_t workspace_bytes,
+                      t2o_stream_t stream) {
+    return t2o::chain_forward(n_ops, op_ids, param_off, img, mask, mask_ch, params, param_stride, target, out, l1_sum,
+                              B, H, W, curve_steps, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_chain_backward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
+                       const float *params, int param_stride, const float *grad_out, const float *target,
+                       const float *grad_l1, float *grad_params, float *grad_img, float *out, float *l1_sum,
+                       int B, int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::chain_backward(n_ops, op_ids, param_off, img, mask, mask_ch, params, param_stride, grad_out, target, grad_l1,
+                               grad_params, grad_img, out, l1_sum, B, H, W, curve_steps, workspace, workspace_bytes,
+                               (cudaStream_t)stream);
+}
+
+int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_per_image, void *workspace,
+               size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::l1_sum_launch(a, b, l1_sum, B, (long long)n_per_image, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_score_candidates(const float *states, int S, const float *targets, int T, const int32_t *state_target,
+                         const int32_t *cand_begin, const int32_t *cand_op, const float *cand_param, int C, float *l1_sum,
+                         int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, C, l1_sum, H, W,
+                                 curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// t2o_common.cuh -- launch descriptors and device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "t2o_math.cuh"
+
+namespace t2o {
+
+constexpr int NT = 256;           // threads per CTA of the chain kernels
+constexpr int NUM_SMS = 148;      // B200
+constexpr int MIN_TILE_PX = 1024; // smallest tile any launcher picks (bounds the workspace)
+constexpr int MAX_PSTRIDE = 256;  // floats per parameter row
+
+// One fused chain, uniform over the batch.
+struct ChainDesc {
+    int n;                  // number of operators
+    int L;                  // curve steps
+    int sharp;              // index of the (single) sharpness operator, or -1
+    int hist_total;         // curve-moment floats per thread (backward)
+    int op[MAX_CHAIN];
+    int poff[MAX_CHAIN];    // column of the operator's first parameter
+    int hoff[MAX_CHAIN];    // first curve-moment slot of the operator (backward)
+};
+
+// Launch geometry.  Without sharpness an image is a flat array of `ngroups` VEC-pixel groups and
+// a tile is a contiguous range of `tile_groups`; with sharpness tiles are TH x TWg groups with a halo.
+struct Geom {
+    int B, H, W;
+    int Wg;                 // W / VEC (2-D tiling only)
+    int tiles_x, tiles_y;   // 2-D tiling only
+    int ntiles;             // tiles per image (gridDim.x)
+    int TH, TWg;            // 2-D tile, in rows / groups
+    int tile_groups;        // 1-D tiling
+    long long ngroups;      // 1-D tiling: H*W / VEC
+};
+
+// ---------------------------------------------------------------- vector global access
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float *p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    else { v[0] = __ldg(p); }
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(float *p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    else if constexpr (VEC == 2) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); }
+    else { *p = v[0]; }
+}
+// shared-memory flavours (plain loads, no read-only path)
+template <int VEC>
+__device__ __forceinline__ void lds_vec(const float *p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else { v[0] = *p; }
+}
+
+// pixel-group loads: three planes (+ optional mask planes)
+template <int VEC>
+__device__ __forceinline__ void ld_px(const float *base, size_t plane, size_t off, float (&x)[3][VEC]) {
+    ld_vec<VEC>(base + off, x[0]);
+    ld_vec<VEC>(base + plane + off, x[1]);
+    ld_vec<VEC>(base + 2 * plane + off, x[2]);
+}
+template <int VEC>
+__device__ __forceinline__ void st_px(float *base, size_t plane, size_t off, const float (&x)[3][VEC]) {
+    st_vec<VEC>(base + off, x[0]);
+    st_vec<VEC>(base + plane + off, x[1]);
+    st_vec<VEC>(base + 2 * plane + off, x[2]);
+}
+template <int VEC>
+__device__ __forceinline__ void ld_mask(const float *mask_b, int mask_ch, size_t plane, size_t off, float (&m)[3][VEC]) {
+    if (mask_b == nullptr) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { m[0][v] = 1.0f; m[1][v] = 1.0f; m[2][v] = 1.0f; }
+    } else if (mask_ch == 3) {
+        ld_px<VEC>(mask_b, plane, off, m);
+    } else {
+        ld_vec<VEC>(mask_b + off, m[0]);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { m[1][v] = m[0][v]; m[2][v] = m[0][v]; }
+    }
+}
+
+// ---------------------------------------------------------------- reductions (fixed order => deterministic)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum over the CTA; result valid in every thread of warp 0.  `red` holds >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect `red` from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = 0.0f;
+    if (warp == 0) {
+        r = lane < nw ? red[lane] : 0.0f;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// "last CTA of the image finishes the reduction": returns true in every thread of exactly one
+// CTA per counter, after all CTAs' partials are visible.  The counter is left at 0 again.
+__device__ __forceinline__ bool arrive_is_last(unsigned int *counter, unsigned int total, int *flag_smem) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        const int last = (ticket == total - 1);
+        if (last) *counter = 0u;
+        *flag_smem = last;
+    }
+    __syncthreads();
+    const bool last = *flag_smem != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// Column sums of a (ntiles, ncols) partial matrix by one CTA: out[col] = sum_t part[t*ncols + col].
+// One warp per column, lanes stride the tiles, then a shuffle tree: fixed order.
+__device__ __forceinline__ void reduce_columns(const float *part, int ntiles, int ncols, float *out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int col = warp; col < ncols; col += nw) {
+        float s = 0.0f;
+#pragma unroll 4
+        for (int t = lane; t < ntiles; t += 32) s += __ldcg(part + (size_t)t * ncols + col);
+        s = warp_sum(s);
+        if (lane == 0) out[col] = s;
+    }
+}
+
+#define T2O_CUDA_OK(expr)                                   \
+    do {                                                    \
+        cudaError_t e__ = (expr);                           \
+        if (e__ != cudaSuccess) { t2o::set_cuda_error(e__); return T2O_ERR_CUDA; } \
+    } while (0)
+
+void set_cuda_error(cudaError_t e);
+
+}  // namespace t2o

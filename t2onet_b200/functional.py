@@ -1,0 +1,280 @@
+"""Tensor-level API over the C-ABI: fused operator chains with autograd, L1, candidate scoring.
+
+Mirrors the call pattern of the reference (file:line in /root/reference):
+  chain(...)           K x Executor.execute(img, op, mask, specified_param=p)   executors/executor.py:33-55
+  chain_l1(...)        ... followed by the L1 to a target                        utils/beam_search.py:170-173,
+                                                                                 experiments/t2onet/train_seq2seqL1.py:85
+  l1_sum / get_dist    (x1 - x2).norm(1) / numel                                 utils/beam_search.py:170-173
+  score_candidates     the evaluations inside get_param_naive / beam_search      utils/beam_search.py:77-87,229-237
+All of them run the hand-written sm_100a kernels; there is no eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+OP_IDENTITY, OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_INPAINT = -1, 0, 1, 2, 3, 4
+OP_TONE, OP_SHARPNESS, OP_WHITE, OP_EXPOSURE, OP_WHITEBALANCE = 5, 6, 7, 8, 9
+CURVE_STEPS = 8
+
+
+def num_params(op_id, curve_steps=CURVE_STEPS):
+    if op_id == OP_COLOR:
+        return 3 * curve_steps
+    if op_id == OP_TONE:
+        return curve_steps
+    if op_id == OP_WHITEBALANCE:
+        return 3
+    if op_id == OP_IDENTITY:
+        return 0
+    return 1
+
+
+def _prep_img(t, name):
+    if t is None:
+        return None
+    _lib.require_cuda(t)
+    if t.dim() != 4 or t.shape[1] != 3:
+        raise _lib.T2OError('%s must be (B, 3, H, W), got %s' % (name, tuple(t.shape)))
+    return t.contiguous()
+
+
+def _prep_mask(mask, img):
+    if mask is None:
+        return None, 0
+    _lib.require_cuda(mask)
+    if mask.dim() != 4 or mask.shape[1] not in (1, 3) or mask.shape[0] != img.shape[0] or mask.shape[2:] != img.shape[2:]:
+        raise _lib.T2OError('mask must be (B, 1|3, H, W) matching the image, got %s' % (tuple(mask.shape),))
+    return mask.contiguous(), mask.shape[1]
+
+
+def pack_params(op_ids, params, B, device, curve_steps=CURVE_STEPS):
+    """List of per-op (B, n_k) tensors -> one (B, sum n_k) row-major tensor + column offsets."""
+    offs, cols, off = [], [], 0
+    for op, p in zip(op_ids, params):
+        n = num_params(op, curve_steps)
+        offs.append(off)
+        if n == 0:
+            continue
+        if p.dim() != 2 or p.shape[0] != B or p.shape[1] < n:
+            raise _lib.T2OError('operator %d needs a (B=%d, >=%d) parameter tensor, got %s' % (op, B, n, tuple(p.shape)))
+        cols.append(p[:, :n])
+        off += n
+    if off == 0:
+        return torch.zeros(B, 1, device=device), offs, 1
+    packed = torch.cat(cols, dim=1).contiguous().float()
+    return packed, offs, off
+
+
+def split_segments(op_ids):
+    """Launch segments: at most MAX_CHAIN operators and at most one sharpness operator each."""
+    segs, cur, has_sharp = [], [], False
+    for i, op in enumerate(op_ids):
+        if len(cur) == _lib.MAX_CHAIN or (op == OP_SHARPNESS and has_sharp):
+            segs.append(cur)
+            cur, has_sharp = [], False
+        cur.append(i)
+        has_sharp = has_sharp or op == OP_SHARPNESS
+    if cur:
+        segs.append(cur)
+    return segs
+
+
+def _forward_raw(op_ids, offs, img, mask, mask_ch, packed, pstride, target, want_out, want_l1, curve_steps, flags=0):
+    B, _, H, W = img.shape
+    lib = _lib.lib()
+    out = torch.empty_like(img) if want_out else None
+    l1 = torch.empty(B, device=img.device, dtype=torch.float32) if want_l1 else None
+    nbytes = lib.t2o_workspace_bytes(B, H, W, pstride)
+    ws = _lib.workspace(img.device, nbytes)
+    st = lib.t2o_chain_forward(len(op_ids), _lib.int_array(op_ids), _lib.int_array(offs), _lib.ptr(img), _lib.ptr(mask),
+                               mask_ch, _lib.ptr(packed), pstride, _lib.ptr(target), _lib.ptr(out), _lib.ptr(l1),
+                               B, H, W, curve_steps, flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(img.device))
+    _lib.check(st)
+    return out, l1
+
+
+def _backward_raw(op_ids, offs, img, mask, mask_ch, packed, pstride, grad_out, target, grad_l1, want_gimg,
+                  want_out, want_l1, curve_steps):
+    B, _, H, W = img.shape
+    lib = _lib.lib()
+    gp = torch.empty(B, pstride, device=img.device, dtype=torch.float32)
+    gi = torch.empty_like(img) if want_gimg else None
+    out = torch.empty_like(img) if want_out else None
+    l1 = torch.empty(B, device=img.device, dtype=torch.float32) if want_l1 else None
+    nbytes = lib.t2o_workspace_bytes(B, H, W, pstride)
+    ws = _lib.workspace(img.device, nbytes)
+    st = lib.t2o_chain_backward(len(op_ids), _lib.int_array(op_ids), _lib.int_array(offs), _lib.ptr(img), _lib.ptr(mask),
+                                mask_ch, _lib.ptr(packed), pstride, _lib.ptr(grad_out), _lib.ptr(target),
+                                _lib.ptr(grad_l1), _lib.ptr(gp), _lib.ptr(gi), _lib.ptr(out), _lib.ptr(l1),
+                                B, H, W, curve_steps, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(img.device))
+    _lib.check(st)
+    return gp, gi, out, l1
+
+
+class _ChainFn(torch.autograd.Function):
+    """One launch segment: out = chain(img; params).  Backward recomputes the chain in-kernel."""
+
+    @staticmethod
+    def forward(ctx, img, packed, mask, op_ids, offs, curve_steps):
+        mask_c, mask_ch = _prep_mask(mask, img)
+        out, _ = _forward_raw(op_ids, offs, img, mask_c, mask_ch, packed, packed.shape[1], None, True, False, curve_steps)
+        ctx.save_for_backward(img, packed, mask_c if mask_c is not None else torch.empty(0, device=img.device))
+        ctx.meta = (tuple(op_ids), tuple(offs), mask_ch, curve_steps)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, packed, mask_c = ctx.saved_tensors
+        op_ids, offs, mask_ch, curve_steps = ctx.meta
+        mask_c = mask_c if mask_ch else None
+        need_img = ctx.needs_input_grad[0]
+        gp, gi, _, _ = _backward_raw(op_ids, offs, img, mask_c, mask_ch, packed, packed.shape[1], grad_out.contiguous(),
+                                     None, None, need_img, False, False, curve_steps)
+        return gi, (gp if ctx.needs_input_grad[1] else None), None, None, None, None
+
+
+class _ChainL1Fn(torch.autograd.Function):
+    """One launch segment ending in the fused L1: l1_sum[b] = sum |chain(img)[b] - target[b]|."""
+
+    @staticmethod
+    def forward(ctx, img, packed, target, mask, op_ids, offs, curve_steps):
+        mask_c, mask_ch = _prep_mask(mask, img)
+        _, l1 = _forward_raw(op_ids, offs, img, mask_c, mask_ch, packed, packed.shape[1], target, False, True, curve_steps)
+        ctx.save_for_backward(img, packed, target, mask_c if mask_c is not None else torch.empty(0, device=img.device))
+        ctx.meta = (tuple(op_ids), tuple(offs), mask_ch, curve_steps)
+        return l1
+
+    @staticmethod
+    def backward(ctx, grad_l1):
+        img, packed, target, mask_c = ctx.saved_tensors
+        op_ids, offs, mask_ch, curve_steps = ctx.meta
+        mask_c = mask_c if mask_ch else None
+        need_img = ctx.needs_input_grad[0]
+        gp, gi, _, _ = _backward_raw(op_ids, offs, img, mask_c, mask_ch, packed, packed.shape[1], None, target,
+                                     grad_l1.contiguous().float(), need_img, False, False, curve_steps)
+        return gi, (gp if ctx.needs_input_grad[1] else None), None, None, None, None, None
+
+
+def _seg_inputs(op_ids, params, seg, B, device, curve_steps):
+    ops = [op_ids[i] for i in seg]
+    packed, offs, _ = pack_params(ops, [params[i] for i in seg], B, device, curve_steps)
+    return ops, packed, offs
+
+
+def chain(img, op_ids, params, mask=None, curve_steps=CURVE_STEPS):
+    """Apply operators op_ids[k] with parameters params[k] ((B, n_k) tensors) in sequence.
+    Differentiable w.r.t. img and params.  Identity steps (op id < 0) pass the image through."""
+    img = _prep_img(img, 'img')
+    op_ids = [int(o) for o in op_ids]
+    if all(o < 0 for o in op_ids):
+        return img
+    keep = [i for i, o in enumerate(op_ids) if o >= 0]
+    op_ids, params = [op_ids[i] for i in keep], [params[i] for i in keep]
+    B = img.shape[0]
+    for seg in split_segments(op_ids):
+        ops, packed, offs = _seg_inputs(op_ids, params, seg, B, img.device, curve_steps)
+        img = _ChainFn.apply(img, packed, mask, ops, offs, curve_steps)
+    return img
+
+
+def chain_l1(img, op_ids, params, target, mask=None, curve_steps=CURVE_STEPS):
+    """Per-image sum |chain(img) - target| (B,), without materialising the edited image.
+    Differentiable w.r.t. img and params."""
+    img, target = _prep_img(img, 'img'), _prep_img(target, 'target')
+    op_ids = [int(o) for o in op_ids]
+    keep = [i for i, o in enumerate(op_ids) if o >= 0]
+    op_ids, params = [op_ids[i] for i in keep], [params[i] for i in keep]
+    if not op_ids:
+        return l1_sum(img, target)
+    B = img.shape[0]
+    segs = split_segments(op_ids)
+    for seg in segs[:-1]:
+        ops, packed, offs = _seg_inputs(op_ids, params, seg, B, img.device, curve_steps)
+        img = _ChainFn.apply(img, packed, mask, ops, offs, curve_steps)
+    ops, packed, offs = _seg_inputs(op_ids, params, segs[-1], B, img.device, curve_steps)
+    return _ChainL1Fn.apply(img, packed, target, mask, ops, offs, curve_steps)
+
+
+def chain_forward_backward(img, op_ids, params, target, mask=None, want_out=True, want_grad_img=False,
+                           loss_scale=None, curve_steps=CURVE_STEPS):
+    """ONE kernel launch for a whole training-style step on a single segment: edited image, per-image L1
+    sums to `target`, and the gradients of  loss = sum_b loss_scale[b] * l1_sum[b]  w.r.t. every
+    operator parameter (and optionally the input image).  loss_scale defaults to 1/numel (the mean L1 of
+    experiments/t2onet/train_seq2seqL1.py:85).  Returns (out, l1_sum, [grad_param_k], grad_img)."""
+    img, target = _prep_img(img, 'img'), _prep_img(target, 'target')
+    op_ids = [int(o) for o in op_ids]
+    if len(split_segments(op_ids)) != 1 or any(o < 0 for o in op_ids):
+        raise _lib.T2OError('chain_forward_backward takes one launch segment (<= 8 ops, <= 1 sharpness, no identity)')
+    B = img.shape[0]
+    packed, offs, pstride = pack_params(op_ids, params, B, img.device, curve_steps)
+    mask_c, mask_ch = _prep_mask(mask, img)
+    if loss_scale is None:
+        loss_scale = torch.full((B,), 1.0 / img.numel(), device=img.device, dtype=torch.float32)
+    gp, gi, out, l1 = _backward_raw(op_ids, offs, img, mask_c, mask_ch, packed, pstride, None, target,
+                                    loss_scale.contiguous().float(), want_grad_img, want_out, True, curve_steps)
+    grads = [gp[:, o:o + num_params(op, curve_steps)] for op, o in zip(op_ids, offs)]
+    return out, l1, grads, gi
+
+
+def process_raw(img, op_id, param, curve_steps=CURVE_STEPS):
+    """Operator.process(img, param) itself (no mask blend, no clamp): models/operators.py:128."""
+    img = _prep_img(img, 'img')
+    packed, offs, pstride = pack_params([op_id], [param], img.shape[0], img.device, curve_steps)
+    out, _ = _forward_raw([op_id], offs, img, None, 0, packed, pstride, None, True, False, curve_steps,
+                          flags=_lib.FLAG_RAW_PROCESS)
+    return out
+
+
+def l1_sum(a, b):
+    """Per-image sum |a - b| -> (B,)."""
+    _lib.require_cuda(a, b)
+    if a.shape != b.shape:
+        raise _lib.T2OError('l1_sum: shape mismatch %s vs %s' % (tuple(a.shape), tuple(b.shape)))
+    a, b = a.contiguous(), b.contiguous()
+    B = a.shape[0]
+    n = a.numel() // B
+    lib = _lib.lib()
+    out = torch.empty(B, device=a.device, dtype=torch.float32)
+    ws = _lib.workspace(a.device, 1 << 20)
+    st = lib.t2o_l1_sum(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), B, n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device))
+    _lib.check(st)
+    return out
+
+
+def score_candidates(states, targets, cand_state, cand_op, cand_param, state_target=None, curve_steps=CURVE_STEPS):
+    """Score C single-operator candidates: l1_sum[c] = sum |clamp(op_c(states[cand_state[c]]; param_c)) - target|.
+
+    states (S,3,H,W), targets (T,3,H,W) on the GPU; cand_state / cand_op: int sequences or tensors (C,),
+    cand_state ascending; cand_param (C, <=24) float.  state_target (S,) picks each state's target
+    (default s % T).  Returns a (C,) float32 CUDA tensor in candidate order."""
+    states, targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
+    dev = states.device
+    S, _, H, W = states.shape
+    T = targets.shape[0]
+    cs = torch.as_tensor(cand_state, dtype=torch.int64).cpu()
+    C = int(cs.numel())
+    if C == 0:
+        return torch.empty(0, device=dev, dtype=torch.float32)
+    if bool((cs[1:] < cs[:-1]).any()) or int(cs.min()) < 0 or int(cs.max()) >= S:
+        raise _lib.T2OError('cand_state must be ascending and within [0, S)')
+    begin = torch.zeros(S + 1, dtype=torch.int64)
+    begin[1:] = torch.cumsum(torch.bincount(cs, minlength=S), 0)
+    begin = begin.to(torch.int32).to(dev)
+    ops = torch.as_tensor(cand_op, dtype=torch.int32).to(dev).contiguous()
+    prm = torch.as_tensor(cand_param, dtype=torch.float32)
+    if prm.dim() != 2 or prm.shape[0] != C or prm.shape[1] > _lib.MAX_OP_PARAMS:
+        raise _lib.T2OError('cand_param must be (C, <=24)')
+    if prm.shape[1] < _lib.MAX_OP_PARAMS:
+        prm = torch.cat([prm, prm.new_zeros(C, _lib.MAX_OP_PARAMS - prm.shape[1])], 1)
+    prm = prm.to(dev).contiguous()
+    st_t = None if state_target is None else torch.as_tensor(state_target, dtype=torch.int32).to(dev).contiguous()
+    lib = _lib.lib()
+    out = torch.empty(C, device=dev, dtype=torch.float32)
+    ws = _lib.workspace(dev, lib.t2o_score_workspace_bytes(S, C, H, W))
+    st = lib.t2o_score_candidates(_lib.ptr(states), S, _lib.ptr(targets), T, _lib.ptr(st_t), _lib.ptr(begin),
+                                  _lib.ptr(ops), _lib.ptr(prm), C, _lib.ptr(out), H, W, curve_steps,
+                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(st)
+    return out

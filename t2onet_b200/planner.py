@@ -1,0 +1,249 @@
+"""Drop-in operation planner: utils/beam_search.py of the reference (and its fixed-order /
+eps-greedy variants) with the same function names, signatures and return structure, running on the
+candidate-scoring kernel.
+
+What changes underneath: the reference fits the parameters of every
+(beam state, operator) pair one after the other, each Nelder-Mead evaluation being an
+`executor.execute` + `get_dist` + `.item()` round trip (utils/beam_search.py:77-87).  Here all fits
+of a beam step advance in lock-step (t2onet_b200/nelder_mead.py) and every round scores the pending
+vertex of every fit with ONE `t2o_score_candidates` launch over the TMA-staged state tiles.  The
+selection logic (utils/beam_search.py:239-259) is unchanged.
+
+Only the 'L1' distance is implemented: the discriminator branches of the reference call undefined
+names (utils/beam_search.py:42,55) and are dead code.
+"""
+import random
+
+import numpy as np
+import torch
+
+from . import functional as TF
+from .nelder_mead import nelder_mead, run_lockstep
+
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+NM_INIT_ZERO, NM_INIT_ONE = (0, 1, 2, 6), (3, 5)
+
+
+def get_dist(x1, x2, dist_type='L1'):
+    """utils/beam_search.py:170-180: (x1 - x2).norm(1) / x1.numel() as a 0-dim tensor."""
+    if dist_type != 'L1':
+        assert False, '{} is invalid distance'.format(dist_type)
+    if x1.requires_grad or x2.requires_grad:
+        return _L1Dist.apply(x1, x2)
+    return TF.l1_sum(x1, x2).sum() / x1.numel()
+
+
+class _L1Dist(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2):
+        ctx.save_for_backward(x1, x2)
+        return TF.l1_sum(x1, x2).sum() / x1.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2 = ctx.saved_tensors
+        s = torch.sign(x1 - x2) * (g / x1.numel())
+        return s, -s
+
+
+def execute(I, operation, param, executor):
+    """utils/beam_search.py:165-167"""
+    img, _ = executor.execute(I, operation, None, features=None, specified_param=param, has_noise=False)
+    return img
+
+
+def _param0(operation, executor):
+    """utils/beam_search.py:149-155"""
+    n = executor.get_param_num(operation)
+    if operation in NM_INIT_ZERO:
+        return np.zeros(n)
+    if operation in NM_INIT_ONE:
+        return np.ones(n)
+    assert False, 'the operation is not global operation'
+
+
+def fit_params_nelder_mead(states, targets, problems, executor, state_target=None, counter=None):
+    """Fit many (state index, operator) problems at once.
+
+    states (S,3,H,W) / targets (T,3,H,W) CUDA tensors; problems: list of (state_idx, operation).
+    Returns a list of NMResult in problem order (x is float64, as scipy returns it)."""
+    numel = float(states[0].numel())
+    L = getattr(executor.opt, 'curve_steps', 8)
+    gens = {i: nelder_mead(_param0(op, executor)) for i, (s, op) in enumerate(problems)}
+    order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))   # candidates sorted by state
+    rank = {k: r for r, k in enumerate(order)}
+
+    def score(keys, points):
+        keys_sorted = sorted(keys, key=lambda k: rank[k])
+        pts = dict(zip(keys, points))
+        C = len(keys_sorted)
+        prm = np.zeros((C, 24), dtype=np.float32)
+        for r, k in enumerate(keys_sorted):
+            p = pts[k]
+            prm[r, :len(p)] = p                     # float64 -> float32, as torch.tensor([param], dtype=torch.float)
+        l1 = TF.score_candidates(states, targets, [problems[k][0] for k in keys_sorted],
+                                 [problems[k][1] for k in keys_sorted], torch.from_numpy(prm),
+                                 state_target=state_target, curve_steps=L)
+        vals = (l1 / numel).tolist()                # fp32 division, then .item() -> python float
+        if counter is not None:
+            counter[0] += C
+        by_key = dict(zip(keys_sorted, vals))
+        return [by_key[k] for k in keys]
+
+    res = run_lockstep(gens, score)
+    return [res[i] for i in range(len(problems))]
+
+
+def get_param_naive(img, out, txt, mask, param0, executor, discriminator, op_ind, dist_type, optimizer):
+    """utils/beam_search.py:65-91 (L1 only): Nelder-Mead from param0 -> (param (1,n) tensor, success)."""
+    assert dist_type == 'L1'
+    L = getattr(executor.opt, 'curve_steps', 8)
+    numel = float(img.numel())
+    gen = nelder_mead(np.asarray(param0, dtype=np.float64))
+
+    def score(keys, points):
+        prm = np.zeros((1, 24), dtype=np.float32)
+        prm[0, :len(points[0])] = points[0]
+        l1 = TF.score_candidates(img, out, [0], [op_ind], torch.from_numpy(prm), curve_steps=L)
+        return (l1 / numel).tolist()
+    res = run_lockstep({0: gen}, score)[0]
+    return torch.tensor(np.array([list(res.x)])).to(img.device), res.success
+
+
+def gd_minimize(func, param0, method='adam'):
+    """utils/beam_search.py:94-128"""
+    num_iters, tol = 1000, 1e-5
+    param0.requires_grad_()
+    success_flag = False
+    if method == 'lbfgs':
+        success_flag = True
+        optimizer = torch.optim.LBFGS([param0], lr=1)
+
+        def closure():
+            optimizer.zero_grad()
+            loss = func(param0)
+            loss.backward()
+            return loss
+        optimizer.step(closure)
+    elif method == 'adam':
+        optimizer = torch.optim.Adam([param0], lr=1e-2)
+        loss_prev = 10000
+        for _ in range(num_iters):
+            optimizer.zero_grad()
+            loss = func(param0)
+            cur_loss = loss.item()
+            if (loss_prev - cur_loss) < tol:
+                success_flag = True
+                break
+            loss_prev = cur_loss
+            loss.backward()
+            optimizer.step()
+    return param0.detach(), success_flag
+
+
+def get_param_gd(img, out, txt, mask, param0, executor, discriminator, op_ind, dist_type, optimizer):
+    """utils/beam_search.py:131-145: the fused chain+L1 kernel forward, the recompute kernel backward."""
+    assert dist_type == 'L1'
+    L = getattr(executor.opt, 'curve_steps', 8)
+
+    def func(param):
+        return TF.chain_l1(img, [op_ind], [param], out, None, L).sum() / img.numel()
+    return gd_minimize(func, param0, method=optimizer)
+
+
+def get_param(I0, I1, txt, operation, executor, discriminator, dist_type, optimizer):
+    """utils/beam_search.py:148-162"""
+    param0 = torch.from_numpy(_param0(operation, executor)).float()
+    if optimizer == 'Nelder-Mead':
+        return get_param_naive(I0, I1, txt, None, param0.numpy(), executor, discriminator, operation, dist_type, optimizer)
+    bs = I0.shape[0]
+    param0 = param0.view(1, -1).repeat(bs, 1).to(I0.device)
+    return get_param_gd(I0, I1, txt, None, param0, executor, discriminator, operation, dist_type, optimizer)
+
+
+def _score_outputs(I_list, ops, params, I_gt, executor):
+    """I_out and dist for every fitted candidate of a step (utils/beam_search.py:230,237)."""
+    outs, dists = [], []
+    numel = float(I_gt.numel())
+    L = getattr(executor.opt, 'curve_steps', 8)
+    for I, op, p in zip(I_list, ops, params):
+        p32 = p.to(I.device).float()
+        packed, offs, pstride = TF.pack_params([op], [p32], I.shape[0], I.device, L)
+        out, l1 = TF._forward_raw([op], offs, I, None, 0, packed, pstride, I_gt, True, True, L)
+        outs.append(out)
+        dists.append(l1.sum() / numel)
+    vals = torch.stack(dists).tolist() if dists else []
+    return outs, vals
+
+
+def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,
+                dist_type, optimizer, replace=False, _variant='default', _eps=0.05, counter=None):
+    """utils/beam_search.py:196-264 -- same arguments and return value:
+    actions: list(beam) of list(step) of (op_name, param list, dist); Is: same nesting of CPU images."""
+    assert dist_type == 'L1', 'only the L1 distance is implemented'
+    I_0 = I_0.to(device) if not I_0.is_cuda else I_0
+    I_gt = I_gt.to(I_0.device)
+    min_dist = float('inf')
+    sequences = [[[], float('inf')]]
+    I_buff = [I_0]
+    for i in range(max_step):
+        all_candidates, I_tmp_list, tmp_min_dists = [], [], []
+        no_update_flag, finish_flag = True, False
+        # -- every (beam state, operator) pair of this step (utils/beam_search.py:220-223)
+        problems = []
+        for j in range(len(I_buff)):
+            step_ops = [operations[i]] if _variant == 'fixed_order' else operations
+            for operation in step_ops:
+                if not replace and operation in [operation_names.index(v[0]) for v in sequences[j][0]]:
+                    continue
+                problems.append((j, operation))
+        # -- fit all of them (utils/beam_search.py:229)
+        if optimizer == 'Nelder-Mead' and problems:
+            states = torch.cat(I_buff, 0).contiguous()
+            fits = fit_params_nelder_mead(states, I_gt, problems, executor, state_target=[0] * len(I_buff),
+                                          counter=counter)
+            params = [torch.tensor(np.array([list(r.x)])) for r in fits]
+        else:
+            params = [get_param(I_buff[j], I_gt, txt, op, executor, None, dist_type, optimizer)[0] for j, op in problems]
+        # -- apply + score (utils/beam_search.py:230-237), then the reference's bookkeeping (:239-246)
+        outs, dists = _score_outputs([I_buff[j] for j, _ in problems], [op for _, op in problems], params, I_gt, executor)
+        for (j, operation), param, I_out, dist in zip(problems, params, outs, dists):
+            if _variant == 'eps_greedy' or dist < min_dist:
+                tmp_min_dists.append(dist)
+                candidate = [sequences[j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out.cpu())], dist]
+                all_candidates.append(candidate)
+                I_tmp_list.append(I_out)
+                if _variant != 'eps_greedy':
+                    no_update_flag = False
+                if dist < err:
+                    finish_flag = True
+        min_dist = min(tmp_min_dists) if len(tmp_min_dists) > 0 else min_dist
+        if len(all_candidates) < beam_size:
+            all_candidates += sequences
+            I_tmp_list += I_buff
+        dists_arr = np.array([v[1] for v in all_candidates])
+        order = np.argsort(dists_arr)
+        if _variant == 'eps_greedy' and random.random() < _eps:
+            sequences = random.choices(all_candidates, k=beam_size)
+        else:
+            sequences = [all_candidates[idx] for idx in order][:beam_size]
+        I_buff = [I_tmp_list[idx] for idx in order][:beam_size]
+        if no_update_flag or finish_flag:
+            break
+    actions = [[act[:-1] for act in seq[0]] for seq in sequences]
+    Is = [[act[-1] for act in seq[0]] for seq in sequences]
+    return actions, Is
+
+
+def beam_search_fixed_order(I_0, I_gt, txt, executor, beam_size, operations, operation_names, max_step, err, dist_type,
+                            optimizer, replace=False):
+    """utils/beam_search_fixed_order.py:225-293 (no discriminator argument; one operator per step)."""
+    return beam_search(I_0, I_gt, txt, executor, None, beam_size, operations, operation_names, max_step, err, dist_type,
+                       optimizer, replace, _variant='fixed_order')
+
+
+def beam_search_eps_greedy(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,
+                           dist_type, optimizer, eps=0.05, replace=False):
+    """utils/beam_search_eps_greedy.py:238-309"""
+    return beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,
+                       dist_type, optimizer, replace, _variant='eps_greedy', _eps=eps)

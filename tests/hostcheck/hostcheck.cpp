@@ -1,0 +1,138 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the product's per-pixel arithmetic (t2onet_b200/csrc/t2o_math.cuh, the code the CUDA
+// kernels inline) on the CPU over whole images, so that the closed forms and hand-derived
+// gradients can be checked against the oracle in the GPU-less authoring container.  It stores
+// every intermediate image (no tiling, no recompute) and is never loaded by the product.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../t2onet_b200/csrc/t2o_math.cuh"
+
+using namespace t2o;
+
+extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float *img, const float *mask, int mask_ch,
+                        const float *params, int pstride, const float *grad_out, const float *target,
+                        const float *grad_l1, float *out, float *l1_sum, float *grad_params, float *grad_img,
+                        int B, int H, int W, int L) {
+    const size_t plane = (size_t)H * W;
+    const bool has_mask = mask != nullptr;
+    std::vector<float> tabs(MAX_CHAIN * TAB);
+    std::vector<std::vector<float>> xs(n_ops + 1, std::vector<float>(3 * plane));
+    std::vector<float> g(3 * plane), gn(3 * plane), gyv(3 * plane);
+    for (int b = 0; b < B; ++b) {
+        const float *ib = img + (size_t)b * 3 * plane;
+        const float *mb = has_mask ? mask + (size_t)b * mask_ch * plane : nullptr;
+        auto M = [&](int c, size_t i) { return has_mask ? mb[(mask_ch == 3 ? c : 0) * plane + i] : 1.0f; };
+        for (int k = 0; k < n_ops; ++k) build_table(ops[k], params + (size_t)b * pstride + poff[k], L, &tabs[k * TAB]);
+        std::memcpy(xs[0].data(), ib, 3 * plane * sizeof(float));
+        // forward
+        for (int k = 0; k < n_ops; ++k) {
+            const float *x = xs[k].data();
+            float *y = xs[k + 1].data();
+            const float *tab = &tabs[k * TAB];
+            if (ops[k] == OP_SHARPNESS) {
+                for (int c = 0; c < 3; ++c)
+                    for (int yy = 0; yy < H; ++yy)
+                        for (int xx = 0; xx < W; ++xx) {
+                            const size_t i = (size_t)yy * W + xx;
+                            const float *pc = x + c * plane;
+                            const float ctr = pc[i];
+                            const float up = yy > 0 ? pc[i - W] : 0.f, dn = yy < H - 1 ? pc[i + W] : 0.f;
+                            const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
+                            const float v = fmaf(tab[0], laplace(ctr, up, dn, lf, rt), ctr);
+                            y[c * plane + i] = sat01(blend(v, ctr, M(c, i), has_mask));
+                        }
+            } else {
+                for (size_t i = 0; i < plane; ++i) {
+                    float r = x[i], gg = x[plane + i], bb = x[2 * plane + i];
+                    op_apply(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i), has_mask);
+                    y[i] = r; y[plane + i] = gg; y[2 * plane + i] = bb;
+                }
+            }
+        }
+        const float *fin = xs[n_ops].data();
+        if (out) std::memcpy(out + (size_t)b * 3 * plane, fin, 3 * plane * sizeof(float));
+        if (l1_sum && target) {
+            double s = 0;
+            for (size_t i = 0; i < 3 * plane; ++i) s += fabsf(fin[i] - target[(size_t)b * 3 * plane + i]);
+            l1_sum[b] = (float)s;
+        }
+        if (!grad_params && !grad_img) continue;
+        // upstream gradient
+        for (size_t i = 0; i < 3 * plane; ++i) {
+            if (grad_out) g[i] = grad_out[(size_t)b * 3 * plane + i];
+            else {
+                const float d = fin[i] - target[(size_t)b * 3 * plane + i];
+                g[i] = grad_l1[b] * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+            }
+        }
+        if (grad_params) std::memset(grad_params + (size_t)b * pstride, 0, pstride * sizeof(float));
+        for (int k = n_ops - 1; k >= 0; --k) {
+            const float *x = xs[k].data();
+            const float *tab = &tabs[k * TAB];
+            float acc[3] = {0, 0, 0};
+            std::vector<double> accd(3, 0.0);
+            float hist[3 * HIST];
+            std::vector<double> histd(3 * HIST, 0.0);
+            if (ops[k] == OP_SHARPNESS) {
+                const float p = tab[0];
+                double accp = 0;
+                for (int c = 0; c < 3; ++c)
+                    for (int yy = 0; yy < H; ++yy)
+                        for (int xx = 0; xx < W; ++xx) {
+                            const size_t i = (size_t)yy * W + xx;
+                            const float *pc = x + c * plane;
+                            const float ctr = pc[i];
+                            const float up = yy > 0 ? pc[i - W] : 0.f, dn = yy < H - 1 ? pc[i + W] : 0.f;
+                            const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
+                            const float lap = laplace(ctr, up, dn, lf, rt);
+                            float gy, gd;
+                            blend_bwd(fmaf(p, lap, ctr), ctr, M(c, i), has_mask, g[c * plane + i], gy, gd);
+                            gyv[c * plane + i] = gy;
+                            gn[c * plane + i] = gd;
+                            accp += (double)gy * lap;
+                        }
+                for (int c = 0; c < 3; ++c)
+                    for (int yy = 0; yy < H; ++yy)
+                        for (int xx = 0; xx < W; ++xx) {
+                            const size_t i = (size_t)yy * W + xx;
+                            const float *pg = gyv.data() + c * plane;
+                            const float up = yy > 0 ? pg[i - W] : 0.f, dn = yy < H - 1 ? pg[i + W] : 0.f;
+                            const float lf = xx > 0 ? pg[i - 1] : 0.f, rt = xx < W - 1 ? pg[i + 1] : 0.f;
+                            gn[c * plane + i] += pg[i] + p * laplace(pg[i], up, dn, lf, rt);
+                        }
+                if (grad_params) grad_params[(size_t)b * pstride + poff[k]] = (float)accp;
+                g.swap(gn);
+                continue;
+            }
+            for (size_t i = 0; i < plane; ++i) {
+                float gr = g[i], gg = g[plane + i], gb = g[2 * plane + i];
+                for (int t = 0; t < 3 * HIST; ++t) hist[t] = 0.f;
+                acc[0] = acc[1] = acc[2] = 0.f;
+                Hist h{hist, 1};
+                pointwise_bwd(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], M(0, i), M(1, i), M(2, i), has_mask,
+                              gr, gg, gb, acc, h, true);
+                g[i] = gr; g[plane + i] = gg; g[2 * plane + i] = gb;
+                for (int t = 0; t < 3; ++t) accd[t] += acc[t];
+                for (int t = 0; t < 3 * HIST; ++t) histd[t] += hist[t];
+            }
+            if (grad_params) {
+                float *gp = grad_params + (size_t)b * pstride + poff[k];
+                if (ops[k] == OP_TONE || ops[k] == OP_COLOR) {
+                    const int nc = ops[k] == OP_TONE ? 1 : 3;
+                    for (int c = 0; c < nc; ++c) {
+                        float mom[HIST];
+                        for (int t = 0; t < HIST; ++t) mom[t] = (float)histd[c * HIST + t];
+                        curve_param_grad(tab + c * CT, L, mom, gp + c * L);
+                    }
+                } else {
+                    const int n = op_num_params(ops[k], L);
+                    for (int t = 0; t < n && t < 3; ++t) gp[t] = (float)accd[t];
+                }
+            }
+        }
+        if (grad_img) std::memcpy(grad_img + (size_t)b * 3 * plane, g.data(), 3 * plane * sizeof(float));
+    }
+    return 0;
+}

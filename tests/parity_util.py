@@ -1,0 +1,52 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import numpy as np
+import torch
+
+from oracle import ops as O
+
+TOL_PIX = 1e-5      # north star: max-abs on edited pixels and on the L1 (fp32)
+TOL_GRAD = 1e-4     # north star: relative on parameter gradients
+
+
+def sample_params(op, B, g, wide=False):
+    n = O.num_params(op)
+    u = torch.rand(B, n, generator=g)
+    if op == O.OP_BRIGHTNESS:
+        return (u * 0.6 - 0.3) if not wide else (u * 4 - 2)
+    if op == O.OP_CONTRAST:
+        return (u - 0.5) if not wide else (u * 2 - 1)
+    if op == O.OP_SATURATION:
+        return (u - 0.2) if not wide else (u * 3 - 1.5)
+    if op == O.OP_COLOR:
+        return 0.9 + 0.2 * u
+    if op == O.OP_TONE:
+        return 0.5 + 1.5 * u
+    if op == O.OP_SHARPNESS:
+        return u * 1.5
+    if op == O.OP_EXPOSURE:
+        return u * 2 - 1
+    if op == O.OP_WHITEBALANCE:
+        return 0.4 + 1.4 * u
+    return u
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+def max_abs(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
+
+
+def oracle_chain_with_grads(img, ops, params, target, mask=None, wgt=None):
+    """CPU oracle: out, per-image L1 sums, and gradients of loss w.r.t. params and img, where
+    loss = (out*wgt).sum() if wgt is given else mean |out - target|."""
+    x = img.clone().requires_grad_()
+    ps = [p.clone().requires_grad_() for p in params]
+    out = O.chain(x, ops, ps, mask)
+    l1 = (out - target).abs().flatten(1).sum(1) if target is not None else None
+    loss = (out * wgt).sum() if wgt is not None else O.l1_mean(out, target)
+    loss.backward()
+    gps = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ps]
+    return out.detach(), None if l1 is None else l1.detach(), gps, x.grad

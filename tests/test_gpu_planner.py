@@ -1,0 +1,140 @@
+"""Planner and Executor-API parity on the GPU: the drop-in beam_search / get_param / Executor against
+the oracle and the transcripts recorded from the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from oracle import planner as OP
+from parity_util import TOL_GRAD, TOL_PIX, max_abs, rel_err, sample_params
+
+pytestmark = pytest.mark.gpu
+GLOBAL_OPS = [0, 1, 2, 3, 5, 6]
+
+
+@pytest.fixture(scope='module')
+def T():
+    import t2onet_b200 as T
+    return T
+
+
+@pytest.fixture(scope='module')
+def pair(golden_dir):
+    d = np.load(os.path.join(golden_dir, 'planner_pair.npz'))
+    tr = json.load(open(os.path.join(golden_dir, 'planner_transcripts.json')))
+    return torch.from_numpy(d['I0']), torch.from_numpy(d['Igt']), tr
+
+
+def test_nelder_mead_fits_match_reference(T, pair):
+    """Per-(state, operator) fits: same optimum (distance within 1e-5, scalar parameters within 1e-3) as the
+    reference's scipy run; the evaluation count may differ by a few simplex steps (fp32 L1 low bits)."""
+    I0, Igt, tr = pair
+    ex = T.Executor(T.default_options()).cuda()
+    for op in GLOBAL_OPS:
+        param, ok = T.planner.get_param(I0.cuda(), Igt.cuda(), None, op, ex, None, 'L1', 'Nelder-Mead')
+        ref = tr['nm_fits'][str(op)]
+        out = T.planner.execute(I0.cuda(), op, param.float(), ex)
+        dist = T.planner.get_dist(out, Igt.cuda(), 'L1').item()
+        assert abs(dist - ref['dist']) <= 2e-4 if op in (3, 5) else abs(dist - ref['dist']) <= 1e-5
+        if op in (0, 1, 2, 6):
+            assert abs(param[0, 0].item() - ref['param'][0]) <= 1e-3
+        assert tuple(param.shape) == (1, O.num_params(op)) and param.dtype == torch.float64
+
+
+def test_beam_search_matches_reference_transcript(T, pair):
+    I0, Igt, tr = pair
+    ex = T.Executor(T.default_options()).cuda()
+    cnt = [0]
+    actions, Is = T.planner.beam_search(I0.cuda(), Igt.cuda(), None, ex, None, 2, GLOBAL_OPS, O.ACTION_NAMES, 3, 1e-2,
+                                        'L1', 'Nelder-Mead', counter=cnt)
+    ref = tr['beam2']['actions']
+    assert [[a[0] for a in seq] for seq in actions] == [[a[0] for a in seq] for seq in ref]     # op sequences: exact
+    for seq, rseq in zip(actions, ref):
+        for a, r in zip(seq, rseq):
+            assert abs(a[2] - r[2]) <= 5e-4
+            assert isinstance(a[1], list) and len(a[1]) == len(r[1])
+    assert len(Is) == 2 and tuple(Is[0][0].shape) == (1, 3, 16, 16) and not Is[0][0].is_cuda
+    assert cnt[0] > 1000
+    actions_f, _ = T.planner.beam_search_fixed_order(I0.cuda(), Igt.cuda(), None, ex, 1, GLOBAL_OPS, O.ACTION_NAMES, 3,
+                                                     1e-2, 'L1', 'Nelder-Mead')
+    assert [[a[0] for a in seq] for seq in actions_f] == [[a[0] for a in seq] for seq in tr['fixed']['actions']]
+
+
+def test_beam_search_planted_sequence_vs_oracle(T):
+    """A planted brightness -> tone edit on a 32x32 pair: the GPU planner and the CPU oracle planner
+    (scipy Nelder-Mead on the oracle operators) must choose the same operator sequences."""
+    g = torch.Generator().manual_seed(10 + 3001)
+    I0 = torch.rand(1, 3, 32, 32, generator=g) * 0.7 + 0.15
+    with torch.no_grad():
+        Igt = O.execute(5, O.execute(0, I0, torch.tensor([[0.2]])), sample_params(5, 1, g))
+    ops = [0, 1, 5, 6]
+    ref, _ = OP.beam_search(I0, Igt, None, O.OracleExecutor(), None, 2, ops, O.ACTION_NAMES, 2, 1e-3, 'L1', 'Nelder-Mead')
+    ex = T.Executor(T.default_options()).cuda()
+    got, _ = T.planner.beam_search(I0.cuda(), Igt.cuda(), None, ex, None, 2, ops, O.ACTION_NAMES, 2, 1e-3, 'L1', 'Nelder-Mead')
+    assert [[a[0] for a in s] for s in got] == [[a[0] for a in s] for s in ref]
+    for s, r in zip(got, ref):
+        assert abs(s[-1][2] - r[-1][2]) <= 3e-4
+
+
+@pytest.mark.parametrize('optimizer', ['adam', 'lbfgs'])
+def test_gradient_planner_optimizers(T, optimizer):
+    g = torch.Generator().manual_seed(77)
+    I0 = torch.rand(1, 3, 24, 24, generator=g) * 0.8 + 0.1
+    Igt = O.execute(1, I0, torch.tensor([[0.35]]))
+    ex = T.Executor(T.default_options()).cuda()
+    p_ref, _ = OP.get_param(I0, Igt, 1, O.OracleExecutor(), optimizer)
+    p_got, _ = T.planner.get_param(I0.cuda(), Igt.cuda(), None, 1, ex, None, 'L1', optimizer)
+    assert abs(p_got.item() - p_ref.item()) <= 2e-3
+
+
+def test_executor_api_and_fc_head_gradients(T):
+    """Executor.execute with features: the FC head stays PyTorch, the operator runs in the kernel; the
+    loss and the gradients w.r.t. fc weights and the input image match the oracle graph."""
+    torch.manual_seed(10)
+    opt = T.default_options()
+    ex = T.Executor(opt).cuda()
+    assert ex.name_list == ['brightness', 'contrast', 'saturation', 'hue', 'inpaint_obj', 'tone', 'sharpness', 'color_bg']
+    assert ex.get_param_num(3) == 24 and ex.get_param_num(5) == 8 and ex.get_param_bnd(6) == (1.5, 0, 0.75)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(4, 3, 32, 32, generator=g)
+    feat = torch.randn(4, 512, generator=g) * 0.3
+    tgt = torch.rand(4, 3, 32, 32, generator=g)
+    out_id, p_id = ex.execute(img.cuda(), -1, None)
+    assert out_id.data_ptr() == img.cuda().data_ptr() or torch.equal(out_id.cpu(), img)
+    assert tuple(p_id.shape) == (4, 24) and float(p_id.abs().sum()) == 0.0
+    for op_ind in [0, 1, 2, 3, 5, 6, 7]:
+        Op = ex.ops[op_ind]
+        Op.zero_grad()
+        x = img.cuda().requires_grad_()
+        out, param = ex.execute(x, op_ind, None, features=feat.cuda())
+        assert param is Op.param and tuple(param.shape) == (4, Op.num_op_param)
+        loss = (out - tgt.cuda()).abs().mean()
+        loss.backward()
+        # oracle graph with the same head weights
+        w = {k: v.detach().cpu().clone().requires_grad_() for k, v in Op.named_parameters()}
+        xo = img.clone().requires_grad_()
+        h = torch.nn.functional.leaky_relu(feat @ w['fc1.weight'].t() + w['fc1.bias'])
+        po = O.regress(op_ind, h @ w['fc2.weight'].t() + w['fc2.bias'], opt)
+        oo = O.execute(op_ind, xo, po)
+        lo = (oo - tgt).abs().mean()
+        lo.backward()
+        assert max_abs(out.detach().cpu(), oo.detach()) <= TOL_PIX
+        assert abs(loss.item() - lo.item()) <= TOL_PIX
+        assert rel_err(x.grad.cpu(), xo.grad) <= TOL_GRAD
+        if op_ind != 7:
+            assert rel_err(Op.fc2.weight.grad.cpu(), w['fc2.weight'].grad) <= TOL_GRAD
+            assert rel_err(Op.fc1.weight.grad.cpu(), w['fc1.weight'].grad) <= TOL_GRAD
+    with pytest.raises(NotImplementedError):
+        ex.execute(img.cuda(), 4, None, specified_param=torch.zeros(4, 1).cuda())
+    # extra operator classes of models/operators.py without an Executor slot
+    for cls, op in ((T.ExposureOperator, 8), (T.ImprovedWhiteBalanceOperator, 9)):
+        o = cls(opt).cuda()
+        f = torch.randn(4, 512, generator=g)
+        out = o.execute(img.cuda(), features=f.cuda())
+        w = {k: v.detach().cpu() for k, v in o.named_parameters()}
+        h = torch.nn.functional.leaky_relu(f @ w['fc1.weight'].t() + w['fc1.bias'])
+        po = O.regress(op, h @ w['fc2.weight'].t() + w['fc2.bias'], opt)
+        assert max_abs(out.detach().cpu(), O.execute(op, img, po)) <= TOL_PIX
