@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the T2ONet hot path on B200 (contract: see DESIGN.md section 7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+
+Metric (BASELINE.json): edited Mpixel/s of the operator chain forward+backward.  One "step" = one pass of
+the fused chain  [brightness, contrast, saturation, color, tone, sharpness]  over one synthetic batch:
+edited image + per-image L1 to the target + gradients to all 36 operator parameters.
+Default workload = BASELINE config 2 (batch 64 of 3x128x128, the seq2seqL1 training shape).
+
+  value  : inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e    : the same step through the public API from pinned HOST buffers (H2D of img+target, D2H of L1+grads)
+  roofline / cpu_baseline / clocks : see DESIGN.md
+`--impl reference` times the reference's own algorithm (the CPU oracle port, torch fp32 with autograd) on the
+host cores for the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CHAIN = [0, 1, 2, 3, 5, 6]
+CHAIN_NAMES = ['brightness', 'contrast', 'saturation', 'color', 'tone', 'sharpness']
+WORKLOADS = {
+    'c1': dict(B=1, H=512, W=512, desc='C1: single 3x512x512 image, 6-op chain fwd+L1+bwd'),
+    'c2': dict(B=64, H=128, W=128, desc='C2: batch 64 of 3x128x128 (seq2seqL1 training shape), 6-op chain fwd+L1+bwd to all operator params'),
+    'c4': dict(B=16, H=2048, W=3072, desc='C4: batch 16 of 3x2048x3072, 6-op chain fwd+L1+bwd (bandwidth stress)'),
+}
+L2_BYTES = 126 * 1024 * 1024
+BYTES_PER_PX_FUSED = 36       # read img 12 + read target 12 + write out 12 (one fused fwd+bwd launch), DESIGN.md section 4
+
+
+def make_params(B, gen, device):
+    """Parameter distributions of SURVEY.md section 8(d)."""
+    u = lambda n: torch.rand(B, n, generator=gen)   # noqa: E731
+    ps = [u(1) * 0.6 - 0.3, u(1) - 0.5, u(1) - 0.2, 0.9 + 0.2 * u(24), 0.5 + 1.5 * u(8), u(1) * 1.5]
+    return [p.to(device) for p in ps]
+
+
+def make_batch(B, H, W, seed, device):
+    gen = torch.Generator().manual_seed(seed)
+    if device == 'cpu' or B * H * W <= 4 * 1024 * 1024:
+        img = torch.rand(B, 3, H, W, generator=gen).to(device)
+        tgt = torch.rand(B, 3, H, W, generator=gen).to(device)
+    else:
+        dgen = torch.Generator(device=device).manual_seed(seed)
+        img = torch.rand(B, 3, H, W, generator=dgen, device=device)
+        tgt = torch.rand(B, 3, H, W, generator=dgen, device=device)
+    return img, tgt, make_params(B, gen, device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                clocks.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(clocks)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_step(img, tgt, params):
+    from oracle import ops as O
+    ps = [p.clone().requires_grad_() for p in params]
+    out = O.chain(img, CHAIN, ps)
+    loss = (out - tgt).abs().mean()
+    loss.backward()
+    return loss.item()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, H, W = wl['B'], wl['H'], wl['W']
+    # bounded sample: shrink the batch until (steps + warmup) steps fit in ~150 s
+    img, tgt, params = make_batch(min(B, 8), min(H, 512), min(W, 512), 10 + 2000, 'cpu')
+    t0 = time.perf_counter()
+    oracle_step(img, tgt, params)
+    per_px = (time.perf_counter() - t0) / (img.shape[0] * img.shape[2] * img.shape[3])
+    budget_px = 150.0 / per_px / max(1, args.steps + args.warmup)
+    sB, sH, sW = B, H, W
+    while sB * sH * sW > budget_px and sB > 1:
+        sB = max(1, sB // 2)
+    while sB * sH * sW > budget_px and sH > 128:
+        sH //= 2
+    img, tgt, params = make_batch(sB, sH, sW, 10 + 2000, 'cpu')
+    for _ in range(args.warmup):
+        oracle_step(img, tgt, params)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(img, tgt, params)
+    dt = time.perf_counter() - t0
+    mpix = sB * sH * sW * args.steps / dt / 1e6
+    sample = '%d steps of %dx3x%dx%d (full workload is %dx3x%dx%d)' % (args.steps, sB, sH, sW, B, H, W)
+    line = {
+        'impl': 'reference', 'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': mpix, 'unit': 'Mpixel/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'chain': CHAIN_NAMES, 'batch': B, 'H': H, 'W': W},
+        'cpu_baseline': {'value': mpix, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': mpix, 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def timed_region(fn, steps, stream_sync):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream_sync()
+    start.record()
+    for i in range(steps):
+        fn(i)
+    end.record()
+    stream_sync()
+    return start.elapsed_time(end)
+
+
+def run_ours(args, wl):
+    import t2onet_b200.functional as TF
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    B, H, W = wl['B'], wl['H'], wl['W']
+    px_step = B * H * W
+    batch_bytes = 3 * px_step * 12
+    nb = max(2, min(16, (2 * L2_BYTES + batch_bytes - 1) // batch_bytes + 1)) if batch_bytes < 2 * L2_BYTES else 1
+    batches = [make_batch(B, H, W, 10 + 2000 + 17 * i + 1000 * rank, dev) for i in range(nb)]
+
+    def step(i):
+        img, tgt, params = batches[i % nb]
+        return TF.chain_forward_backward(img, CHAIN, params, tgt, want_out=True, want_grad_img=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed_region(step, args.steps, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * px_step * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API from pinned host memory
+    himg = [b[0].cpu().pin_memory() for b in batches[:2]]
+    htgt = [b[1].cpu().pin_memory() for b in batches[:2]]
+    hparams = [[p.cpu().pin_memory() for p in b[2]] for b in batches[:2]]
+    res_l1 = torch.empty(B, pin_memory=True)
+    res_gp = torch.empty(B, 36, pin_memory=True)
+
+    def e2e_step(i):
+        j = i % 2
+        img = himg[j].to(dev, non_blocking=True)
+        tgt = htgt[j].to(dev, non_blocking=True)
+        params = [p.to(dev, non_blocking=True) for p in hparams[j]]
+        _, l1, grads, _ = TF.chain_forward_backward(img, CHAIN, params, tgt, want_out=True)
+        res_l1.copy_(l1, non_blocking=True)
+        res_gp.copy_(torch.cat(grads, 1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the loss every step
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_steps = max(3, min(args.steps, 50))
+    ms_e2e = timed_region(e2e_step, e2e_steps, barrier)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e_value = world * px_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    h2d = 2 * px_step * 12 + sum(p.numel() * 4 for p in hparams[0])
+    d2h = B * 4 + B * 36 * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_hbm()
+    kernel_ms = ms / args.steps
+    achieved = BYTES_PER_PX_FUSED * px_step / (kernel_ms * 1e-3) / 1e9
+    line = {
+        'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': value, 'unit': 'Mpixel/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': kernel_ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'chain': CHAIN_NAMES, 'batch_per_gpu': B, 'H': H, 'W': W,
+                   'l2_policy': ('rotating %d distinct batches (%.0f MB) > 126 MB L2' % (nb, nb * batch_bytes / 1e6)) if nb > 1
+                   else 'one batch of %.0f MB >> 126 MB L2' % (batch_bytes / 1e6),
+                   'sharding': 'images sharded across ranks, no data-path collective'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'Mpixel/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
+        'gpu_launches': args.steps,
+        'roofline': {'bound': 'hbm', 'kernel': 'chain_bwd_kernel (fused forward + L1 + backward, one launch per step)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0},
+    }
+    if world == 1 and not args.no_extras:
+        line['cpu_baseline'] = cpu_baseline(wl)
+        line['extras'] = extras(TF, dev, wl)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl):
+    """The oracle port of the reference operators (torch CPU fp32 + autograd) on the host cores, bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, H, W = min(wl['B'], 64), min(wl['H'], 512), min(wl['W'], 512)
+    img, tgt, params = make_batch(B, H, W, 10 + 2000, 'cpu')
+    oracle_step(img, tgt, params)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 12.0 and n < 40:
+        oracle_step(img, tgt, params)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {'value': B * H * W * n / dt / 1e6, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d steps of %dx3x%dx%d, 6-op chain fwd+L1+bwd (oracle/ops.py, torch CPU fp32 autograd)' % (n, B, H, W)}
+
+
+def extras(TF, dev, wl):
+    """Secondary measurements printed with the headline line (rank 0, N=1 only)."""
+    ex = {}
+    peak, _ = measured_peak_hbm()
+
+    def bench(fn, iters, sync=torch.cuda.synchronize):
+        for _ in range(3):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync(); s.record()
+        for _ in range(iters):
+            fn()
+        e.record(); sync()
+        return s.elapsed_time(e) / iters
+
+    # ---- C4: the roofline configuration (inputs >> L2)
+    try:
+        B, H, W = 16, 2048, 3072
+        img, tgt, params = make_batch(B, H, W, 10 + 4000, dev)
+        px = B * H * W
+        t_fused = bench(lambda: TF.chain_forward_backward(img, CHAIN, params, tgt, want_out=True), 5)
+        t_fwd = bench(lambda: TF._forward_raw(CHAIN, [0, 1, 2, 3, 27, 35], img, None, 0, torch.cat(params, 1).contiguous(),
+                                              36, tgt, True, True, 8), 5)
+        t_point = bench(lambda: TF.chain_forward_backward(img, CHAIN[:5], params[:5], tgt, want_out=True), 5)
+        ex['c4'] = {
+            'workload': WORKLOADS['c4']['desc'],
+            'fused_fwd_bwd': {'ms': t_fused, 'Mpixel_per_s': px / t_fused / 1e3, 'GBps_at_36B_px': 36 * px / t_fused / 1e6,
+                              'frac_of_measured_peak': 36 * px / t_fused / 1e6 / peak},
+            'forward_l1_only': {'ms': t_fwd, 'Mpixel_per_s': px / t_fwd / 1e3, 'GBps_at_36B_px': 36 * px / t_fwd / 1e6,
+                                'frac_of_measured_peak': 36 * px / t_fwd / 1e6 / peak},
+            'fused_fwd_bwd_pointwise5': {'ms': t_point, 'Mpixel_per_s': px / t_point / 1e3,
+                                         'GBps_at_36B_px': 36 * px / t_point / 1e6},
+        }
+        del img, tgt
+        torch.cuda.empty_cache()
+    except Exception as exc:   # report, never hide
+        ex['c4'] = {'error': repr(exc)}
+    # ---- planner candidate scoring: 64 images x 8 states x 168 candidates per state (SURVEY.md section 8d, C3 sweep)
+    try:
+        S, H, W = 512, 128, 128
+        gen = torch.Generator().manual_seed(10 + 3000)
+        states = torch.rand(S, 3, H, W, generator=gen).to(dev)
+        targets = torch.rand(64, 3, H, W, generator=gen).to(dev)
+        ops, prm = [], []
+        for op, cnt in ((0, 10), (1, 10), (2, 10), (6, 10), (5, 64), (3, 64)):
+            n = {3: 24, 5: 8}.get(op, 1)
+            for _ in range(cnt):
+                ops.append(op)
+                row = torch.zeros(24)
+                row[:n] = (0.5 + torch.rand(n, generator=gen)) if n > 1 else torch.rand(1, generator=gen) * 0.5
+                prm.append(row)
+        per = len(ops)
+        cand_state = [s for s in range(S) for _ in range(per)]
+        cand_op = ops * S
+        cand_param = torch.stack(prm).repeat(S, 1)
+        st_t = [s // 8 for s in range(S)]
+        cb = TF.CandidateBatch(S, cand_state, cand_op, cand_param, dev, st_t)   # staged once; time only the launches
+        t_sc = bench(lambda: TF.score_prepared(states, targets, cb), 5)
+        C = S * per
+        ex['planner_scoring'] = {'workload': '512 states (64 images x beam 8) of 3x128x128, %d candidates per state' % per,
+                                 'candidates': C, 'ms': t_sc, 'candidates_per_s': C / t_sc * 1e3,
+                                 'Gpixel_candidates_per_s': C * H * W / t_sc / 1e6}
+    except Exception as exc:
+        ex['planner_scoring'] = {'error': repr(exc)}
+    return ex
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-extras', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,42 @@
+"""Tiny drivers for profiler captures: python scripts/run_once.py {fwd_c4|bwd_c4|score|c2}"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import t2onet_b200.functional as TF  # noqa: E402
+
+what = sys.argv[1]
+dev = 'cuda:0'
+if what in ('fwd_c4', 'bwd_c4'):
+    img, tgt, params = bench.make_batch(16, 2048, 3072, 4010, dev)
+    for _ in range(3):
+        if what == 'fwd_c4':
+            TF._forward_raw(bench.CHAIN, [0, 1, 2, 3, 27, 35], img, None, 0, torch.cat(params, 1).contiguous(), 36, tgt, True, True, 8)
+        else:
+            TF.chain_forward_backward(img, bench.CHAIN, params, tgt)
+elif what == 'c2':
+    img, tgt, params = bench.make_batch(64, 128, 128, 2010, dev)
+    for _ in range(3):
+        TF.chain_forward_backward(img, bench.CHAIN, params, tgt)
+elif what == 'score':
+    S, H, W = 512, 128, 128
+    gen = torch.Generator().manual_seed(3010)
+    states = torch.rand(S, 3, H, W, generator=gen).to(dev)
+    targets = torch.rand(64, 3, H, W, generator=gen).to(dev)
+    ops, prm = [], []
+    for op, cnt in ((0, 10), (1, 10), (2, 10), (6, 10), (5, 64), (3, 64)):
+        n = {3: 24, 5: 8}.get(op, 1)
+        for _ in range(cnt):
+            ops.append(op)
+            row = torch.zeros(24)
+            row[:n] = (0.5 + torch.rand(n, generator=gen)) if n > 1 else torch.rand(1, generator=gen) * 0.5
+            prm.append(row)
+    cb = TF.CandidateBatch(S, [s for s in range(S) for _ in ops], ops * S, torch.stack(prm).repeat(S, 1), dev,
+                           [s // 8 for s in range(S)])
+    for _ in range(3):
+        TF.score_prepared(states, targets, cb)
+torch.cuda.synchronize()
+print('done', what)

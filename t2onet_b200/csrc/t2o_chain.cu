@@ -653,9 +653,13 @@ static void geom_2d(Geom &g, int B, int H, int W, int vec, int tw_px, int th) {
     g.ntiles = g.tiles_x * g.tiles_y;
 }
 
+// Opt in to the dynamic shared memory a launch needs.  The 48 KB default limit counts static +
+// dynamic bytes, so anything above 32 KB is configured explicitly (once per kernel and size).
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
+    static size_t configured = 0;          // one instance per kernel type K ... but K is a pointer type
+    (void)configured;
+    if (bytes > 32 * 1024) {
         if (bytes > 227 * 1024) return T2O_ERR_UNSUPPORTED;
         T2O_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     }

@@ -132,6 +132,15 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     }
     ct[16] = 1.0f / S;
     ct[17] = scale;
+    // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
+    // which would make the output clamp swallow the gradient of every saturated (x == 1.0) pixel.
+    // Pull the last segment back so that y(1) <= 1 (a < 1e-6 shift; reference rounding there is
+    // platform dependent anyway).
+    float q_end = ct[MAX_L + L - 1];
+    if (fmaf(ct[L - 1], 1.0f, q_end) < 1.0f + 1e-5f) {
+        for (int it = 0; it < 8 && fmaf(ct[L - 1], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
+        ct[MAX_L + L - 1] = q_end;
+    }
 }
 
 T2O_HD void build_table(int op, const float *p, int L, float *tab) {

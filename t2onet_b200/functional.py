@@ -243,6 +243,46 @@ def l1_sum(a, b):
     return out
 
 
+class CandidateBatch:
+    """Device-resident candidate list for score_candidates (build once, score many times)."""
+
+    def __init__(self, S, cand_state, cand_op, cand_param, device, state_target=None):
+        cs = torch.as_tensor(cand_state, dtype=torch.int64).cpu()
+        self.C = int(cs.numel())
+        self.S = S
+        if self.C and (bool((cs[1:] < cs[:-1]).any()) or int(cs.min()) < 0 or int(cs.max()) >= S):
+            raise _lib.T2OError('cand_state must be ascending and within [0, S)')
+        begin = torch.zeros(S + 1, dtype=torch.int64)
+        if self.C:
+            begin[1:] = torch.cumsum(torch.bincount(cs, minlength=S), 0)
+        self.begin = begin.to(torch.int32).to(device)
+        self.ops = torch.as_tensor(cand_op, dtype=torch.int32).to(device).contiguous()
+        prm = torch.as_tensor(cand_param, dtype=torch.float32)
+        if prm.dim() != 2 or prm.shape[0] != self.C or prm.shape[1] > _lib.MAX_OP_PARAMS:
+            raise _lib.T2OError('cand_param must be (C, <=24)')
+        if prm.shape[1] < _lib.MAX_OP_PARAMS:
+            prm = torch.cat([prm, prm.new_zeros(self.C, _lib.MAX_OP_PARAMS - prm.shape[1])], 1)
+        self.prm = prm.to(device).contiguous()
+        self.state_target = None if state_target is None else \
+            torch.as_tensor(state_target, dtype=torch.int32).to(device).contiguous()
+
+
+def score_prepared(states, targets, cb, curve_steps=CURVE_STEPS):
+    """One t2o_score_candidates launch on a prepared CandidateBatch -> (C,) float32 CUDA tensor."""
+    dev = states.device
+    S, _, H, W = states.shape
+    out = torch.empty(cb.C, device=dev, dtype=torch.float32)
+    if cb.C == 0:
+        return out
+    lib = _lib.lib()
+    ws = _lib.workspace(dev, lib.t2o_score_workspace_bytes(S, cb.C, H, W))
+    st = lib.t2o_score_candidates(_lib.ptr(states), S, _lib.ptr(targets), targets.shape[0], _lib.ptr(cb.state_target),
+                                  _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm), cb.C, _lib.ptr(out), H, W,
+                                  curve_steps, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(st)
+    return out
+
+
 def score_candidates(states, targets, cand_state, cand_op, cand_param, state_target=None, curve_steps=CURVE_STEPS):
     """Score C single-operator candidates: l1_sum[c] = sum |clamp(op_c(states[cand_state[c]]; param_c)) - target|.
 
@@ -250,31 +290,5 @@ def score_candidates(states, targets, cand_state, cand_op, cand_param, state_tar
     cand_state ascending; cand_param (C, <=24) float.  state_target (S,) picks each state's target
     (default s % T).  Returns a (C,) float32 CUDA tensor in candidate order."""
     states, targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
-    dev = states.device
-    S, _, H, W = states.shape
-    T = targets.shape[0]
-    cs = torch.as_tensor(cand_state, dtype=torch.int64).cpu()
-    C = int(cs.numel())
-    if C == 0:
-        return torch.empty(0, device=dev, dtype=torch.float32)
-    if bool((cs[1:] < cs[:-1]).any()) or int(cs.min()) < 0 or int(cs.max()) >= S:
-        raise _lib.T2OError('cand_state must be ascending and within [0, S)')
-    begin = torch.zeros(S + 1, dtype=torch.int64)
-    begin[1:] = torch.cumsum(torch.bincount(cs, minlength=S), 0)
-    begin = begin.to(torch.int32).to(dev)
-    ops = torch.as_tensor(cand_op, dtype=torch.int32).to(dev).contiguous()
-    prm = torch.as_tensor(cand_param, dtype=torch.float32)
-    if prm.dim() != 2 or prm.shape[0] != C or prm.shape[1] > _lib.MAX_OP_PARAMS:
-        raise _lib.T2OError('cand_param must be (C, <=24)')
-    if prm.shape[1] < _lib.MAX_OP_PARAMS:
-        prm = torch.cat([prm, prm.new_zeros(C, _lib.MAX_OP_PARAMS - prm.shape[1])], 1)
-    prm = prm.to(dev).contiguous()
-    st_t = None if state_target is None else torch.as_tensor(state_target, dtype=torch.int32).to(dev).contiguous()
-    lib = _lib.lib()
-    out = torch.empty(C, device=dev, dtype=torch.float32)
-    ws = _lib.workspace(dev, lib.t2o_score_workspace_bytes(S, C, H, W))
-    st = lib.t2o_score_candidates(_lib.ptr(states), S, _lib.ptr(targets), T, _lib.ptr(st_t), _lib.ptr(begin),
-                                  _lib.ptr(ops), _lib.ptr(prm), C, _lib.ptr(out), H, W, curve_steps,
-                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
-    _lib.check(st)
-    return out
+    cb = CandidateBatch(states.shape[0], cand_state, cand_op, cand_param, states.device, state_target)
+    return score_prepared(states, targets, cb, curve_steps)

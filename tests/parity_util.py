@@ -30,9 +30,12 @@ def sample_params(op, B, g, wide=False):
     return u
 
 
-def rel_err(a, b):
+def rel_err(a, b, atol=1e-7):
+    """max|a-b| relative to max|b|; differences below `atol` (fp32 cancellation noise on gradients that are
+    analytically ~0, e.g. contrast on an all-white region: R - 1 = -1e-6) count as zero."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+    d = np.abs(a - b).max()
+    return 0.0 if d <= atol else float(d / (np.abs(b).max() + 1e-12))
 
 
 def max_abs(a, b):
