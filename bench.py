@@ -221,7 +221,7 @@ def run_ours(args, wl):
     res_gp = torch.empty(B, 36, pin_memory=True)
 
     def e2e_step(i):
-        j = i % 2
+        j = i % len(himg)
         img = himg[j].to(dev, non_blocking=True)
         tgt = htgt[j].to(dev, non_blocking=True)
         params = [p.to(dev, non_blocking=True) for p in hparams[j]]

@@ -1,0 +1,8 @@
+// Backward instantiations: SHARP = false, HAS_MASK = false (see t2o_chain_kernels.cuh).
+#include "t2o_chain_kernels.cuh"
+
+namespace t2o {
+int launch_bwd_flat_nomask(int vec, bool small_chain, const BwdArgs &a, size_t smem, cudaStream_t stream) {
+    return launch_bwd_sel<false, false>(vec, small_chain, a, smem, stream);
+}
+}  // namespace t2o

@@ -29,10 +29,13 @@ struct Geom {
     int B, H, W;
     int Wg;                 // W / VEC (2-D tiling only)
     int tiles_x, tiles_y;   // 2-D tiling only
-    int ntiles;             // tiles per image (gridDim.x)
+    int ntiles;             // tiles per image
+    int nchunks;            // CTAs per image (gridDim.x): nchunks * tiles_per_cta >= ntiles
+    int tiles_per_cta;      // 2-D backward: tiles a CTA walks through (amortises per-CTA setup / reduction)
     int TH, TWg;            // 2-D tile, in rows / groups
     int tile_groups;        // 1-D tiling
     long long ngroups;      // 1-D tiling: H*W / VEC
+    unsigned int mul_tiles_x, mul_tw, mul_rw, mul_gw, mul_xw;   // ceil(2^32 / d) magic numbers (fast_div)
 };
 
 // ---------------------------------------------------------------- vector global access

@@ -16,8 +16,12 @@
 //       brightness    y_c = v' * (1 - u_c/(v+eps)),            v' = clamp(v(1+p), 0, 1)
 //       saturation    y_c = v  * (1 - u_c * s'/d),             s' = clamp(s(1+p), 0, 1)   (d == 0: y_c = v)
 //     (f*s of hsv_to_rgb is u_c/(v+eps) exactly; the sector select is continuous, so no branch)
-//   Curves:           j = min(floor(L x), L-1);  y = k'_j x + Q_j,  k' = k L/S, Q_j = L/S sum_{i<j} k_i/L - k'_j j/L
-//   Curve param grads: 2L+1 moments per curve (A_j = sum g, Bx_j = sum g x over bin j, C = sum g y)
+//   Contrast:         0.5 - 0.5 cos(pi L) = sin^2(pi L / 2), odd/even polynomials in L on [0, 1]
+//   Curves:           j = floor(L x);  y = k'_j x + Q_j,  k' = k L/S, Q_j = L/S sum_{i<j} k_i/L - k'_j j/L
+//   Curve param grads: per bin j the moments A_j = sum g, Bx_j = sum g x; per curve C = sum g y
+//
+// The instruction budget matters: at the HBM roofline a B200 SM has ~2 cycles per pixel, so the
+// hot paths avoid IEEE division (MUFU.RCP, 1 ulp), libm trigonometry and float->int conversions.
 #pragma once
 #include <math.h>
 
@@ -37,8 +41,8 @@ enum : int {
 constexpr int MAX_CHAIN = 8;
 constexpr int MAX_L = 8;
 constexpr int TAB = 64;    // floats in one (image, op) table
-constexpr int CT = 20;     // floats in one curve table: k'[8], Q[8], 1/S, L/S, pad
-constexpr int HIST = 17;   // moments of one curve: A[8], Bx[8], C
+constexpr int CT = 20;     // floats in one curve table: (k', Q) x 9 interleaved, 1/S, L/S
+constexpr int NBIN = MAX_L + 1;   // histogram bins of one curve (bin L collects x == 1.0, merged into L-1)
 constexpr float HSV_EPS = 1e-6f;     // kornia.rgb_to_hsv eps
 constexpr float LUM_EPS = 1e-6f;     // models/operators.py:244
 constexpr float CURVE_EPS = 1e-10f;  // models/operators.py:579,610
@@ -55,7 +59,10 @@ T2O_HD int op_num_params(int op, int L) {
     }
 }
 T2O_HD bool op_is_curve(int op) { return op == OP_TONE || op == OP_COLOR; }
-T2O_HD int op_hist_floats(int op) { return op == OP_TONE ? HIST : (op == OP_COLOR ? 3 * HIST : 0); }
+// float2 histogram slots (A_j, Bx_j) a curve operator needs per thread in the backward pass
+T2O_HD int op_hist_slots(int op) { return op == OP_TONE ? NBIN : (op == OP_COLOR ? 3 * NBIN : 0); }
+
+struct F2 { float a, b; };   // == float2 without needing vector_types.h on the host
 
 // ---------------------------------------------------------------- scalar helpers
 T2O_HD float sat01(float z) {
@@ -65,9 +72,27 @@ T2O_HD float sat01(float z) {
     return fminf(fmaxf(z, 0.0f), 1.0f);
 #endif
 }
-T2O_HD bool in01(float z) { return z >= 0.0f && z <= 1.0f; }   // torch.clamp backward: closed interval
-T2O_HD float rcp(float x) { return 1.0f / x; }
-T2O_HD float fdiv(float a, float b) { return a / b; }
+// torch.clamp backward passes the gradient on the closed interval [0, 1].  On the device this is ONE
+// unsigned compare of the bit pattern (non-negative floats order like unsigned ints; negatives and NaN
+// have larger patterns).  The only deviation is z == -0.0f, which counts as outside.
+T2O_HD bool in01(float z) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(z) <= 0x3F800000u;
+#else
+    return z >= 0.0f && z <= 1.0f;
+#endif
+}
+// 1/x as a bare MUFU.RCP (<= 1 ulp) instead of the ~10-instruction IEEE sequence
+T2O_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+T2O_HD float fdiv(float a, float b) { return a * rcp(b); }
 T2O_HD float mul_rn(float a, float b) {
 #if defined(__CUDA_ARCH__)
     return __fmul_rn(a, b);
@@ -82,19 +107,25 @@ T2O_HD float add_rn(float a, float b) {
     volatile float r = a + b; return r;
 #endif
 }
-T2O_HD float cospi_f(float x) {
-#if defined(__CUDA_ARCH__)
-    return cospif(x);
-#else
-    return cosf(PI_F * x);
-#endif
+// sin(pi/2 L) and cos(pi/2 L) for L in [0, 1]: Chebyshev-fitted polynomials in L^2, |err| < 2e-7 in fp32
+T2O_HD float sin_halfpi(float L) {
+    const float t = L * L;
+    float p = 0.0001516751217423007f;
+    p = fmaf(p, t, -0.004674150608479977f);
+    p = fmaf(p, t, 0.07968991994857788f);
+    p = fmaf(p, t, -0.6459637880325317f);
+    p = fmaf(p, t, 1.5707963705062866f);
+    return p * L;
 }
-T2O_HD float sinpi_f(float x) {
-#if defined(__CUDA_ARCH__)
-    return sinpif(x);
-#else
-    return sinf(PI_F * x);
-#endif
+T2O_HD float cos_halfpi(float L) {
+    const float t = L * L;
+    float p = -2.3824535674066283e-05f;
+    p = fmaf(p, t, 0.0009177238680422306f);
+    p = fmaf(p, t, -0.02086268737912178f);
+    p = fmaf(p, t, 0.2536693215370178f);
+    p = fmaf(p, t, -1.2337005138397217f);
+    p = fmaf(p, t, 1.0f);
+    return p;
 }
 T2O_HD float max3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
 T2O_HD float min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
@@ -112,6 +143,8 @@ T2O_HD float lum_rn(float r, float g, float b) {
 // whitebal.  : tab[0..2]
 // tone       : one curve table at tab[0]
 // color      : three curve tables at tab[0], tab[CT], tab[2*CT]
+// curve table: ct[2j] = k'_j, ct[2j+1] = Q_j for j = 0..L (entry L repeats L-1: it serves x == 1.0),
+//              ct[18] = 1/S, ct[19] = L/S
 T2O_HD void build_curve(const float *k, int L, float *ct) {
     float S = 0.0f;
     for (int i = 0; i < L; ++i) S += k[i];
@@ -119,28 +152,30 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     const float scale = (float)L / S;
     const float invL = 1.0f / (float)L;
     float prefix = 0.0f;
-    for (int j = 0; j < MAX_L; ++j) {
+    for (int j = 0; j < NBIN; ++j) {
         if (j < L) {
             const float kp = k[j] * scale;
-            ct[j] = kp;
-            ct[MAX_L + j] = prefix * scale - kp * ((float)j * invL);
+            ct[2 * j] = kp;
+            ct[2 * j + 1] = prefix * scale - kp * ((float)j * invL);
             prefix += k[j] * invL;
         } else {
-            ct[j] = 0.0f;
-            ct[MAX_L + j] = 0.0f;
+            ct[2 * j] = 0.0f;
+            ct[2 * j + 1] = 0.0f;
         }
     }
-    ct[16] = 1.0f / S;
-    ct[17] = scale;
     // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
     // which would make the output clamp swallow the gradient of every saturated (x == 1.0) pixel.
     // Pull the last segment back so that y(1) <= 1 (a < 1e-6 shift; reference rounding there is
     // platform dependent anyway).
-    float q_end = ct[MAX_L + L - 1];
-    if (fmaf(ct[L - 1], 1.0f, q_end) < 1.0f + 1e-5f) {
-        for (int it = 0; it < 8 && fmaf(ct[L - 1], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
-        ct[MAX_L + L - 1] = q_end;
+    float q_end = ct[2 * (L - 1) + 1];
+    if (fmaf(ct[2 * (L - 1)], 1.0f, q_end) < 1.0f + 1e-5f) {
+        for (int it = 0; it < 8 && fmaf(ct[2 * (L - 1)], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
+        ct[2 * (L - 1) + 1] = q_end;
     }
+    ct[2 * L] = ct[2 * (L - 1)];
+    ct[2 * L + 1] = ct[2 * (L - 1) + 1];
+    ct[18] = 1.0f / S;
+    ct[19] = scale;
 }
 
 T2O_HD void build_table(int op, const float *p, int L, float *tab) {
@@ -157,50 +192,59 @@ T2O_HD void build_table(int op, const float *p, int L, float *tab) {
 }
 
 // ---------------------------------------------------------------- blend + clamp (models/operators.py:129-130)
-T2O_HD float blend(float y, float x, float m, bool has_mask) { return has_mask ? fmaf(y, m, x * (1.0f - m)) : y; }
+template <bool HM>
+T2O_HD float blend(float y, float x, float m) { return HM ? fmaf(y, m, x * (1.0f - m)) : y; }
 
 // ---------------------------------------------------------------- forward: y = process(x; p)   (pre-blend)
 T2O_HD void brightness_y(const float *tab, float r, float g, float b, float &yr, float &yg, float &yb) {
     const float v = max3(r, g, b);
     const float inv = rcp(v + HSV_EPS);
     const float v2 = sat01(v * tab[1]);
-    yr = v2 * (1.0f - (v - r) * inv);
-    yg = v2 * (1.0f - (v - g) * inv);
-    yb = v2 * (1.0f - (v - b) * inv);
+    yr = v2 * fmaf(r - v, inv, 1.0f);
+    yg = v2 * fmaf(g - v, inv, 1.0f);
+    yb = v2 * fmaf(b - v, inv, 1.0f);
 }
 
 T2O_HD void saturation_y(const float *tab, float r, float g, float b, float &yr, float &yg, float &yb) {
     const float v = max3(r, g, b), mn = min3(r, g, b);
     const float d = v - mn;
-    const float s = fdiv(d, v + HSV_EPS);
-    const float s2 = sat01(s * tab[1]);
-    const float rho = d > 0.0f ? fdiv(s2, d) : 0.0f;
-    const float vr = v * rho;
-    yr = v - (v - r) * vr;
-    yg = v - (v - g) * vr;
-    yb = v - (v - b) * vr;
+    const float s2 = sat01(d * rcp(v + HSV_EPS) * tab[1]);
+    const float vr = v * (s2 * rcp(fmaxf(d, 1e-30f)));      // d == 0  =>  s2 == 0  =>  vr == 0
+    yr = fmaf(r - v, vr, v);
+    yg = fmaf(g - v, vr, v);
+    yb = fmaf(b - v, vr, v);
 }
 
 T2O_HD void contrast_y(const float *tab, float r, float g, float b, float &yr, float &yg, float &yb) {
     const float L = sat01(lum_rn(r, g, b));
-    const float cl = 0.5f - 0.5f * cospi_f(L);
-    const float R = fdiv(cl, L + LUM_EPS);
-    const float F = fmaf(tab[0], R, tab[1]);      // (1-p) + p*R
+    const float sh = sin_halfpi(L);
+    const float R = sh * sh * rcp(L + LUM_EPS);     // (0.5 - 0.5 cos(pi L)) / (L + eps)
+    const float F = fmaf(tab[0], R, tab[1]);        // (1-p) + p*R
     yr = r * F; yg = g * F; yb = b * F;
 }
 
-T2O_HD int curve_bin(float xs, int L) {
-    const int j = (int)(xs * (float)L);
-    return j < L - 1 ? j : L - 1;
+// bin of a clamped input xs in [0, 1]: j = floor(L xs) in 0..L, t = L xs, tf = float(j)
+T2O_HD int curve_bin(float xs, int L, float &t, float &tf) {
+    t = xs * (float)L;
+#if defined(__CUDA_ARCH__)
+    const float u = __fadd_rd(t, 8388608.0f);       // 2^23 + floor(t): the low mantissa bits are the bin
+    tf = u - 8388608.0f;
+    return __float_as_int(u) & 15;
+#else
+    tf = floorf(t);
+    return (int)tf;
+#endif
 }
 T2O_HD float curve_y(const float *ct, int L, float x) {
     const float xs = sat01(x);
-    const int j = curve_bin(xs, L);
-    return fmaf(ct[j], xs, ct[MAX_L + j]);
+    float t, tf;
+    const int j = curve_bin(xs, L, t, tf);
+    const F2 seg = *reinterpret_cast<const F2 *>(ct + 2 * j);
+    return fmaf(seg.a, xs, seg.b);
 }
 
 // y = x + p * laplace(x), zero padding handled by the caller (neighbours outside the image are 0)
-T2O_HD float laplace(float c, float up, float dn, float lf, float rt) { return 4.0f * c - up - dn - lf - rt; }
+T2O_HD float laplace(float c, float up, float dn, float lf, float rt) { return fmaf(4.0f, c, -((up + dn) + (lf + rt))); }
 
 // pointwise operators only (sharpness needs neighbours and is applied by the kernels)
 T2O_HD void op_y(int op, const float *tab, int L, float r, float g, float b, float &yr, float &yg, float &yb) {
@@ -218,51 +262,71 @@ T2O_HD void op_y(int op, const float *tab, int L, float r, float g, float b, flo
 }
 
 // one full Operator.execute on a pixel (pointwise operators): x <- clamp(blend(process(x)))
+template <bool HM>
 T2O_HD void op_apply(int op, const float *tab, int L, float &r, float &g, float &b,
-                     float mr, float mg, float mb, bool has_mask, bool raw = false) {
+                     float mr, float mg, float mb, bool raw = false) {
     if (op < 0) return;                       // identity: no clamp (executors/executor.py:44-46)
     float yr, yg, yb;
     op_y(op, tab, L, r, g, b, yr, yg, yb);
     if (raw) { r = yr; g = yg; b = yb; return; }   // Operator.process only
-    r = sat01(blend(yr, r, mr, has_mask));
-    g = sat01(blend(yg, g, mg, has_mask));
-    b = sat01(blend(yb, b, mb, has_mask));
+    r = sat01(blend<HM>(yr, r, mr));
+    g = sat01(blend<HM>(yg, g, mg));
+    b = sat01(blend<HM>(yb, b, mb));
+}
+
+// same, from (r,g,b) into (or,og,ob): lets the backward kernels keep every operator's input without copies
+template <bool HM>
+T2O_HD void op_apply_io(int op, const float *tab, int L, float r, float g, float b, float &orr, float &og, float &ob,
+                        float mr, float mg, float mb) {
+    if (op < 0) { orr = r; og = g; ob = b; return; }
+    float yr, yg, yb;
+    op_y(op, tab, L, r, g, b, yr, yg, yb);
+    orr = sat01(blend<HM>(yr, r, mr));
+    og = sat01(blend<HM>(yg, g, mg));
+    ob = sat01(blend<HM>(yb, b, mb));
 }
 
 // ---------------------------------------------------------------- backward
 // Gradient through blend + clamp: g (dLoss/d out) -> gy (dLoss/d y) and gd (direct path to x).
-T2O_HD void blend_bwd(float y, float x, float m, bool has_mask, float g, float &gy, float &gd) {
-    const float z = blend(y, x, m, has_mask);
+template <bool HM>
+T2O_HD void blend_bwd(float y, float x, float m, float g, float &gy, float &gd) {
+    const float z = blend<HM>(y, x, m);
     const float gz = in01(z) ? g : 0.0f;
-    gy = has_mask ? gz * m : gz;
-    gd = has_mask ? gz * (1.0f - m) : 0.0f;
+    gy = HM ? gz * m : gz;
+    gd = HM ? gz * (1.0f - m) : 0.0f;
 }
 
-// Histogram sink for the curve moments.  `h[slot * stride]` is private to the calling thread.
+// Histogram sink for the curve moments: `h[slot * stride]` is an (A, Bx) pair private to the thread.
 struct Hist {
-    float *h;
+    F2 *h;
     int stride;
-    T2O_HD void add(int slot, float v) const { h[slot * stride] += v; }
+    T2O_HD void add(int slot, float a, float b) const {
+        F2 v = h[slot * stride];
+        v.a += a; v.b += b;
+        h[slot * stride] = v;
+    }
 };
 
 // Each *_bwd takes the operator input x = (r,g,b), the mask, the upstream gradient
 // (gr,gg,gb) = dLoss/d(out) and returns dLoss/d(x) in place.  `acc` receives the parameter
 // gradient contributions when `own` is true (halo pixels recompute but must not accumulate).
-T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb, bool has_mask,
+template <bool HM>
+T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
                            float &gr, float &gg, float &gb, float *acc, bool own) {
     const float q = tab[1];
     const float v = max3(r, g, b), mn = min3(r, g, b);
     const float inv = rcp(v + HSV_EPS);
     const float t = v * q;
     const float v2 = sat01(t);
-    const float ipq = in01(t) ? q : 0.0f;
-    const float wr = 1.0f - (v - r) * inv, wg = 1.0f - (v - g) * inv, wb = 1.0f - (v - b) * inv;
+    const bool ip = in01(t);
+    const float ipq = ip ? q : 0.0f;
+    const float wr = fmaf(r - v, inv, 1.0f), wg = fmaf(g - v, inv, 1.0f), wb = fmaf(b - v, inv, 1.0f);
     float gyr, gyg, gyb, gdr, gdg, gdb;
-    blend_bwd(v2 * wr, r, mr, has_mask, gr, gyr, gdr);
-    blend_bwd(v2 * wg, g, mg, has_mask, gg, gyg, gdg);
-    blend_bwd(v2 * wb, b, mb, has_mask, gb, gyb, gdb);
+    blend_bwd<HM>(v2 * wr, r, mr, gr, gyr, gdr);
+    blend_bwd<HM>(v2 * wg, g, mg, gg, gyg, gdg);
+    blend_bwd<HM>(v2 * wb, b, mb, gb, gyb, gdb);
     const float G = gyr * wr + gyg * wg + gyb * wb;                   // dLoss/d v'
-    if (own) acc[0] += in01(t) ? v * G : 0.0f;
+    if (own) acc[0] += ip ? v * G : 0.0f;
     if (v == mn) {          // gray pixel: the reference routes everything through max -> channel 0
         gr = gdr + G * ipq; gg = gdg; gb = gdb;
         return;
@@ -270,27 +334,28 @@ T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr
     const float k = v2 * inv;
     const float Gv = G * (ipq - k);
     const int im = argmax3(r, g, b);
-    gr = gdr + gyr * k + (im == 0 ? Gv : 0.0f);
-    gg = gdg + gyg * k + (im == 1 ? Gv : 0.0f);
-    gb = gdb + gyb * k + (im == 2 ? Gv : 0.0f);
+    gr = fmaf(gyr, k, gdr) + (im == 0 ? Gv : 0.0f);
+    gg = fmaf(gyg, k, gdg) + (im == 1 ? Gv : 0.0f);
+    gb = fmaf(gyb, k, gdb) + (im == 2 ? Gv : 0.0f);
 }
 
-T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb, bool has_mask,
+template <bool HM>
+T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
                            float &gr, float &gg, float &gb, float *acc, bool own) {
     const float q = tab[1];
     const float v = max3(r, g, b), mn = min3(r, g, b);
     const float d = v - mn;
     const float inv = rcp(v + HSV_EPS);
-    const float s = fdiv(d, v + HSV_EPS);
-    const float t = s * q;
+    const float t = d * inv * q;
     const float s2 = sat01(t);
-    const float rho = d > 0.0f ? fdiv(s2, d) : 0.0f;
+    const float id = rcp(fmaxf(d, 1e-30f));
+    const float rho = s2 * id;
     const float ur = v - r, ug = v - g, ub = v - b;
     const float vr = v * rho;
     float gyr, gyg, gyb, gdr, gdg, gdb;
-    blend_bwd(v - ur * vr, r, mr, has_mask, gr, gyr, gdr);
-    blend_bwd(v - ug * vr, g, mg, has_mask, gg, gyg, gdg);
-    blend_bwd(v - ub * vr, b, mb, has_mask, gb, gyb, gdb);
+    blend_bwd<HM>(fmaf(-ur, vr, v), r, mr, gr, gyr, gdr);
+    blend_bwd<HM>(fmaf(-ug, vr, v), g, mg, gg, gyg, gdg);
+    blend_bwd<HM>(fmaf(-ub, vr, v), b, mb, gb, gyb, gdb);
     const float Sg = gyr + gyg + gyb;
     if (!(d > 0.0f)) {      // gray pixel: y = v for every channel, max -> channel 0
         gr = gdr + Sg; gg = gdg; gb = gdb;
@@ -302,7 +367,6 @@ T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr
         if (own) acc[0] -= v * inv * Su;
         rho_v = -q * inv * inv; rho_mn = 0.0f;
     } else if (t > 1.0f) {  // s' = 1    ->  rho = 1 / d
-        const float id = rcp(d);
         rho_v = -id * id; rho_mn = id * id;
     } else {                // s' = 0
         rho_v = 0.0f; rho_mn = 0.0f;
@@ -310,12 +374,13 @@ T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr
     const float Gv = Sg - rho * Su - vr * Sg - v * rho_v * Su;
     const float Gmn = -v * rho_mn * Su;
     const int im = argmax3(r, g, b), in = argmin3(r, g, b);
-    gr = gdr + gyr * vr + (im == 0 ? Gv : 0.0f) + (in == 0 ? Gmn : 0.0f);
-    gg = gdg + gyg * vr + (im == 1 ? Gv : 0.0f) + (in == 1 ? Gmn : 0.0f);
-    gb = gdb + gyb * vr + (im == 2 ? Gv : 0.0f) + (in == 2 ? Gmn : 0.0f);
+    gr = fmaf(gyr, vr, gdr) + (im == 0 ? Gv : 0.0f) + (in == 0 ? Gmn : 0.0f);
+    gg = fmaf(gyg, vr, gdg) + (im == 1 ? Gv : 0.0f) + (in == 1 ? Gmn : 0.0f);
+    gb = fmaf(gyb, vr, gdb) + (im == 2 ? Gv : 0.0f) + (in == 2 ? Gmn : 0.0f);
 }
 
-T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb, bool has_mask,
+template <bool HM>
+T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
                          float &gr, float &gg, float &gb, float *acc, bool own) {
     const float p = tab[0];
     const float lum = lum_rn(r, g, b);
@@ -323,97 +388,103 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     // torch.min(torch.max(lum, 0), 1): binary max/min split the gradient 0.5/0.5 on ties
     const float f0 = lum > 0.0f ? 1.0f : (lum == 0.0f ? 0.5f : 0.0f);
     const float f1 = L < 1.0f ? 1.0f : (fmaxf(lum, 0.0f) == 1.0f ? 0.5f : 0.0f);
-    const float cl = 0.5f - 0.5f * cospi_f(L);
-    const float dcl = 0.5f * PI_F * sinpi_f(L);
+    const float sh = sin_halfpi(L), ch = cos_halfpi(L);
+    const float cl = sh * sh;                       // 0.5 - 0.5 cos(pi L)
+    const float dcl = PI_F * sh * ch;               // 0.5 pi sin(pi L)
     const float iden = rcp(L + LUM_EPS);
     const float R = cl * iden;
     const float dR = (dcl - R) * iden;
     const float F = fmaf(p, R, tab[1]);
     float gyr, gyg, gyb, gdr, gdg, gdb;
-    blend_bwd(r * F, r, mr, has_mask, gr, gyr, gdr);
-    blend_bwd(g * F, g, mg, has_mask, gg, gyg, gdg);
-    blend_bwd(b * F, b, mb, has_mask, gb, gyb, gdb);
+    blend_bwd<HM>(r * F, r, mr, gr, gyr, gdr);
+    blend_bwd<HM>(g * F, g, mg, gg, gyg, gdg);
+    blend_bwd<HM>(b * F, b, mb, gb, gyb, gdb);
     const float Sgc = gyr * r + gyg * g + gyb * b;
-    if (own) acc[0] += (R - 1.0f) * Sgc;
+    if (own) acc[0] = fmaf(R - 1.0f, Sgc, acc[0]);
     const float k = p * dR * f0 * f1 * Sgc;
-    gr = gdr + gyr * F + 0.27f * k;
-    gg = gdg + gyg * F + 0.67f * k;
-    gb = gdb + gyb * F + 0.06f * k;
+    gr = fmaf(gyr, F, gdr) + 0.27f * k;
+    gg = fmaf(gyg, F, gdg) + 0.67f * k;
+    gb = fmaf(gyb, F, gdb) + 0.06f * k;
 }
 
-// one channel of a curve operator
-T2O_HD float curve_bwd(const float *ct, int L, float x, float m, bool has_mask, float g, const Hist &hist, bool own) {
+// one channel of a curve operator; accC accumulates C = sum g*y of this curve
+template <bool HM>
+T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, const Hist &hist, float &accC, bool own) {
     const float xs = sat01(x);
-    const int j = curve_bin(xs, L);
-    const float kp = ct[j];
-    const float y = fmaf(kp, xs, ct[MAX_L + j]);
+    float t, tf;
+    const int j = curve_bin(xs, L, t, tf);
+    const F2 seg = *reinterpret_cast<const F2 *>(ct + 2 * j);
+    const float y = fmaf(seg.a, xs, seg.b);
     float gy, gd;
-    blend_bwd(y, x, m, has_mask, g, gy, gd);
+    blend_bwd<HM>(y, x, m, g, gy, gd);
     if (own) {
-        hist.add(j, gy);
-        hist.add(MAX_L + j, gy * xs);
-        hist.add(2 * MAX_L, gy * y);
+        hist.add(j, gy, gy * xs);
+        accC = fmaf(gy, y, accC);
     }
-    float slope = kp;
-    if (j > 0 && xs * (float)L == (float)j) slope += ct[j - 1];   // exact knot: both clamp terms pass
+    float slope = seg.a;
+    if (t == tf && j > 0 && j < L) slope += ct[2 * (j - 1)];        // exact knot: both clamp terms pass
     return gd + (in01(x) ? gy * slope : 0.0f);
 }
 
-// dLoss/dk_i of one curve from its block-reduced moments (A, Bx, C): k has L entries
-T2O_HD void curve_param_grad(const float *ct, int L, const float *mom, float *gk) {
-    const float invS = ct[16], scale = ct[17];
+// dLoss/dk_i of one curve from its block-reduced moments A[NBIN], Bx[NBIN] and C.  Bin L holds the
+// inputs equal to 1.0; they act like bin L-1 with the full 1/L step, so the two bins are merged.
+T2O_HD void curve_param_grad(const float *ct, int L, const float *A, const float *Bx, float C, float *gk) {
+    const float invS = ct[18], scale = ct[19];
     float tail = 0.0f;                       // sum_{j > i} A_j
     for (int i = L - 1; i >= 0; --i) {
+        const float Ai = A[i] + (i == L - 1 ? A[L] : 0.0f);
+        const float Bi = Bx[i] + (i == L - 1 ? Bx[L] : 0.0f);
         const float x0 = (float)i / (float)L;
-        const float sgc = (mom[MAX_L + i] - x0 * mom[i]) + tail / (float)L;
-        gk[i] = scale * sgc - invS * mom[2 * MAX_L];
-        tail += mom[i];
+        const float sgc = (Bi - x0 * Ai) + tail / (float)L;
+        gk[i] = scale * sgc - invS * C;
+        tail += Ai;
     }
 }
 
+template <bool HM>
 T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, float b,
-                          float mr, float mg, float mb, bool has_mask,
+                          float mr, float mg, float mb,
                           float &gr, float &gg, float &gb, float *acc, const Hist &hist, bool own) {
     switch (op) {
-        case OP_BRIGHTNESS: brightness_bwd(tab, r, g, b, mr, mg, mb, has_mask, gr, gg, gb, acc, own); break;
-        case OP_CONTRAST: contrast_bwd(tab, r, g, b, mr, mg, mb, has_mask, gr, gg, gb, acc, own); break;
-        case OP_SATURATION: saturation_bwd(tab, r, g, b, mr, mg, mb, has_mask, gr, gg, gb, acc, own); break;
+        case OP_BRIGHTNESS: brightness_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
+        case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
+        case OP_SATURATION: saturation_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
         case OP_TONE:
-            gr = curve_bwd(tab, L, r, mr, has_mask, gr, hist, own);
-            gg = curve_bwd(tab, L, g, mg, has_mask, gg, hist, own);
-            gb = curve_bwd(tab, L, b, mb, has_mask, gb, hist, own);
+            gr = curve_bwd<HM>(tab, L, r, mr, gr, hist, acc[0], own);
+            gg = curve_bwd<HM>(tab, L, g, mg, gg, hist, acc[0], own);
+            gb = curve_bwd<HM>(tab, L, b, mb, gb, hist, acc[0], own);
             break;
         case OP_COLOR: {
-            Hist h1{hist.h + HIST * hist.stride, hist.stride}, h2{hist.h + 2 * HIST * hist.stride, hist.stride};
-            gr = curve_bwd(tab, L, r, mr, has_mask, gr, hist, own);
-            gg = curve_bwd(tab + CT, L, g, mg, has_mask, gg, h1, own);
-            gb = curve_bwd(tab + 2 * CT, L, b, mb, has_mask, gb, h2, own);
+            Hist h1{hist.h + NBIN * hist.stride, hist.stride}, h2{hist.h + 2 * NBIN * hist.stride, hist.stride};
+            gr = curve_bwd<HM>(tab, L, r, mr, gr, hist, acc[0], own);
+            gg = curve_bwd<HM>(tab + CT, L, g, mg, gg, h1, acc[1], own);
+            gb = curve_bwd<HM>(tab + 2 * CT, L, b, mb, gb, h2, acc[2], own);
             break;
         }
         case OP_WHITE: {
             float gy, gd;
-            blend_bwd(1.0f, r, mr, has_mask, gr, gy, gd); gr = gd;
-            blend_bwd(1.0f, g, mg, has_mask, gg, gy, gd); gg = gd;
-            blend_bwd(1.0f, b, mb, has_mask, gb, gy, gd); gb = gd;
+            blend_bwd<HM>(1.0f, r, mr, gr, gy, gd); gr = gd;
+            blend_bwd<HM>(1.0f, g, mg, gg, gy, gd); gg = gd;
+            blend_bwd<HM>(1.0f, b, mb, gb, gy, gd); gb = gd;
             break;
         }
         case OP_EXPOSURE: {
             const float e = tab[1];
             float gyr, gyg, gyb, gdr, gdg, gdb;
-            blend_bwd(r * e, r, mr, has_mask, gr, gyr, gdr);
-            blend_bwd(g * e, g, mg, has_mask, gg, gyg, gdg);
-            blend_bwd(b * e, b, mb, has_mask, gb, gyb, gdb);
+            blend_bwd<HM>(r * e, r, mr, gr, gyr, gdr);
+            blend_bwd<HM>(g * e, g, mg, gg, gyg, gdg);
+            blend_bwd<HM>(b * e, b, mb, gb, gyb, gdb);
             if (own) acc[0] += LN2_F * e * (gyr * r + gyg * g + gyb * b);
-            gr = gdr + gyr * e; gg = gdg + gyg * e; gb = gdb + gyb * e;
+            gr = fmaf(gyr, e, gdr); gg = fmaf(gyg, e, gdg); gb = fmaf(gyb, e, gdb);
             break;
         }
         case OP_WHITEBALANCE: {
             float gyr, gyg, gyb, gdr, gdg, gdb;
-            blend_bwd(r * tab[0], r, mr, has_mask, gr, gyr, gdr);
-            blend_bwd(g * tab[1], g, mg, has_mask, gg, gyg, gdg);
-            blend_bwd(b * tab[2], b, mb, has_mask, gb, gyb, gdb);
-            if (own) { acc[0] += gyr * r; acc[1] += gyg * g; acc[2] += gyb * b; }
-            gr = gdr + gyr * tab[0]; gg = gdg + gyg * tab[1]; gb = gdb + gyb * tab[2];
+            blend_bwd<HM>(r * tab[0], r, mr, gr, gyr, gdr);
+            blend_bwd<HM>(g * tab[1], g, mg, gg, gyg, gdg);
+            blend_bwd<HM>(b * tab[2], b, mb, gb, gyb, gdb);
+            if (own) { acc[0] = fmaf(gyr, r, acc[0]); acc[1] = fmaf(gyg, g, acc[1]); acc[2] = fmaf(gyb, b, acc[2]); }
+            gr = fmaf(gyr, tab[0], gdr); gg = fmaf(gyg, tab[1], gdg); gb = fmaf(gyb, tab[2], gdb);
             break;
         }
         default: break;     // identity: gradient passes unchanged

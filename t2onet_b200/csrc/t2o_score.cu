@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
 #define T2O_CASE(OPC)                                                                                         \
     case OPC:                                                                                                 \
         _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                       \
-            op_apply(OPC, tab, a.L, x[0][v], x[1][v], x[2][v], 1.0f, 1.0f, 1.0f, false);                      \
+            op_apply<false>(OPC, tab, a.L, x[0][v], x[1][v], x[2][v], 1.0f, 1.0f, 1.0f);                           \
         break;
                     T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
                     T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)

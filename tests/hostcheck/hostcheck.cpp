@@ -41,12 +41,13 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                             const float up = yy > 0 ? pc[i - W] : 0.f, dn = yy < H - 1 ? pc[i + W] : 0.f;
                             const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
                             const float v = fmaf(tab[0], laplace(ctr, up, dn, lf, rt), ctr);
-                            y[c * plane + i] = sat01(blend(v, ctr, M(c, i), has_mask));
+                            y[c * plane + i] = sat01(has_mask ? blend<true>(v, ctr, M(c, i)) : v);
                         }
             } else {
                 for (size_t i = 0; i < plane; ++i) {
                     float r = x[i], gg = x[plane + i], bb = x[2 * plane + i];
-                    op_apply(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i), has_mask);
+                    if (has_mask) op_apply<true>(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i));
+                    else op_apply<false>(ops[k], tab, L, r, gg, bb, 1.f, 1.f, 1.f);
                     y[i] = r; y[plane + i] = gg; y[2 * plane + i] = bb;
                 }
             }
@@ -73,8 +74,8 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             const float *tab = &tabs[k * TAB];
             float acc[3] = {0, 0, 0};
             std::vector<double> accd(3, 0.0);
-            float hist[3 * HIST];
-            std::vector<double> histd(3 * HIST, 0.0);
+            F2 hist[3 * NBIN];
+            std::vector<double> histA(3 * NBIN, 0.0), histB(3 * NBIN, 0.0);
             if (ops[k] == OP_SHARPNESS) {
                 const float p = tab[0];
                 double accp = 0;
@@ -88,7 +89,8 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                             const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
                             const float lap = laplace(ctr, up, dn, lf, rt);
                             float gy, gd;
-                            blend_bwd(fmaf(p, lap, ctr), ctr, M(c, i), has_mask, g[c * plane + i], gy, gd);
+                            if (has_mask) blend_bwd<true>(fmaf(p, lap, ctr), ctr, M(c, i), g[c * plane + i], gy, gd);
+                            else blend_bwd<false>(fmaf(p, lap, ctr), ctr, 1.f, g[c * plane + i], gy, gd);
                             gyv[c * plane + i] = gy;
                             gn[c * plane + i] = gd;
                             accp += (double)gy * lap;
@@ -108,23 +110,27 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             }
             for (size_t i = 0; i < plane; ++i) {
                 float gr = g[i], gg = g[plane + i], gb = g[2 * plane + i];
-                for (int t = 0; t < 3 * HIST; ++t) hist[t] = 0.f;
+                for (int t = 0; t < 3 * NBIN; ++t) hist[t].a = hist[t].b = 0.f;
                 acc[0] = acc[1] = acc[2] = 0.f;
                 Hist h{hist, 1};
-                pointwise_bwd(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], M(0, i), M(1, i), M(2, i), has_mask,
-                              gr, gg, gb, acc, h, true);
+                if (has_mask)
+                    pointwise_bwd<true>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], M(0, i), M(1, i), M(2, i),
+                                        gr, gg, gb, acc, h, true);
+                else
+                    pointwise_bwd<false>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], 1.f, 1.f, 1.f,
+                                         gr, gg, gb, acc, h, true);
                 g[i] = gr; g[plane + i] = gg; g[2 * plane + i] = gb;
                 for (int t = 0; t < 3; ++t) accd[t] += acc[t];
-                for (int t = 0; t < 3 * HIST; ++t) histd[t] += hist[t];
+                for (int t = 0; t < 3 * NBIN; ++t) { histA[t] += hist[t].a; histB[t] += hist[t].b; }
             }
             if (grad_params) {
                 float *gp = grad_params + (size_t)b * pstride + poff[k];
                 if (ops[k] == OP_TONE || ops[k] == OP_COLOR) {
                     const int nc = ops[k] == OP_TONE ? 1 : 3;
                     for (int c = 0; c < nc; ++c) {
-                        float mom[HIST];
-                        for (int t = 0; t < HIST; ++t) mom[t] = (float)histd[c * HIST + t];
-                        curve_param_grad(tab + c * CT, L, mom, gp + c * L);
+                        float A[NBIN], Bx[NBIN];
+                        for (int t = 0; t < NBIN; ++t) { A[t] = (float)histA[c * NBIN + t]; Bx[t] = (float)histB[c * NBIN + t]; }
+                        curve_param_grad(tab + c * CT, L, A, Bx, (float)accd[c], gp + c * L);
                     }
                 } else {
                     const int n = op_num_params(ops[k], L);
