@@ -57,7 +57,7 @@ enum t2o_op {
 enum t2o_status {
     T2O_OK = 0,
     T2O_ERR_INVALID_ARG = 1,      /* NULL where required, bad sizes, bad op id */
-    T2O_ERR_UNSUPPORTED = 2,      /* inpaint, curve_steps > 8, more than one sharpen per launch, ... */
+    T2O_ERR_UNSUPPORTED = 2,      /* inpaint, curve_steps > 8, an operator type twice in one backward launch, ... */
     T2O_ERR_WORKSPACE = 3,        /* workspace too small */
     T2O_ERR_CUDA = 4,             /* a CUDA runtime call failed (see t2o_last_cuda_error) */
     T2O_ERR_NO_DEVICE = 5         /* no sm_100 device / driver entry point missing */
@@ -103,6 +103,8 @@ int t2o_chain_forward(int n_ops, const int *op_ids /*host*/, const int *param_of
  *   grad_params (B, param_stride)   every column of the row is written (0 outside the used slots)
  *   grad_img    (B,3,H,W) or NULL   dLoss/d(img)
  *   out, l1_sum           or NULL   the forward results, for a fused forward+backward step
+ * Every operator type (sharpness included) may appear at most once per launch: the kernel keeps one register
+ * accumulator slot per type (T2O_ERR_UNSUPPORTED otherwise; the binding splits longer chains into launches).
  * Gradient conventions follow torch autograd on the reference graph: clamp passes the gradient on
  * the closed interval, the contrast luminance clamp splits ties 0.5/0.5, HSV max/min route to the
  * first tied channel (exact for gray pixels; two-channel ties see DESIGN.md).

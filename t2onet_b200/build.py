@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libt2o_b200.so')
-SOURCES = ['t2o_chain.cu', 't2o_chain_bwd_flat_nomask.cu', 't2o_chain_bwd_flat_mask.cu', 't2o_chain_bwd_sharp_nomask.cu',
-           't2o_chain_bwd_sharp_mask.cu', 't2o_score.cu', 't2o_cabi.cu']
-HEADERS = ['t2o_math.cuh', 't2o_common.cuh', 't2o_chain_kernels.cuh', os.path.join('..', '..', 'include', 't2o.h')]
+SOURCES = ['t2o_chain.cu', 't2o_step.cu',
+           't2o_score.cu', 't2o_cabi.cu']
+HEADERS = ['t2o_math.cuh', 't2o_common.cuh', 't2o_chain_kernels.cuh', 't2o_step_kernels.cuh', os.path.join('..', '..', 'include', 't2o.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

@@ -12,8 +12,9 @@ const char *last_cuda_error() { return g_cuda_err; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace: [counters: B x u32][L1 partials: B x maxtiles][grad partials: B x maxtiles x pstride]
-// upper bound of partials per image for every tiling a launcher can pick (tiles are >= 32 x 32 px or >= 1024 px flat)
-static inline size_t max_tiles(int H, int W) { return ((size_t)W / 32 + 2) * ((size_t)H / 32 + 2); }
+// upper bound of partials per image for every tiling a launcher can pick: forward tiles are >= 32 x 32 px or
+// >= 1024 px flat; step-kernel chunks are >= 1024 px flat or (strip of >= 28 groups) x (band of >= 16 rows)
+size_t max_tiles(int H, int W) { return ((size_t)W / 28 + 2) * ((size_t)H / 16 + 2); }
 size_t chain_workspace_bytes(int B, int H, int W, int pstride) {
     const size_t mt = max_tiles(H, W);
     return align_up((size_t)B * 4, 256) + align_up((size_t)B * mt * 4, 256) + align_up((size_t)B * mt * (size_t)(pstride > 0 ? pstride : 1) * 4, 256);
@@ -22,7 +23,7 @@ struct Workspace {
     unsigned int *counters;
     float *part_l1, *part_gp;
 };
-static Workspace carve(void *ws, int B, int H, int W) {
+Workspace carve_workspace(void *ws, int B, int H, int W) {
     const size_t mt = max_tiles(H, W);
     char *p = (char *)ws;
     Workspace w;
@@ -36,8 +37,8 @@ static int make_desc(int n_ops, const int *op_ids, const int *param_off, int L, 
     if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids || !param_off) return T2O_ERR_INVALID_ARG;
     if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
     if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
-    d.n = n_ops; d.L = L; d.sharp = -1; d.hist_total = 0;
-    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; d.hoff[k] = 0; }
+    d.n = n_ops; d.L = L; d.sharp = -1;
+    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
     for (int k = 0; k < n_ops; ++k) {
         const int op = op_ids[k];
         if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
@@ -47,8 +48,7 @@ static int make_desc(int n_ops, const int *op_ids, const int *param_off, int L, 
             if (d.sharp >= 0) return T2O_ERR_UNSUPPORTED;
             d.sharp = k;
         }
-        d.op[k] = op; d.poff[k] = param_off[k]; d.hoff[k] = d.hist_total;
-        d.hist_total += op_hist_slots(op);
+        d.op[k] = op; d.poff[k] = param_off[k];
     }
     return T2O_OK;
 }
@@ -138,7 +138,7 @@ int chain_forward(int n_ops, const int *op_ids, const int *param_off, const floa
     if (!out && !l1_sum) return T2O_ERR_INVALID_ARG;
     if (l1_sum && (!ws || ws_bytes < chain_workspace_bytes(B, H, W, pstride))) return T2O_ERR_WORKSPACE;
     if (B > 65535) return T2O_ERR_UNSUPPORTED;
-    Workspace w = carve(ws, B, H, W);
+    Workspace w = carve_workspace(ws, B, H, W);
     a.img = img; a.mask = mask; a.params = params; a.target = target; a.out = out; a.l1_sum = l1_sum;
     a.part_l1 = w.part_l1; a.counters = w.counters; a.mask_ch = mask_ch; a.pstride = pstride;
     const size_t plane = (size_t)H * W;
@@ -152,58 +152,6 @@ int chain_forward(int n_ops, const int *op_ids, const int *param_off, const floa
     geom_2d(a.g, B, H, W, vec, 256, 32, 1);
     const size_t smem = (size_t)3 * (a.g.TH + 2) * (a.g.TWg + 2) * vec * sizeof(float);
     return mask ? launch_fwd_vec<true, true>(vec, a, smem, stream) : launch_fwd_vec<true, false>(vec, a, smem, stream);
-}
-
-int chain_backward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
-                   const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
-                   float *grad_params, float *grad_img, float *out, float *l1_sum,
-                   int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
-    BwdArgs a;
-    int st = make_desc(n_ops, op_ids, param_off, L, pstride, a.ch);
-    if (st != T2O_OK) return st;
-    if (!img || B < 1 || H < 1 || W < 1 || (pstride > 0 && !params)) return T2O_ERR_INVALID_ARG;
-    if (mask && mask_ch != 1 && mask_ch != 3) return T2O_ERR_INVALID_ARG;
-    if (!grad_out && (!target || !grad_l1)) return T2O_ERR_INVALID_ARG;
-    if (l1_sum && !target) return T2O_ERR_INVALID_ARG;
-    if (!grad_params && !grad_img) return T2O_ERR_INVALID_ARG;
-    if (!ws || ws_bytes < chain_workspace_bytes(B, H, W, pstride)) return T2O_ERR_WORKSPACE;
-    if (B > 65535) return T2O_ERR_UNSUPPORTED;
-    Workspace w = carve(ws, B, H, W);
-    a.img = img; a.mask = mask; a.params = params; a.grad_out = grad_out; a.target = target; a.grad_l1 = grad_l1;
-    a.grad_params = grad_params; a.grad_img = grad_img; a.out = out; a.l1_sum = l1_sum;
-    a.part_l1 = w.part_l1; a.part_gp = w.part_gp; a.counters = w.counters; a.mask_ch = mask_ch; a.pstride = pstride;
-    const size_t plane = (size_t)H * W;
-    const void *ptrs[] = {img, mask, target, out, grad_out, grad_img};
-    const size_t hist_bytes = (size_t)a.ch.hist_total * NT * sizeof(F2);
-    int vec = pick_vec_flat(ptrs, 6, plane);
-    const bool small_chain = n_ops <= 2;
-    if (!small_chain && vec > 2) vec = 2;              // register budget: KMAX x 3 x VEC saved inputs
-    if (a.ch.sharp < 0) {
-        geom_flat(a.g, B, H, W, vec);
-        return mask ? launch_bwd_flat_mask(vec, small_chain, a, hist_bytes, stream)
-                    : launch_bwd_flat_nomask(vec, small_chain, a, hist_bytes, stream);
-    }
-    while (vec > 1 && W % vec != 0) vec >>= 1;
-    // largest tile whose X (tile+2), GY (tile+1) [, GD] regions and curve moments leave room for 2 CTAs / SM
-    static const int cand[4][2] = {{32, 128}, {32, 64}, {16, 64}, {32, 32}};
-    const int hgx = vec == 1 ? 2 : 1;
-    size_t smem = 0;
-    for (int i = 0; i < 4; ++i) {
-        geom_2d(a.g, B, H, W, vec, cand[i][1], cand[i][0], hgx);
-        const size_t xs = (size_t)3 * (a.g.TH + 4) * (a.g.TWg + 2 * hgx) * vec;
-        const size_t gs = (size_t)3 * (a.g.TH + 2) * (a.g.TWg + 2) * vec;
-        smem = hist_bytes + (xs + gs * (mask ? 2 : 1)) * sizeof(float);
-        if (smem <= 110 * 1024) break;
-    }
-    // several tiles per CTA amortise the per-CTA work (tables, moment zeroing and reduction); keep >= ~4 waves
-    const long long total_tiles = (long long)a.g.ntiles * B;
-    int tpc = (int)(total_tiles / (NUM_SMS * 2 * 4));
-    if (tpc < 1) tpc = 1;
-    if (tpc > 32) tpc = 32;
-    a.g.tiles_per_cta = tpc;
-    a.g.nchunks = (a.g.ntiles + tpc - 1) / tpc;
-    return mask ? launch_bwd_sharp_mask(vec, small_chain, a, smem, stream)
-                : launch_bwd_sharp_nomask(vec, small_chain, a, smem, stream);
 }
 
 int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long long n, void *ws, size_t ws_bytes,

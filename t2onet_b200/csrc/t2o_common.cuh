@@ -17,10 +17,8 @@ struct ChainDesc {
     int n;                  // number of operators
     int L;                  // curve steps
     int sharp;              // index of the (single) sharpness operator, or -1
-    int hist_total;         // curve-moment floats per thread (backward)
     int op[MAX_CHAIN];
     int poff[MAX_CHAIN];    // column of the operator's first parameter
-    int hoff[MAX_CHAIN];    // first curve-moment slot of the operator (backward)
 };
 
 // Launch geometry.  Without sharpness an image is a flat array of `ngroups` VEC-pixel groups and
@@ -31,7 +29,7 @@ struct Geom {
     int tiles_x, tiles_y;   // 2-D tiling only
     int ntiles;             // tiles per image
     int nchunks;            // CTAs per image (gridDim.x): nchunks * tiles_per_cta >= ntiles
-    int tiles_per_cta;      // 2-D backward: tiles a CTA walks through (amortises per-CTA setup / reduction)
+    int tiles_per_cta;
     int TH, TWg;            // 2-D tile, in rows / groups
     int tile_groups;        // 1-D tiling
     long long ngroups;      // 1-D tiling: H*W / VEC

@@ -18,7 +18,7 @@
 //     (f*s of hsv_to_rgb is u_c/(v+eps) exactly; the sector select is continuous, so no branch)
 //   Contrast:         0.5 - 0.5 cos(pi L) = sin^2(pi L / 2), odd/even polynomials in L on [0, 1]
 //   Curves:           j = floor(L x);  y = k'_j x + Q_j,  k' = k L/S, Q_j = L/S sum_{i<j} k_i/L - k'_j j/L
-//   Curve param grads: per bin j the moments A_j = sum g, Bx_j = sum g x; per curve C = sum g y
+//   Curve param grads: G_i = sum g clamp(L x - i, 0, 1), C = sum g y  ->  dLoss/dk_i = (G_i - C) / S
 //
 // The instruction budget matters: at the HBM roofline a B200 SM has ~2 cycles per pixel, so the
 // hot paths avoid IEEE division (MUFU.RCP, 1 ulp), libm trigonometry and float->int conversions.
@@ -42,7 +42,7 @@ constexpr int MAX_CHAIN = 8;
 constexpr int MAX_L = 8;
 constexpr int TAB = 64;    // floats in one (image, op) table
 constexpr int CT = 20;     // floats in one curve table: (k', Q) x 9 interleaved, 1/S, L/S
-constexpr int NBIN = MAX_L + 1;   // histogram bins of one curve (bin L collects x == 1.0, merged into L-1)
+constexpr int NBIN = MAX_L + 1;   // segments of one curve table (entry L repeats L-1: it serves x == 1.0)
 constexpr float HSV_EPS = 1e-6f;     // kornia.rgb_to_hsv eps
 constexpr float LUM_EPS = 1e-6f;     // models/operators.py:244
 constexpr float CURVE_EPS = 1e-10f;  // models/operators.py:579,610
@@ -59,8 +59,6 @@ T2O_HD int op_num_params(int op, int L) {
     }
 }
 T2O_HD bool op_is_curve(int op) { return op == OP_TONE || op == OP_COLOR; }
-// float2 histogram slots (A_j, Bx_j) a curve operator needs per thread in the backward pass
-T2O_HD int op_hist_slots(int op) { return op == OP_TONE ? NBIN : (op == OP_COLOR ? 3 * NBIN : 0); }
 
 struct F2 { float a, b; };   // == float2 without needing vector_types.h on the host
 
@@ -296,23 +294,40 @@ T2O_HD void blend_bwd(float y, float x, float m, float g, float &gy, float &gd) 
     gd = HM ? gz * (1.0f - m) : 0.0f;
 }
 
-// Histogram sink for the curve moments: `h[slot * stride]` is an (A, Bx) pair private to the thread.
-struct Hist {
-    F2 *h;
-    int stride;
-    T2O_HD void add(int slot, float a, float b) const {
-        F2 v = h[slot * stride];
-        v.a += a; v.b += b;
-        h[slot * stride] = v;
-    }
+// Per-thread parameter-gradient accumulators: one slot per operator TYPE (a backward launch holds each
+// operator type at most once, the binding splits longer chains), statically indexed so they live in registers.
+// Curves: G[i] = sum g * clamp(L x - i, 0, 1) and C = sum g * y, from which dLoss/dk_i = (G[i] - C) / S
+// (y = sum_i k_i clamp(L x - i, 0, 1) / S with S = sum k + eps: models/operators.py:579-585, 610-616).
+struct GradAcc {
+    float color[3][MAX_L];
+    float colorC[3];
+    float bright, contrast, satur, expo, sharp;
+    float tone[MAX_L];
+    float toneC;
+    float wb[3];
 };
+constexpr int ACC_SLOTS = 48;     // slot layout used by the kernels' reduction (see acc_slot_* below)
+constexpr int ACC_COLOR = 0, ACC_COLOR_C = 24, ACC_BRIGHT = 27, ACC_CONTRAST = 28, ACC_SATUR = 29, ACC_EXPO = 30,
+              ACC_SHARP = 31, ACC_TONE = 32, ACC_TONE_C = 40, ACC_WB = 41;
+T2O_HD void acc_zero(GradAcc &a) {
+    for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L; ++i) a.color[c][i] = 0.0f; a.colorC[c] = 0.0f; a.wb[c] = 0.0f; }
+    for (int i = 0; i < MAX_L; ++i) a.tone[i] = 0.0f;
+    a.toneC = 0.0f; a.bright = 0.0f; a.contrast = 0.0f; a.satur = 0.0f; a.expo = 0.0f; a.sharp = 0.0f;
+}
+T2O_HD void acc_to_slots(const GradAcc &a, float *v) {     // v[ACC_SLOTS]
+    for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L; ++i) v[ACC_COLOR + c * MAX_L + i] = a.color[c][i]; v[ACC_COLOR_C + c] = a.colorC[c]; v[ACC_WB + c] = a.wb[c]; }
+    for (int i = 0; i < MAX_L; ++i) v[ACC_TONE + i] = a.tone[i];
+    v[ACC_TONE_C] = a.toneC; v[ACC_BRIGHT] = a.bright; v[ACC_CONTRAST] = a.contrast; v[ACC_SATUR] = a.satur;
+    v[ACC_EXPO] = a.expo; v[ACC_SHARP] = a.sharp;
+    for (int i = ACC_WB + 3; i < ACC_SLOTS; ++i) v[i] = 0.0f;
+}
 
 // Each *_bwd takes the operator input x = (r,g,b), the mask, the upstream gradient
-// (gr,gg,gb) = dLoss/d(out) and returns dLoss/d(x) in place.  `acc` receives the parameter
-// gradient contributions when `own` is true (halo pixels recompute but must not accumulate).
+// (gr,gg,gb) = dLoss/d(out) and returns dLoss/d(x) in place.  The parameter-gradient contribution goes
+// to `acc` when `own` is true (halo pixels recompute but must not accumulate).
 template <bool HM>
 T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
-                           float &gr, float &gg, float &gb, float *acc, bool own) {
+                           float &gr, float &gg, float &gb, float &acc, bool own) {
     const float q = tab[1];
     const float v = max3(r, g, b), mn = min3(r, g, b);
     const float inv = rcp(v + HSV_EPS);
@@ -326,7 +341,7 @@ T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr
     blend_bwd<HM>(v2 * wg, g, mg, gg, gyg, gdg);
     blend_bwd<HM>(v2 * wb, b, mb, gb, gyb, gdb);
     const float G = gyr * wr + gyg * wg + gyb * wb;                   // dLoss/d v'
-    if (own) acc[0] += ip ? v * G : 0.0f;
+    if (own) acc += ip ? v * G : 0.0f;
     if (v == mn) {          // gray pixel: the reference routes everything through max -> channel 0
         gr = gdr + G * ipq; gg = gdg; gb = gdb;
         return;
@@ -341,7 +356,7 @@ T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr
 
 template <bool HM>
 T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
-                           float &gr, float &gg, float &gb, float *acc, bool own) {
+                           float &gr, float &gg, float &gb, float &acc, bool own) {
     const float q = tab[1];
     const float v = max3(r, g, b), mn = min3(r, g, b);
     const float d = v - mn;
@@ -364,7 +379,7 @@ T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr
     const float Su = gyr * ur + gyg * ug + gyb * ub;
     float rho_v, rho_mn;
     if (in01(t)) {          // s' = s q  ->  rho = q / (v + eps)
-        if (own) acc[0] -= v * inv * Su;
+        if (own) acc -= v * inv * Su;
         rho_v = -q * inv * inv; rho_mn = 0.0f;
     } else if (t > 1.0f) {  // s' = 1    ->  rho = 1 / d
         rho_v = -id * id; rho_mn = id * id;
@@ -381,7 +396,7 @@ T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr
 
 template <bool HM>
 T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
-                         float &gr, float &gg, float &gb, float *acc, bool own) {
+                         float &gr, float &gg, float &gb, float &acc, bool own) {
     const float p = tab[0];
     const float lum = lum_rn(r, g, b);
     const float L = sat01(lum);
@@ -400,16 +415,16 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     blend_bwd<HM>(g * F, g, mg, gg, gyg, gdg);
     blend_bwd<HM>(b * F, b, mb, gb, gyb, gdb);
     const float Sgc = gyr * r + gyg * g + gyb * b;
-    if (own) acc[0] = fmaf(R - 1.0f, Sgc, acc[0]);
+    if (own) acc = fmaf(R - 1.0f, Sgc, acc);
     const float k = p * dR * f0 * f1 * Sgc;
     gr = fmaf(gyr, F, gdr) + 0.27f * k;
     gg = fmaf(gyg, F, gdg) + 0.67f * k;
     gb = fmaf(gyb, F, gdb) + 0.06f * k;
 }
 
-// one channel of a curve operator; accC accumulates C = sum g*y of this curve
+// one channel of a curve operator: G[i] += g * clamp(L x - i, 0, 1), accC += g * y
 template <bool HM>
-T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, const Hist &hist, float &accC, bool own) {
+T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, float *G, float &accC, bool own) {
     const float xs = sat01(x);
     float t, tf;
     const int j = curve_bin(xs, L, t, tf);
@@ -417,50 +432,38 @@ T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, const 
     const float y = fmaf(seg.a, xs, seg.b);
     float gy, gd;
     blend_bwd<HM>(y, x, m, g, gy, gd);
-    if (own) {
-        hist.add(j, gy, gy * xs);
-        accC = fmaf(gy, y, accC);
-    }
+    const float ga = own ? gy : 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < MAX_L; ++i) G[i] = fmaf(ga, sat01(t - (float)i), G[i]);
+    accC = fmaf(ga, y, accC);
     float slope = seg.a;
     if (t == tf && j > 0 && j < L) slope += ct[2 * (j - 1)];        // exact knot: both clamp terms pass
     return gd + (in01(x) ? gy * slope : 0.0f);
 }
 
-// dLoss/dk_i of one curve from its block-reduced moments A[NBIN], Bx[NBIN] and C.  Bin L holds the
-// inputs equal to 1.0; they act like bin L-1 with the full 1/L step, so the two bins are merged.
-T2O_HD void curve_param_grad(const float *ct, int L, const float *A, const float *Bx, float C, float *gk) {
-    const float invS = ct[18], scale = ct[19];
-    float tail = 0.0f;                       // sum_{j > i} A_j
-    for (int i = L - 1; i >= 0; --i) {
-        const float Ai = A[i] + (i == L - 1 ? A[L] : 0.0f);
-        const float Bi = Bx[i] + (i == L - 1 ? Bx[L] : 0.0f);
-        const float x0 = (float)i / (float)L;
-        const float sgc = (Bi - x0 * Ai) + tail / (float)L;
-        gk[i] = scale * sgc - invS * C;
-        tail += Ai;
-    }
-}
+// dLoss/dk_i of one curve from its reduced accumulators: (G[i] - C) / S
+T2O_HD float curve_param_grad(const float *ct, float Gi, float C) { return ct[18] * (Gi - C); }
 
 template <bool HM>
 T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, float b,
                           float mr, float mg, float mb,
-                          float &gr, float &gg, float &gb, float *acc, const Hist &hist, bool own) {
+                          float &gr, float &gg, float &gb, GradAcc &A, bool own) {
     switch (op) {
-        case OP_BRIGHTNESS: brightness_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
-        case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
-        case OP_SATURATION: saturation_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, acc, own); break;
+        case OP_BRIGHTNESS: brightness_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.bright, own); break;
+        case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.contrast, own); break;
+        case OP_SATURATION: saturation_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.satur, own); break;
         case OP_TONE:
-            gr = curve_bwd<HM>(tab, L, r, mr, gr, hist, acc[0], own);
-            gg = curve_bwd<HM>(tab, L, g, mg, gg, hist, acc[0], own);
-            gb = curve_bwd<HM>(tab, L, b, mb, gb, hist, acc[0], own);
+            gr = curve_bwd<HM>(tab, L, r, mr, gr, A.tone, A.toneC, own);
+            gg = curve_bwd<HM>(tab, L, g, mg, gg, A.tone, A.toneC, own);
+            gb = curve_bwd<HM>(tab, L, b, mb, gb, A.tone, A.toneC, own);
             break;
-        case OP_COLOR: {
-            Hist h1{hist.h + NBIN * hist.stride, hist.stride}, h2{hist.h + 2 * NBIN * hist.stride, hist.stride};
-            gr = curve_bwd<HM>(tab, L, r, mr, gr, hist, acc[0], own);
-            gg = curve_bwd<HM>(tab + CT, L, g, mg, gg, h1, acc[1], own);
-            gb = curve_bwd<HM>(tab + 2 * CT, L, b, mb, gb, h2, acc[2], own);
+        case OP_COLOR:
+            gr = curve_bwd<HM>(tab, L, r, mr, gr, A.color[0], A.colorC[0], own);
+            gg = curve_bwd<HM>(tab + CT, L, g, mg, gg, A.color[1], A.colorC[1], own);
+            gb = curve_bwd<HM>(tab + 2 * CT, L, b, mb, gb, A.color[2], A.colorC[2], own);
             break;
-        }
         case OP_WHITE: {
             float gy, gd;
             blend_bwd<HM>(1.0f, r, mr, gr, gy, gd); gr = gd;
@@ -474,7 +477,7 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
             blend_bwd<HM>(r * e, r, mr, gr, gyr, gdr);
             blend_bwd<HM>(g * e, g, mg, gg, gyg, gdg);
             blend_bwd<HM>(b * e, b, mb, gb, gyb, gdb);
-            if (own) acc[0] += LN2_F * e * (gyr * r + gyg * g + gyb * b);
+            if (own) A.expo += LN2_F * e * (gyr * r + gyg * g + gyb * b);
             gr = fmaf(gyr, e, gdr); gg = fmaf(gyg, e, gdg); gb = fmaf(gyb, e, gdb);
             break;
         }
@@ -483,7 +486,7 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
             blend_bwd<HM>(r * tab[0], r, mr, gr, gyr, gdr);
             blend_bwd<HM>(g * tab[1], g, mg, gg, gyg, gdg);
             blend_bwd<HM>(b * tab[2], b, mb, gb, gyb, gdb);
-            if (own) { acc[0] = fmaf(gyr, r, acc[0]); acc[1] = fmaf(gyg, g, acc[1]); acc[2] = fmaf(gyb, b, acc[2]); }
+            if (own) { A.wb[0] = fmaf(gyr, r, A.wb[0]); A.wb[1] = fmaf(gyg, g, A.wb[1]); A.wb[2] = fmaf(gyb, b, A.wb[2]); }
             gr = fmaf(gyr, tab[0], gdr); gg = fmaf(gyg, tab[1], gdg); gb = fmaf(gyb, tab[2], gdb);
             break;
         }

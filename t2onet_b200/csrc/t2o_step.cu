@@ -1,0 +1,197 @@
+// t2o_step.cu -- host side of t2o_chain_backward: geometry, workspace carving, launch selection for the fused
+// forward + L1 + backward kernels of t2o_step_kernels.cuh.
+#include "t2o_step_kernels.cuh"
+
+namespace t2o {
+
+size_t chain_workspace_bytes(int B, int H, int W, int pstride);
+struct Workspace {
+    unsigned int *counters;
+    float *part_l1, *part_gp;
+};
+Workspace carve_workspace(void *ws, int B, int H, int W);
+size_t max_tiles(int H, int W);
+
+static int make_step_desc(int n_ops, const int *op_ids, const int *param_off, int L, int pstride, StepDesc &d) {
+    if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids || !param_off) return T2O_ERR_INVALID_ARG;
+    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
+    if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
+    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1;
+    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
+    for (int i = 0; i < ACC_SLOTS; ++i) d.slot_col[i] = -1;
+    bool seen[OP_COUNT] = {false};
+    for (int k = 0; k < n_ops; ++k) {
+        const int op = op_ids[k];
+        if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
+        if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
+        const int po = param_off[k];
+        if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
+        d.op[k] = op; d.poff[k] = po;
+        if (op < 0) continue;
+        // one accumulator slot per operator type: a launch holds each type at most once (the binding splits)
+        if (seen[op]) return T2O_ERR_UNSUPPORTED;
+        seen[op] = true;
+        switch (op) {
+            case OP_SHARPNESS: d.sharp = k; d.slot_col[ACC_SHARP] = po; break;
+            case OP_BRIGHTNESS: d.slot_col[ACC_BRIGHT] = po; break;
+            case OP_CONTRAST: d.slot_col[ACC_CONTRAST] = po; break;
+            case OP_SATURATION: d.slot_col[ACC_SATUR] = po; break;
+            case OP_EXPOSURE: d.slot_col[ACC_EXPO] = po; break;
+            case OP_WHITEBALANCE: for (int c = 0; c < 3; ++c) d.slot_col[ACC_WB + c] = po + c; break;
+            case OP_TONE:
+                d.k_tone = k;
+                for (int i = 0; i < L; ++i) d.slot_col[ACC_TONE + i] = po + i;
+                break;
+            case OP_COLOR:
+                d.k_color = k;
+                for (int c = 0; c < 3; ++c)
+                    for (int i = 0; i < L; ++i) d.slot_col[ACC_COLOR + c * MAX_L + i] = po + c * L + i;
+                break;
+            default: break;     // white: no parameter gradient (models/operators.py:510-512 ignores the parameter)
+        }
+    }
+    return T2O_OK;
+}
+
+static int pick_vec(const void *const *ptrs, int nptr, size_t plane) {
+    int vec = (plane % 4 == 0) ? 4 : (plane % 2 == 0 ? 2 : 1);
+    for (int i = 0; i < nptr; ++i) {
+        if (!ptrs[i]) continue;
+        const uintptr_t a = (uintptr_t)ptrs[i];
+        while (vec > 1 && (a % (vec * 4)) != 0) vec >>= 1;
+    }
+    return vec;
+}
+
+// resident CTAs per SM of a kernel at a given dynamic shared memory size (cached by the caller's static)
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SNT, smem) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+static void geom_step_flat(StepGeom &g, int B, int H, int W, int vec, int slots) {
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.H = H; g.W = W;
+    const long long plane = (long long)H * W;
+    g.ngroups = plane / vec;
+    const long long total = g.ngroups * B;
+    // one wave of CTAs unless a thread would then own more than ~32 groups
+    long long waves = total / ((long long)slots * SNT * 32);
+    if (waves < 1) waves = 1;
+    if (waves > 16) waves = 16;
+    long long cg = (total + slots * waves - 1) / (slots * waves);
+    const long long quantum = SNT;
+    cg = (cg + quantum - 1) / quantum * quantum;
+    const long long min_groups = (1024 + vec - 1) / vec;       // a chunk holds >= 1024 pixels (bounds the workspace)
+    if (cg < min_groups) cg = (min_groups + quantum - 1) / quantum * quantum;
+    g.chunk_groups = (int)cg;
+    g.nchunks = (int)((g.ngroups + cg - 1) / cg);
+    if (g.nchunks < 1) g.nchunks = 1;
+}
+
+static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots) {
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.H = H; g.W = W;
+    g.Wg = W / vec;
+    if (g.Wg <= 32) {
+        int lg = 0;
+        while ((1 << lg) < g.Wg) ++lg;
+        g.lgTWp = lg; g.HL = 0; g.IW = g.Wg; g.strips = 1;
+    } else {
+        g.lgTWp = 5; g.HL = vec >= 2 ? 1 : 2; g.IW = 32 - 2 * g.HL;
+        g.strips = (g.Wg + g.IW - 1) / g.IW;
+    }
+    g.RPW = 32 >> g.lgTWp;
+    g.R = SNW * g.RPW;
+    g.RING = g.R + 2;
+    // band height: minimise waves x (steps + 1) over the number of bands; a band holds >= 16 rows
+    long long best = -1;
+    int best_hb = H;
+    const int max_nb = H / 16 > 1 ? H / 16 : 1;
+    for (int nb = 1; nb <= max_nb; ++nb) {
+        const int hb = (H + nb - 1) / nb;
+        const int bands = (H + hb - 1) / hb;
+        const int steps = (hb + 4 + g.R - 1) / g.R;
+        const long long ctas = (long long)B * g.strips * bands;
+        const long long waves = (ctas + slots - 1) / slots;
+        const long long cost = waves * (steps + 1);
+        if (best < 0 || cost < best) { best = cost; best_hb = hb; }
+    }
+    g.HB = best_hb;
+    g.bands = (H + g.HB - 1) / g.HB;
+    g.steps = (g.HB + 4 + g.R - 1) / g.R;
+    g.nchunks = g.strips * g.bands;
+}
+
+static size_t rows_smem_bytes(const StepGeom &g, const StepDesc &d, int vec, bool has_mask) {
+    const int TWp = 1 << g.lgTWp;
+    const size_t ringf = (size_t)g.RING * 3 * (TWp + 2) * vec;
+    const size_t ntp = d.sharp > 1 ? d.sharp - 1 : 0;
+    const size_t ntq = d.n - d.sharp - 1;
+    return ((has_mask ? 3 : 2) * ringf + ntp * g.RING * 3 * TWp * vec + ntq * 3 * SNT * vec) * sizeof(float);
+}
+
+template <int VEC, bool HM>
+static int launch_step(StepArgs &a, cudaStream_t stream) {
+    const bool rows = a.ch.sharp >= 0;
+    const int B = a.g.B, H = a.g.H, W = a.g.W;
+    size_t smem;
+    if (!rows) {
+        smem = (size_t)a.ch.n * 3 * SNT * VEC * sizeof(float);
+        int st = step_set_smem(step_flat_kernel<VEC, HM>, smem);
+        if (st) return st;
+        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM>, smem));
+        dim3 grid(a.g.nchunks, B);
+        step_flat_kernel<VEC, HM><<<grid, SNT, smem, stream>>>(a);
+    } else {
+        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * 2);
+        smem = rows_smem_bytes(a.g, a.ch, VEC, HM);
+        int st = step_set_smem(step_sharp_kernel<VEC, HM>, smem);
+        if (st) return st;
+        const int res = resident_ctas(step_sharp_kernel<VEC, HM>, smem);
+        if (res != 2) geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * res);     // the ring sizes do not depend on the band split
+        dim3 grid(a.g.nchunks, B);
+        step_sharp_kernel<VEC, HM><<<grid, SNT, smem, stream>>>(a);
+    }
+    T2O_CUDA_OK(cudaGetLastError());
+    return T2O_OK;
+}
+
+template <bool HM>
+static int launch_step_vec(int vec, StepArgs &a, cudaStream_t stream) {
+    if (vec == 4) return launch_step<4, HM>(a, stream);
+    if (vec == 2) return launch_step<2, HM>(a, stream);
+    return launch_step<1, HM>(a, stream);
+}
+
+int chain_backward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
+                   const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
+                   float *grad_params, float *grad_img, float *out, float *l1_sum,
+                   int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    int st = make_step_desc(n_ops, op_ids, param_off, L, pstride, a.ch);
+    if (st != T2O_OK) return st;
+    if (!img || B < 1 || H < 1 || W < 1 || (pstride > 0 && !params)) return T2O_ERR_INVALID_ARG;
+    if (mask && mask_ch != 1 && mask_ch != 3) return T2O_ERR_INVALID_ARG;
+    if (!grad_out && (!target || !grad_l1)) return T2O_ERR_INVALID_ARG;
+    if (l1_sum && !target) return T2O_ERR_INVALID_ARG;
+    if (!grad_params && !grad_img) return T2O_ERR_INVALID_ARG;
+    if (!ws || ws_bytes < chain_workspace_bytes(B, H, W, pstride)) return T2O_ERR_WORKSPACE;
+    if (B > 65535) return T2O_ERR_UNSUPPORTED;
+    Workspace w = carve_workspace(ws, B, H, W);
+    a.img = img; a.mask = mask; a.params = params; a.grad_out = grad_out; a.target = target; a.grad_l1 = grad_l1;
+    a.grad_params = grad_params; a.grad_img = grad_img; a.out = out; a.l1_sum = l1_sum;
+    a.part_l1 = w.part_l1; a.part_gp = w.part_gp; a.counters = w.counters; a.mask_ch = mask_ch; a.pstride = pstride;
+    a.g.B = B; a.g.H = H; a.g.W = W;
+    const size_t plane = (size_t)H * W;
+    const void *ptrs[] = {img, mask, target, out, grad_out, grad_img};
+    int vec = pick_vec(ptrs, 6, plane);
+    if (a.ch.sharp >= 0)
+        while (vec > 1 && W % vec != 0) vec >>= 1;
+    return mask ? launch_step_vec<true>(vec, a, stream) : launch_step_vec<false>(vec, a, stream);
+}
+
+}  // namespace t2o

@@ -1,0 +1,500 @@
+// t2o_step_kernels.cuh -- the fused "step" kernels for sm_100a: operator chain forward + L1 + backward in ONE
+// launch (t2o_chain_backward).  Instantiated by t2o_step.cu.
+//
+// Replaces: K x Executor.execute (executors/executor.py:33-55 -> models/operators.py:112-131), the L1 of
+// get_dist / the training loss (utils/beam_search.py:170-173, experiments/t2onet/train_seq2seqL1.py:85) and
+// torch autograd through all of it.
+//
+// Design:
+//   * a thread owns VEC consecutive pixels of the three planes (128-bit coalesced LDG/STG for VEC = 4);
+//   * the chain is a runtime loop over operators with ONE uniform switch per loop iteration; the operator
+//     inputs the backward sweep needs (the "tape") live in shared memory, not in registers, so the loop is
+//     not unrolled and the kernel keeps 4-pixel groups with <= 128 registers;
+//   * parameter gradients accumulate in registers, one slot per operator type (GradAcc), and are reduced
+//     once per CTA: 32-value warp transpose-reductions -> shared -> one partial row per CTA -> the last CTA
+//     of the image sums the partial rows in a fixed order (deterministic, no float atomics);
+//   * a sharpness operator turns the kernel into a row pipeline down a column strip: every warp owns one
+//     image row per step; X = (operators before the stencil)(img) is produced one step ahead into a ring of
+//     R + 2 rows, the stencil + the operators after it + the loss + their backward run one row behind and
+//     leave the gradient at the stencil output in a second ring, the transposed stencil and the backward of
+//     the operators before the stencil run two rows behind, reading their tape from a third ring.  Nothing is
+//     recomputed except the 4 halo rows per band and the 2 halo lanes per strip.
+#pragma once
+#include <cstdio>
+#include <cstring>
+
+#include "t2o_common.cuh"
+#include "../../include/t2o.h"
+
+namespace t2o {
+
+constexpr int SNT = 256;          // threads per CTA
+constexpr int SNW = SNT / 32;     // warps per CTA = image rows per pipeline step (x rows per warp)
+
+struct StepDesc {
+    int n, L, sharp;              // operators, curve steps, index of the sharpness operator or -1
+    int k_tone, k_color;          // chain position of the tone / color operator or -1 (their 1/S lives in the tables)
+    int op[MAX_CHAIN];
+    int poff[MAX_CHAIN];
+    int slot_col[ACC_SLOTS];      // parameter column fed by each accumulator slot, or -1
+};
+
+struct StepGeom {
+    int B, H, W;
+    // flat (no stencil): an image is `ngroups` VEC-pixel groups, a CTA takes a contiguous chunk of them
+    long long ngroups;
+    int chunk_groups;
+    int nchunks;                  // CTAs per image (both tilings)
+    // row pipeline (one stencil)
+    int Wg;                       // groups per image row
+    int lgTWp;                    // log2 of the lanes one row occupies (32 lanes unless the image is narrower)
+    int RPW;                      // rows per warp = 32 >> lgTWp
+    int R;                        // rows per step = SNW * RPW
+    int RING;                     // R + 2
+    int HL;                       // halo lanes on each side of a strip (0: the strip spans the image width)
+    int IW;                       // interior lanes (groups) per strip
+    int strips, bands, HB, steps;
+};
+
+struct StepArgs {
+    StepDesc ch;
+    StepGeom g;
+    const float *img, *mask, *params, *grad_out, *target, *grad_l1;
+    float *grad_params, *grad_img, *out, *l1_sum;
+    float *part_l1, *part_gp;
+    unsigned int *counters;
+    int mask_ch, pstride;
+};
+
+// ---------------------------------------------------------------- operator dispatch over one pixel group
+template <int VEC, bool HM>
+__device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, float (&x)[3][VEC], const float (&m)[3][VEC]) {
+#define T2O_CASE(OPC)                                                                                          \
+    case OPC:                                                                                                  \
+        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                        \
+            op_apply<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);                   \
+        break;
+    switch (op) {
+        T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
+        T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+        default: break;
+    }
+#undef T2O_CASE
+}
+
+template <int VEC, bool HM>
+__device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, const float (&x)[3][VEC],
+                                           const float (&m)[3][VEC], float (&g)[3][VEC], GradAcc &A, bool own) {
+#define T2O_CASE(OPC)                                                                                   \
+    case OPC:                                                                                           \
+        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                 \
+            pointwise_bwd<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],        \
+                              g[0][v], g[1][v], g[2][v], A, own);                                       \
+        break;
+    switch (op) {
+        T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
+        T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+        default: break;
+    }
+#undef T2O_CASE
+}
+
+template <int VEC, bool HM>
+__device__ __forceinline__ void ldm(const float *mask_b, int mask_ch, size_t plane, size_t off, float (&m)[3][VEC]) {
+    if constexpr (HM) ld_mask<VEC>(mask_b, mask_ch, plane, off, m);
+}
+
+// tape entries: three VEC-wide vectors `cstride` vectors apart
+template <int VEC>
+__device__ __forceinline__ void tape_st(typename VecT<VEC>::type *p, int cstride, const float (&x)[3][VEC]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st_vec<VEC>(reinterpret_cast<float *>(p + c * cstride), x[c]);
+}
+template <int VEC>
+__device__ __forceinline__ void tape_ld(const typename VecT<VEC>::type *p, int cstride, float (&x)[3][VEC]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lds_vec<VEC>(reinterpret_cast<const float *>(p + c * cstride), x[c]);
+}
+
+template <int VEC>
+__device__ __forceinline__ void zero3(float (&x)[3][VEC]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[c][v] = 0.0f;
+}
+
+// upstream gradient of a pixel group: explicit grad_out, or the fused L1: gl1 * sign(out - target)
+template <int VEC>
+__device__ __forceinline__ void upstream_grad(const float *go_b, const float *tgt_b, size_t plane, size_t off, float gl1,
+                                              const float (&x)[3][VEC], float (&g)[3][VEC], float &l1, bool own) {
+    if (go_b) {
+        ld_px<VEC>(go_b, plane, off, g);
+        if (tgt_b && own) {
+            float t[3][VEC];
+            ld_px<VEC>(tgt_b, plane, off, t);
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) s += fabsf(x[c][v] - t[c][v]);
+            l1 += s;
+        }
+    } else {
+        float t[3][VEC];
+        ld_px<VEC>(tgt_b, plane, off, t);
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float d = x[c][v] - t[c][v];
+                g[c][v] = d != 0.0f ? copysignf(gl1, gl1 < 0.0f ? -d : d) : 0.0f;
+                s += fabsf(d);
+            }
+        if (own) l1 += s;
+    }
+}
+
+// 5-point stencil of one plane around a VEC-pixel group of a ring row.  `row` points at the group's first
+// float; the rows above / below are `up` / `dn`; row[-1] and row[VEC] are always addressable (zero pads).
+template <int VEC>
+__device__ __forceinline__ void stencil_ring(const float *row, const float *up, const float *dn,
+                                             float (&ctr)[VEC], float (&lap)[VEC]) {
+    float u[VEC], d[VEC];
+    lds_vec<VEC>(row, ctr);
+    lds_vec<VEC>(up, u);
+    lds_vec<VEC>(dn, d);
+    const float lf = row[-1], rt = row[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const float l = v > 0 ? ctr[v - 1] : lf;
+        const float r = v < VEC - 1 ? ctr[v + 1] : rt;
+        lap[v] = laplace(ctr[v], u[v], d[v], l, r);
+    }
+}
+
+// ---------------------------------------------------------------- warp transpose-reductions
+// On return lane l holds sum over the warp of v[l] (N = 32), or of v[l & 15] (N = 16): N - 1 shuffles.
+template <int N>
+__device__ __forceinline__ float warp_reduce_multi(float *v, int lane) {
+#pragma unroll
+    for (int off = N / 2; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = v[0];
+    if (N == 16) r += __shfl_xor_sync(0xffffffffu, r, 16);
+    return r;
+}
+
+struct StepShared {
+    float tabs[MAX_CHAIN][TAB];
+    float wred[SNW][ACC_SLOTS];
+    float tot[ACC_SLOTS];
+    float rowbuf[MAX_PSTRIDE];
+    float red[32];
+    int last_flag;
+};
+
+// CTA partials of the parameter gradients and the L1, then "the last CTA of the image finishes"
+__device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh, GradAcc &A, float l1, int b, int chunk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = a.g.nchunks;
+    if (a.grad_params) {
+        float v[ACC_SLOTS];
+        acc_to_slots(A, v);
+        const float r0 = warp_reduce_multi<32>(v, lane);
+        const float r1 = warp_reduce_multi<16>(v + 32, lane);
+        sh.wred[warp][lane] = r0;
+        if (lane < 16) sh.wred[warp][32 + lane] = r1;
+        for (int i = tid; i < MAX_PSTRIDE; i += SNT) sh.rowbuf[i] = 0.0f;
+        __syncthreads();
+        if (tid < ACC_SLOTS) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SNW; ++w) s += sh.wred[w][tid];
+            sh.tot[tid] = s;
+        }
+        __syncthreads();
+        if (tid < ACC_SLOTS) {
+            const int col = a.ch.slot_col[tid];
+            if (col >= 0) {
+                float val = sh.tot[tid];
+                if (tid < ACC_COLOR_C) {
+                    const int c = tid / MAX_L;
+                    val = curve_param_grad(sh.tabs[a.ch.k_color] + c * CT, val, sh.tot[ACC_COLOR_C + c]);
+                } else if (tid >= ACC_TONE && tid < ACC_TONE_C) {
+                    val = curve_param_grad(sh.tabs[a.ch.k_tone], val, sh.tot[ACC_TONE_C]);
+                }
+                sh.rowbuf[col] = val;
+            }
+        }
+        __syncthreads();
+        float *prow = a.part_gp + ((size_t)b * nchunks + chunk) * a.pstride;
+        for (int i = tid; i < a.pstride; i += SNT) prow[i] = sh.rowbuf[i];
+    }
+    if (a.l1_sum) {
+        const float s = block_sum(l1, sh.red);
+        if (tid == 0) a.part_l1[(size_t)b * nchunks + chunk] = s;
+    }
+    if (a.grad_params || a.l1_sum) {
+        if (arrive_is_last(a.counters + b, (unsigned)nchunks, &sh.last_flag)) {
+            if (a.grad_params)
+                reduce_columns(a.part_gp + (size_t)b * nchunks * a.pstride, nchunks, a.pstride,
+                               a.grad_params + (size_t)b * a.pstride);
+            if (a.l1_sum) {
+                float v = 0.0f;
+                for (int t = tid; t < nchunks; t += SNT) v += __ldcg(a.part_l1 + (size_t)b * nchunks + t);
+                v = block_sum(v, sh.red);
+                if (tid == 0) a.l1_sum[b] = v;
+            }
+        }
+    }
+}
+
+// =========================================================================================== flat (no stencil)
+template <int VEC, bool HM>
+__global__ void __launch_bounds__(SNT, 2) step_flat_kernel(const __grid_constant__ StepArgs a) {
+    using V = typename VecT<VEC>::type;
+    extern __shared__ __align__(16) float dyn_smem[];
+    __shared__ __align__(16) StepShared sh;
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int n = a.ch.n, L = a.ch.L;
+    const size_t plane = (size_t)a.g.H * a.g.W;
+    const float *img_b = a.img + (size_t)b * 3 * plane;
+    const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
+    const float *go_b = a.grad_out ? a.grad_out + (size_t)b * 3 * plane : nullptr;
+    float *out_b = a.out ? a.out + (size_t)b * 3 * plane : nullptr;
+    float *gi_b = a.grad_img ? a.grad_img + (size_t)b * 3 * plane : nullptr;
+    const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
+    const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
+
+    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, sh.tabs[tid]);
+    __syncthreads();
+
+    V *tape = reinterpret_cast<V *>(dyn_smem) + tid;       // input of operator k, plane c: tape[(k*3 + c) * SNT]
+    GradAcc A;
+    acc_zero(A);
+    float l1 = 0.0f;
+
+    const long long g0 = (long long)chunk * a.g.chunk_groups;
+    long long g1 = g0 + a.g.chunk_groups;
+    if (g1 > a.g.ngroups) g1 = a.g.ngroups;
+    for (long long gi = g0 + tid; gi < g1; gi += SNT) {
+        const size_t off = (size_t)gi * VEC;
+        float x[3][VEC], m[3][VEC], g[3][VEC];
+        ld_px<VEC>(img_b, plane, off, x);
+        ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
+            fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+        }
+        upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
+        if (out_b) st_px<VEC>(out_b, plane, off, x);
+#pragma unroll 1
+        for (int k = n - 1; k >= 0; --k) {
+            tape_ld<VEC>(tape + k * 3 * SNT, SNT, x);
+            bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true);
+        }
+        if (gi_b) st_px<VEC>(gi_b, plane, off, g);
+    }
+    step_epilogue(a, sh, A, l1, b, chunk);
+}
+
+// =========================================================================================== row pipeline (one stencil)
+template <int VEC, bool HM>
+__global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
+    using V = typename VecT<VEC>::type;
+    extern __shared__ __align__(16) float dyn_smem[];
+    __shared__ __align__(16) StepShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int strip = chunk % a.g.strips, band = chunk / a.g.strips;
+    const int n = a.ch.n, L = a.ch.L, sp = a.ch.sharp;
+    const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
+    const size_t plane = (size_t)H * W;
+    const float *img_b = a.img + (size_t)b * 3 * plane;
+    const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
+    const float *go_b = a.grad_out ? a.grad_out + (size_t)b * 3 * plane : nullptr;
+    float *out_b = a.out ? a.out + (size_t)b * 3 * plane : nullptr;
+    float *gi_b = a.grad_img ? a.grad_img + (size_t)b * 3 * plane : nullptr;
+    const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
+    const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
+
+    // lane -> (row within the warp, group within the strip)
+    const int lgT = a.g.lgTWp, TWp = 1 << lgT;
+    const int lr = lane >> lgT, lg = lane & (TWp - 1);
+    const int HL = a.g.HL;
+    const int gx = strip * a.g.IW - HL + lg;                       // group index in the image row
+    const bool lane_on = HL > 0 || lg < Wg;                        // lanes that own a ring column
+    const bool col_ok = lane_on && gx >= 0 && gx < Wg;             // ... whose column is inside the image
+    const bool interior = col_ok && lg >= HL && lg < TWp - HL;     // ... and inside the strip proper
+    const int ya = band * a.g.HB;
+    const int yb = ya + a.g.HB < H ? ya + a.g.HB : H;
+    const int R = a.g.R, RING = a.g.RING;
+
+    // shared memory: [X ring][GY ring][GD ring (mask only)][tape of the operators before the stencil][per-thread tape after it]
+    const int rowf = (TWp + 2) * VEC;                              // floats of one ring row of one plane (1 pad group each side)
+    const int ringf = RING * 3 * rowf;
+    float *Xr = dyn_smem;
+    float *GYr = Xr + ringf;
+    float *GDr = GYr + ringf;
+    const int nring = HM ? 3 : 2;
+    V *tapeP = reinterpret_cast<V *>(dyn_smem + nring * ringf);    // [(k-1)][slot][c][TWp], k = 1 .. sp-1
+    const int ntp = sp > 1 ? sp - 1 : 0;
+    V *tapeQ = tapeP + (size_t)ntp * RING * 3 * TWp + tid;         // [(k-sp-1)][c][SNT], k = sp+1 .. n-1
+    for (int i = tid; i < nring * ringf; i += SNT) dyn_smem[i] = 0.0f;
+    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, sh.tabs[tid]);
+    __syncthreads();
+
+    const float p = sh.tabs[sp][0];
+    const bool need_c = gi_b != nullptr || sp > 0;
+    GradAcc A;
+    acc_zero(A);
+    float l1 = 0.0f;
+
+    const int o = warp * a.g.RPW + lr;                              // this thread's row within a step
+    const int colf = (1 + lg) * VEC;                               // float offset of the group inside a ring row
+    int rA = ya - 2 + o, sA = o;                                   // row produced in phase A and its ring slot
+#pragma unroll 1
+    for (int s = 0; s < a.g.steps; ++s) {
+        // ---------------- phase A: X = (operators before the stencil)(img) on row rA
+        if (lane_on) {
+            float x[3][VEC];
+            if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) {
+                const size_t off = (size_t)rA * W + (size_t)gx * VEC;
+                float m[3][VEC];
+                ld_px<VEC>(img_b, plane, off, x);
+                if (sp > 0) {
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+#pragma unroll 1
+                    for (int k = 0; k < sp; ++k) {
+                        if (k >= 1 && interior) tape_st<VEC>(tapeP + (((k - 1) * RING + sA) * 3) * TWp + lg, TWp, x);
+                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+                    }
+                }
+            } else {                                               // outside the image: the stencil's zero padding
+                zero3<VEC>(x);
+            }
+            float *dst = Xr + (sA * 3) * rowf + colf;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * rowf, x[c]);
+        }
+        __syncthreads();
+        // ---------------- phase B: stencil, operators after it, loss, their backward on row rA - 1 -> GY ring
+        {
+            const int rB = rA - 1;
+            if (lane_on && rB >= ya - 1 && rB <= yb) {
+                const int sB = sA >= 1 ? sA - 1 : sA - 1 + RING;
+                float gy[3][VEC], gd[3][VEC];
+                if (col_ok && rB >= 0 && rB < H) {
+                    const bool own = interior && rB >= ya && rB < yb;
+                    const size_t off = (size_t)rB * W + (size_t)gx * VEC;
+                    const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
+                    float x[3][VEC], m[3][VEC], g[3][VEC], ctr[3][VEC], lap[3][VEC];
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        stencil_ring<VEC>(Xr + (sB * 3 + c) * rowf + colf, Xr + (sU * 3 + c) * rowf + colf,
+                                          Xr + (sD * 3 + c) * rowf + colf, ctr[c], lap[c]);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
+                    }
+#pragma unroll 1
+                    for (int k = sp + 1; k < n; ++k) {
+                        tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
+                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+                    }
+                    upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
+                    if (out_b && own) st_px<VEC>(out_b, plane, off, x);
+#pragma unroll 1
+                    for (int k = n - 1; k > sp; --k) {
+                        tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
+                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, own);
+                    }
+                    float accp = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            blend_bwd<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v], g[c][v], gy[c][v], gd[c][v]);
+                            accp = fmaf(gy[c][v], lap[c][v], accp);
+                        }
+                    if (own) A.sharp += accp;
+                } else {                                           // outside the image: no stencil output there
+                    zero3<VEC>(gy);
+                    zero3<VEC>(gd);
+                }
+                if (need_c) {
+                    float *dst = GYr + (sB * 3) * rowf + colf;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * rowf, gy[c]);
+                    if constexpr (HM) {
+                        float *dd = GDr + (sB * 3) * rowf + colf;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) st_vec<VEC>(dd + c * rowf, gd[c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- phase C: transposed stencil, backward of the operators before it, on row rA - 2
+        if (need_c) {
+            const int rC = rA - 2;
+            if (interior && rC >= ya && rC < yb) {
+                const int sC = sA >= 2 ? sA - 2 : sA - 2 + RING;
+                const int sU = sC >= 1 ? sC - 1 : RING - 1, sD = sC + 1 < RING ? sC + 1 : 0;
+                const size_t off = (size_t)rC * W + (size_t)gx * VEC;
+                float g[3][VEC];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float ctr[VEC], lap[VEC];
+                    stencil_ring<VEC>(GYr + (sC * 3 + c) * rowf + colf, GYr + (sU * 3 + c) * rowf + colf,
+                                      GYr + (sD * 3 + c) * rowf + colf, ctr, lap);
+                    float gdv[VEC];
+                    if constexpr (HM) lds_vec<VEC>(GDr + (sC * 3 + c) * rowf + colf, gdv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) g[c][v] = fmaf(p, lap[v], ctr[v]) + (HM ? gdv[v] : 0.0f);
+                }
+                if (sp > 0) {
+                    float x[3][VEC], m[3][VEC];
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+#pragma unroll 1
+                    for (int k = sp - 1; k >= 0; --k) {
+                        if (k >= 1) tape_ld<VEC>(tapeP + (((k - 1) * RING + sC) * 3) * TWp + lg, TWp, x);
+                        else ld_px<VEC>(img_b, plane, off, x);
+                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true);
+                    }
+                }
+                if (gi_b) st_px<VEC>(gi_b, plane, off, g);
+            }
+            __syncthreads();                                       // the rings are rewritten by the next step
+        }
+        rA += R;
+        sA += R;
+        if (sA >= RING) sA -= RING;
+    }
+    step_epilogue(a, sh, A, l1, b, chunk);
+}
+
+// Opt in to the dynamic shared memory a launch needs.
+template <typename K>
+static int step_set_smem(K kernel, size_t bytes) {
+    if (bytes > 200 * 1024) return T2O_ERR_UNSUPPORTED;
+    if (bytes > 40 * 1024)
+        T2O_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return T2O_OK;
+}
+
+}  // namespace t2o

@@ -68,14 +68,16 @@ def pack_params(op_ids, params, B, device, curve_steps=CURVE_STEPS):
 
 
 def split_segments(op_ids):
-    """Launch segments: at most MAX_CHAIN operators and at most one sharpness operator each."""
-    segs, cur, has_sharp = [], [], False
+    """Launch segments: at most MAX_CHAIN operators and each operator type at most once (the backward kernel
+    keeps one register accumulator slot per operator type; the stencil of a second sharpness needs a new pass)."""
+    segs, cur, seen = [], [], set()
     for i, op in enumerate(op_ids):
-        if len(cur) == _lib.MAX_CHAIN or (op == OP_SHARPNESS and has_sharp):
+        if len(cur) == _lib.MAX_CHAIN or op in seen:
             segs.append(cur)
-            cur, has_sharp = [], False
+            cur, seen = [], set()
         cur.append(i)
-        has_sharp = has_sharp or op == OP_SHARPNESS
+        if op >= 0:
+            seen.add(op)
     if cur:
         segs.append(cur)
     return segs
@@ -206,7 +208,7 @@ def chain_forward_backward(img, op_ids, params, target, mask=None, want_out=True
     img, target = _prep_img(img, 'img'), _prep_img(target, 'target')
     op_ids = [int(o) for o in op_ids]
     if len(split_segments(op_ids)) != 1 or any(o < 0 for o in op_ids):
-        raise _lib.T2OError('chain_forward_backward takes one launch segment (<= 8 ops, <= 1 sharpness, no identity)')
+        raise _lib.T2OError('chain_forward_backward takes one launch segment (<= 8 ops, each operator type at most once, no identity)')
     B = img.shape[0]
     packed, offs, pstride = pack_params(op_ids, params, B, img.device, curve_steps)
     mask_c, mask_ch = _prep_mask(mask, img)

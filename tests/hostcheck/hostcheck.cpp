@@ -72,10 +72,7 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
         for (int k = n_ops - 1; k >= 0; --k) {
             const float *x = xs[k].data();
             const float *tab = &tabs[k * TAB];
-            float acc[3] = {0, 0, 0};
-            std::vector<double> accd(3, 0.0);
-            F2 hist[3 * NBIN];
-            std::vector<double> histA(3 * NBIN, 0.0), histB(3 * NBIN, 0.0);
+            std::vector<double> accd(ACC_SLOTS, 0.0);
             if (ops[k] == OP_SHARPNESS) {
                 const float p = tab[0];
                 double accp = 0;
@@ -110,31 +107,36 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             }
             for (size_t i = 0; i < plane; ++i) {
                 float gr = g[i], gg = g[plane + i], gb = g[2 * plane + i];
-                for (int t = 0; t < 3 * NBIN; ++t) hist[t].a = hist[t].b = 0.f;
-                acc[0] = acc[1] = acc[2] = 0.f;
-                Hist h{hist, 1};
+                GradAcc A;
+                acc_zero(A);
                 if (has_mask)
                     pointwise_bwd<true>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], M(0, i), M(1, i), M(2, i),
-                                        gr, gg, gb, acc, h, true);
+                                        gr, gg, gb, A, true);
                 else
                     pointwise_bwd<false>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], 1.f, 1.f, 1.f,
-                                         gr, gg, gb, acc, h, true);
+                                         gr, gg, gb, A, true);
                 g[i] = gr; g[plane + i] = gg; g[2 * plane + i] = gb;
-                for (int t = 0; t < 3; ++t) accd[t] += acc[t];
-                for (int t = 0; t < 3 * NBIN; ++t) { histA[t] += hist[t].a; histB[t] += hist[t].b; }
+                float v[ACC_SLOTS];
+                acc_to_slots(A, v);
+                for (int t = 0; t < ACC_SLOTS; ++t) accd[t] += v[t];
             }
             if (grad_params) {
                 float *gp = grad_params + (size_t)b * pstride + poff[k];
-                if (ops[k] == OP_TONE || ops[k] == OP_COLOR) {
-                    const int nc = ops[k] == OP_TONE ? 1 : 3;
-                    for (int c = 0; c < nc; ++c) {
-                        float A[NBIN], Bx[NBIN];
-                        for (int t = 0; t < NBIN; ++t) { A[t] = (float)histA[c * NBIN + t]; Bx[t] = (float)histB[c * NBIN + t]; }
-                        curve_param_grad(tab + c * CT, L, A, Bx, (float)accd[c], gp + c * L);
-                    }
-                } else {
-                    const int n = op_num_params(ops[k], L);
-                    for (int t = 0; t < n && t < 3; ++t) gp[t] = (float)accd[t];
+                switch (ops[k]) {
+                    case OP_TONE:
+                        for (int i = 0; i < L; ++i) gp[i] = curve_param_grad(tab, (float)accd[ACC_TONE + i], (float)accd[ACC_TONE_C]);
+                        break;
+                    case OP_COLOR:
+                        for (int c = 0; c < 3; ++c)
+                            for (int i = 0; i < L; ++i)
+                                gp[c * L + i] = curve_param_grad(tab + c * CT, (float)accd[ACC_COLOR + c * MAX_L + i], (float)accd[ACC_COLOR_C + c]);
+                        break;
+                    case OP_BRIGHTNESS: gp[0] = (float)accd[ACC_BRIGHT]; break;
+                    case OP_CONTRAST: gp[0] = (float)accd[ACC_CONTRAST]; break;
+                    case OP_SATURATION: gp[0] = (float)accd[ACC_SATUR]; break;
+                    case OP_EXPOSURE: gp[0] = (float)accd[ACC_EXPO]; break;
+                    case OP_WHITEBALANCE: for (int t = 0; t < 3; ++t) gp[t] = (float)accd[ACC_WB + t]; break;
+                    default: break;
                 }
             }
         }

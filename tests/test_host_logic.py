@@ -81,6 +81,8 @@ def test_pack_params_and_segments():
     assert TF.split_segments([6, 1, 6, 5]) == [[0, 1], [2, 3]]
     assert TF.split_segments(list(range(10))) == [list(range(8)), [8, 9]]
     assert TF.split_segments([6, 6, 6]) == [[0], [1], [2]]
+    assert TF.split_segments([0, 0, 1, 5, 1]) == [[0], [1, 2, 3], [4]]      # each operator type once per launch
+    assert TF.split_segments([-1, 0, -1, 0]) == [[0, 1, 2], [3]]
     assert [TF.num_params(o) for o in (-1, 0, 3, 5, 9)] == [0, 1, 24, 8, 3]
 
 
