@@ -17,6 +17,10 @@ if what in ('fwd_c4', 'bwd_c4'):
             TF._forward_raw(bench.CHAIN, [0, 1, 2, 3, 27, 35], img, None, 0, torch.cat(params, 1).contiguous(), 36, tgt, True, True, 8)
         else:
             TF.chain_forward_backward(img, bench.CHAIN, params, tgt)
+elif what == 'p5_c4':
+    img, tgt, params = bench.make_batch(16, 2048, 3072, 4010, dev)
+    for _ in range(4):
+        TF.chain_forward_backward(img, bench.CHAIN[:5], params[:5], tgt)
 elif what == 'c2':
     img, tgt, params = bench.make_batch(64, 128, 128, 2010, dev)
     for _ in range(3):

@@ -18,6 +18,7 @@
 //     (f*s of hsv_to_rgb is u_c/(v+eps) exactly; the sector select is continuous, so no branch)
 //   Contrast:         0.5 - 0.5 cos(pi L) = sin^2(pi L / 2), odd/even polynomials in L on [0, 1]
 //   Curves:           j = floor(L x);  y = k'_j x + Q_j,  k' = k L/S, Q_j = L/S sum_{i<j} k_i/L - k'_j j/L
+//                     (one 16-byte segment record per j: k'_j, Q_j and the extra slope an exact knot passes)
 //   Curve param grads: G_i = sum g clamp(L x - i, 0, 1), C = sum g y  ->  dLoss/dk_i = (G_i - C) / S
 //
 // The instruction budget matters: at the HBM roofline a B200 SM has ~2 cycles per pixel, so the
@@ -39,9 +40,10 @@ enum : int {
 };
 
 constexpr int MAX_CHAIN = 8;
-constexpr int MAX_L = 8;
-constexpr int TAB = 64;    // floats in one (image, op) table
-constexpr int CT = 20;     // floats in one curve table: (k', Q) x 9 interleaved, 1/S, L/S
+constexpr int MAX_L = 8;    // even (the gradient accumulators are paired)
+constexpr int TAB = 128;   // floats in one (image, op) table
+constexpr int CT = 40;     // floats in one curve table: 9 segments x (k', Q, knot slope, 0), then 1/S, L/S
+constexpr int CT_INVS = 36, CT_SCALE = 37;
 constexpr int NBIN = MAX_L + 1;   // segments of one curve table (entry L repeats L-1: it serves x == 1.0)
 constexpr float HSV_EPS = 1e-6f;     // kornia.rgb_to_hsv eps
 constexpr float LUM_EPS = 1e-6f;     // models/operators.py:244
@@ -141,8 +143,10 @@ T2O_HD float lum_rn(float r, float g, float b) {
 // whitebal.  : tab[0..2]
 // tone       : one curve table at tab[0]
 // color      : three curve tables at tab[0], tab[CT], tab[2*CT]
-// curve table: ct[2j] = k'_j, ct[2j+1] = Q_j for j = 0..L (entry L repeats L-1: it serves x == 1.0),
-//              ct[18] = 1/S, ct[19] = L/S
+// curve table: segment j = 0..L at ct[4j]: (k'_j, Q_j, K_j, 0) with K_j = k'_{j-1} for 0 < j < L, else 0: at an
+//              exact knot x = j/L both neighbouring clamp terms of the reference pass the gradient (closed
+//              intervals), so dy/dx = k'_j + K_j there.  Segment L repeats L-1 and serves x == 1.0.
+//              ct[CT_INVS] = 1/S, ct[CT_SCALE] = L/S
 T2O_HD void build_curve(const float *k, int L, float *ct) {
     float S = 0.0f;
     for (int i = 0; i < L; ++i) S += k[i];
@@ -151,29 +155,32 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     const float invL = 1.0f / (float)L;
     float prefix = 0.0f;
     for (int j = 0; j < NBIN; ++j) {
+        float kp = 0.0f, q = 0.0f;
         if (j < L) {
-            const float kp = k[j] * scale;
-            ct[2 * j] = kp;
-            ct[2 * j + 1] = prefix * scale - kp * ((float)j * invL);
+            kp = k[j] * scale;
+            q = prefix * scale - kp * ((float)j * invL);
             prefix += k[j] * invL;
-        } else {
-            ct[2 * j] = 0.0f;
-            ct[2 * j + 1] = 0.0f;
         }
+        ct[4 * j] = kp;
+        ct[4 * j + 1] = q;
+        ct[4 * j + 2] = (j > 0 && j < L) ? k[j - 1] * scale : 0.0f;
+        ct[4 * j + 3] = 0.0f;
     }
     // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
     // which would make the output clamp swallow the gradient of every saturated (x == 1.0) pixel.
     // Pull the last segment back so that y(1) <= 1 (a < 1e-6 shift; reference rounding there is
     // platform dependent anyway).
-    float q_end = ct[2 * (L - 1) + 1];
-    if (fmaf(ct[2 * (L - 1)], 1.0f, q_end) < 1.0f + 1e-5f) {
-        for (int it = 0; it < 8 && fmaf(ct[2 * (L - 1)], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
-        ct[2 * (L - 1) + 1] = q_end;
+    float q_end = ct[4 * (L - 1) + 1];
+    if (fmaf(ct[4 * (L - 1)], 1.0f, q_end) < 1.0f + 1e-5f) {
+        for (int it = 0; it < 8 && fmaf(ct[4 * (L - 1)], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
+        ct[4 * (L - 1) + 1] = q_end;
     }
-    ct[2 * L] = ct[2 * (L - 1)];
-    ct[2 * L + 1] = ct[2 * (L - 1) + 1];
-    ct[18] = 1.0f / S;
-    ct[19] = scale;
+    ct[4 * L] = ct[4 * (L - 1)];
+    ct[4 * L + 1] = ct[4 * (L - 1) + 1];
+    ct[4 * L + 2] = 0.0f;
+    ct[4 * L + 3] = 0.0f;
+    ct[CT_INVS] = 1.0f / S;
+    ct[CT_SCALE] = scale;
 }
 
 T2O_HD void build_table(int op, const float *p, int L, float *tab) {
@@ -233,11 +240,14 @@ T2O_HD int curve_bin(float xs, int L, float &t, float &tf) {
     return (int)tf;
 #endif
 }
+struct F4 { float a, b, c, d; };   // == float4
+// CL: the input is known to lie in [0, 1] (it is the clamped output of the previous operator)
+template <bool CL>
 T2O_HD float curve_y(const float *ct, int L, float x) {
-    const float xs = sat01(x);
+    const float xs = CL ? x : sat01(x);
     float t, tf;
     const int j = curve_bin(xs, L, t, tf);
-    const F2 seg = *reinterpret_cast<const F2 *>(ct + 2 * j);
+    const F2 seg = *reinterpret_cast<const F2 *>(ct + 4 * j);
     return fmaf(seg.a, xs, seg.b);
 }
 
@@ -245,13 +255,14 @@ T2O_HD float curve_y(const float *ct, int L, float x) {
 T2O_HD float laplace(float c, float up, float dn, float lf, float rt) { return fmaf(4.0f, c, -((up + dn) + (lf + rt))); }
 
 // pointwise operators only (sharpness needs neighbours and is applied by the kernels)
+template <bool CL = false>
 T2O_HD void op_y(int op, const float *tab, int L, float r, float g, float b, float &yr, float &yg, float &yb) {
     switch (op) {
         case OP_BRIGHTNESS: brightness_y(tab, r, g, b, yr, yg, yb); break;
         case OP_CONTRAST: contrast_y(tab, r, g, b, yr, yg, yb); break;
         case OP_SATURATION: saturation_y(tab, r, g, b, yr, yg, yb); break;
-        case OP_COLOR: yr = curve_y(tab, L, r); yg = curve_y(tab + CT, L, g); yb = curve_y(tab + 2 * CT, L, b); break;
-        case OP_TONE: yr = curve_y(tab, L, r); yg = curve_y(tab, L, g); yb = curve_y(tab, L, b); break;
+        case OP_COLOR: yr = curve_y<CL>(tab, L, r); yg = curve_y<CL>(tab + CT, L, g); yb = curve_y<CL>(tab + 2 * CT, L, b); break;
+        case OP_TONE: yr = curve_y<CL>(tab, L, r); yg = curve_y<CL>(tab, L, g); yb = curve_y<CL>(tab, L, b); break;
         case OP_WHITE: yr = 1.0f; yg = 1.0f; yb = 1.0f; break;
         case OP_EXPOSURE: yr = r * tab[1]; yg = g * tab[1]; yb = b * tab[1]; break;
         case OP_WHITEBALANCE: yr = r * tab[0]; yg = g * tab[1]; yb = b * tab[2]; break;
@@ -260,28 +271,16 @@ T2O_HD void op_y(int op, const float *tab, int L, float r, float g, float b, flo
 }
 
 // one full Operator.execute on a pixel (pointwise operators): x <- clamp(blend(process(x)))
-template <bool HM>
+template <bool HM, bool CL = false>
 T2O_HD void op_apply(int op, const float *tab, int L, float &r, float &g, float &b,
                      float mr, float mg, float mb, bool raw = false) {
     if (op < 0) return;                       // identity: no clamp (executors/executor.py:44-46)
     float yr, yg, yb;
-    op_y(op, tab, L, r, g, b, yr, yg, yb);
+    op_y<CL>(op, tab, L, r, g, b, yr, yg, yb);
     if (raw) { r = yr; g = yg; b = yb; return; }   // Operator.process only
     r = sat01(blend<HM>(yr, r, mr));
     g = sat01(blend<HM>(yg, g, mg));
     b = sat01(blend<HM>(yb, b, mb));
-}
-
-// same, from (r,g,b) into (or,og,ob): lets the backward kernels keep every operator's input without copies
-template <bool HM>
-T2O_HD void op_apply_io(int op, const float *tab, int L, float r, float g, float b, float &orr, float &og, float &ob,
-                        float mr, float mg, float mb) {
-    if (op < 0) { orr = r; og = g; ob = b; return; }
-    float yr, yg, yb;
-    op_y(op, tab, L, r, g, b, yr, yg, yb);
-    orr = sat01(blend<HM>(yr, r, mr));
-    og = sat01(blend<HM>(yg, g, mg));
-    ob = sat01(blend<HM>(yb, b, mb));
 }
 
 // ---------------------------------------------------------------- backward
@@ -296,30 +295,41 @@ T2O_HD void blend_bwd(float y, float x, float m, float g, float &gy, float &gd) 
 
 // Per-thread parameter-gradient accumulators: one slot per operator TYPE (a backward launch holds each
 // operator type at most once, the binding splits longer chains), statically indexed so they live in registers.
-// Curves: G[i] = sum g * clamp(L x - i, 0, 1) and C = sum g * y, from which dLoss/dk_i = (G[i] - C) / S
-// (y = sum_i k_i clamp(L x - i, 0, 1) / S with S = sum k + eps: models/operators.py:579-585, 610-616).
+// Curves: G[i] = sum g * clamp(L x - i, 0, 1); with y = sum_i k_i clamp(L x - i, 0, 1) / S and S = sum k + eps
+// (models/operators.py:579-585, 610-616):  C = sum g * y = sum_i k_i G[i] / S  and  dLoss/dk_i = (G[i] - C) / S.
+// The curve slots are kept as pairs so that the device accumulates two bins per packed FFMA2 (sm_100 fp32x2).
 struct GradAcc {
-    float color[3][MAX_L];
-    float colorC[3];
+    F2 color[3][MAX_L / 2];
     float bright, contrast, satur, expo, sharp;
-    float tone[MAX_L];
-    float toneC;
+    F2 tone[MAX_L / 2];
     float wb[3];
 };
+// c + a * b on both halves: one FFMA2 issue slot on the device
+T2O_HD F2 fma2(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = __ffma2_rn(make_float2(a.a, a.b), make_float2(b.a, b.b), make_float2(c.a, c.b));
+    return F2{r.x, r.y};
+#else
+    return F2{fmaf(a.a, b.a, c.a), fmaf(a.b, b.b, c.b)};
+#endif
+}
 constexpr int ACC_SLOTS = 48;     // slot layout used by the kernels' reduction (see acc_slot_* below)
-constexpr int ACC_COLOR = 0, ACC_COLOR_C = 24, ACC_BRIGHT = 27, ACC_CONTRAST = 28, ACC_SATUR = 29, ACC_EXPO = 30,
-              ACC_SHARP = 31, ACC_TONE = 32, ACC_TONE_C = 40, ACC_WB = 41;
+constexpr int ACC_COLOR = 0, ACC_BRIGHT = 27, ACC_CONTRAST = 28, ACC_SATUR = 29, ACC_EXPO = 30,
+              ACC_SHARP = 31, ACC_TONE = 32, ACC_WB = 41;
 T2O_HD void acc_zero(GradAcc &a) {
-    for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L; ++i) a.color[c][i] = 0.0f; a.colorC[c] = 0.0f; a.wb[c] = 0.0f; }
-    for (int i = 0; i < MAX_L; ++i) a.tone[i] = 0.0f;
-    a.toneC = 0.0f; a.bright = 0.0f; a.contrast = 0.0f; a.satur = 0.0f; a.expo = 0.0f; a.sharp = 0.0f;
+    for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L / 2; ++i) a.color[c][i] = F2{0.0f, 0.0f}; a.wb[c] = 0.0f; }
+    for (int i = 0; i < MAX_L / 2; ++i) a.tone[i] = F2{0.0f, 0.0f};
+    a.bright = 0.0f; a.contrast = 0.0f; a.satur = 0.0f; a.expo = 0.0f; a.sharp = 0.0f;
 }
 T2O_HD void acc_to_slots(const GradAcc &a, float *v) {     // v[ACC_SLOTS]
-    for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L; ++i) v[ACC_COLOR + c * MAX_L + i] = a.color[c][i]; v[ACC_COLOR_C + c] = a.colorC[c]; v[ACC_WB + c] = a.wb[c]; }
-    for (int i = 0; i < MAX_L; ++i) v[ACC_TONE + i] = a.tone[i];
-    v[ACC_TONE_C] = a.toneC; v[ACC_BRIGHT] = a.bright; v[ACC_CONTRAST] = a.contrast; v[ACC_SATUR] = a.satur;
+    for (int i = 0; i < ACC_SLOTS; ++i) v[i] = 0.0f;
+    for (int c = 0; c < 3; ++c) {
+        for (int i = 0; i < MAX_L / 2; ++i) { v[ACC_COLOR + c * MAX_L + 2 * i] = a.color[c][i].a; v[ACC_COLOR + c * MAX_L + 2 * i + 1] = a.color[c][i].b; }
+        v[ACC_WB + c] = a.wb[c];
+    }
+    for (int i = 0; i < MAX_L / 2; ++i) { v[ACC_TONE + 2 * i] = a.tone[i].a; v[ACC_TONE + 2 * i + 1] = a.tone[i].b; }
+    v[ACC_BRIGHT] = a.bright; v[ACC_CONTRAST] = a.contrast; v[ACC_SATUR] = a.satur;
     v[ACC_EXPO] = a.expo; v[ACC_SHARP] = a.sharp;
-    for (int i = ACC_WB + 3; i < ACC_SLOTS; ++i) v[i] = 0.0f;
 }
 
 // Each *_bwd takes the operator input x = (r,g,b), the mask, the upstream gradient
@@ -422,13 +432,13 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     gb = fmaf(gyb, F, gdb) + 0.06f * k;
 }
 
-// one channel of a curve operator: G[i] += g * clamp(L x - i, 0, 1), accC += g * y
-template <bool HM>
-T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, float *G, float &accC, bool own) {
-    const float xs = sat01(x);
+// one channel of a curve operator: G[i] += g * clamp(L x - i, 0, 1)
+template <bool HM, bool CL>
+T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, F2 *G, bool own) {
+    const float xs = CL ? x : sat01(x);
     float t, tf;
     const int j = curve_bin(xs, L, t, tf);
-    const F2 seg = *reinterpret_cast<const F2 *>(ct + 2 * j);
+    const F4 seg = *reinterpret_cast<const F4 *>(ct + 4 * j);
     const float y = fmaf(seg.a, xs, seg.b);
     float gy, gd;
     blend_bwd<HM>(y, x, m, g, gy, gd);
@@ -436,17 +446,22 @@ T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, float 
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < MAX_L; ++i) G[i] = fmaf(ga, sat01(t - (float)i), G[i]);
-    accC = fmaf(ga, y, accC);
-    float slope = seg.a;
-    if (t == tf && j > 0 && j < L) slope += ct[2 * (j - 1)];        // exact knot: both clamp terms pass
-    return gd + (in01(x) ? gy * slope : 0.0f);
+    for (int i = 0; i < MAX_L / 2; ++i)
+        G[i] = fma2(F2{ga, ga}, F2{sat01(t - (float)(2 * i)), sat01(t - (float)(2 * i + 1))}, G[i]);
+    const float slope = t == tf ? seg.a + seg.c : seg.a;            // exact knot: both clamp terms pass
+    const float gx = gy * slope;
+    return gd + ((CL || in01(x)) ? gx : 0.0f);
 }
 
-// dLoss/dk_i of one curve from its reduced accumulators: (G[i] - C) / S
-T2O_HD float curve_param_grad(const float *ct, float Gi, float C) { return ct[18] * (Gi - C); }
+// dLoss/dk_i of one curve from its reduced accumulators G[0..L): (G[i] - C) / S with C = sum_j (k_j / S) G[j]
+// (k_j / S = k'_j / L from the segment table)
+T2O_HD float curve_param_grad(const float *ct, int L, const float *G, int i) {
+    float C = 0.0f;
+    for (int j = 0; j < L; ++j) C = fmaf(ct[4 * j], G[j], C);
+    return ct[CT_INVS] * (G[i] - C / (float)L);
+}
 
-template <bool HM>
+template <bool HM, bool CL = false>
 T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, float b,
                           float mr, float mg, float mb,
                           float &gr, float &gg, float &gb, GradAcc &A, bool own) {
@@ -455,14 +470,14 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
         case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.contrast, own); break;
         case OP_SATURATION: saturation_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.satur, own); break;
         case OP_TONE:
-            gr = curve_bwd<HM>(tab, L, r, mr, gr, A.tone, A.toneC, own);
-            gg = curve_bwd<HM>(tab, L, g, mg, gg, A.tone, A.toneC, own);
-            gb = curve_bwd<HM>(tab, L, b, mb, gb, A.tone, A.toneC, own);
+            gr = curve_bwd<HM, CL>(tab, L, r, mr, gr, A.tone, own);
+            gg = curve_bwd<HM, CL>(tab, L, g, mg, gg, A.tone, own);
+            gb = curve_bwd<HM, CL>(tab, L, b, mb, gb, A.tone, own);
             break;
         case OP_COLOR:
-            gr = curve_bwd<HM>(tab, L, r, mr, gr, A.color[0], A.colorC[0], own);
-            gg = curve_bwd<HM>(tab + CT, L, g, mg, gg, A.color[1], A.colorC[1], own);
-            gb = curve_bwd<HM>(tab + 2 * CT, L, b, mb, gb, A.color[2], A.colorC[2], own);
+            gr = curve_bwd<HM, CL>(tab, L, r, mr, gr, A.color[0], own);
+            gg = curve_bwd<HM, CL>(tab + CT, L, g, mg, gg, A.color[1], own);
+            gb = curve_bwd<HM, CL>(tab + 2 * CT, L, b, mb, gb, A.color[2], own);
             break;
         case OP_WHITE: {
             float gy, gd;

@@ -1,5 +1,7 @@
 // t2o_step.cu -- host side of t2o_chain_backward: geometry, workspace carving, launch selection for the fused
 // forward + L1 + backward kernels of t2o_step_kernels.cuh.
+#include <cstdlib>
+
 #include "t2o_step_kernels.cuh"
 
 namespace t2o {
@@ -16,7 +18,7 @@ static int make_step_desc(int n_ops, const int *op_ids, const int *param_off, in
     if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids || !param_off) return T2O_ERR_INVALID_ARG;
     if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
     if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
-    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1;
+    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1; d.clamped = 0;
     for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
     for (int i = 0; i < ACC_SLOTS; ++i) d.slot_col[i] = -1;
     bool seen[OP_COUNT] = {false};
@@ -27,6 +29,8 @@ static int make_step_desc(int n_ops, const int *op_ids, const int *param_off, in
         const int po = param_off[k];
         if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
         d.op[k] = op; d.poff[k] = po;
+        // the input of operator k lies in [0, 1] if the last non-identity operator before it exists (its output is clamped)
+        if (k > 0 && (d.op[k - 1] >= 0 || ((d.clamped >> (k - 1)) & 1))) d.clamped |= 1 << k;
         if (op < 0) continue;
         // one accumulator slot per operator type: a launch holds each type at most once (the binding splits)
         if (seen[op]) return T2O_ERR_UNSUPPORTED;
@@ -65,13 +69,13 @@ static int pick_vec(const void *const *ptrs, int nptr, size_t plane) {
 
 // resident CTAs per SM of a kernel at a given dynamic shared memory size (cached by the caller's static)
 template <typename K>
-static int resident_ctas(K kernel, size_t smem) {
+static int resident_ctas(K kernel, int nth, size_t smem) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SNT, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nth, smem) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
-static void geom_step_flat(StepGeom &g, int B, int H, int W, int vec, int slots) {
+static void geom_step_flat(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT) {
     memset(&g, 0, sizeof(g));
     g.B = B; g.H = H; g.W = W;
     const long long plane = (long long)H * W;
@@ -91,21 +95,17 @@ static void geom_step_flat(StepGeom &g, int B, int H, int W, int vec, int slots)
     if (g.nchunks < 1) g.nchunks = 1;
 }
 
-static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots) {
+static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT) {
+    const int SNW = SNT / 32;
     memset(&g, 0, sizeof(g));
     g.B = B; g.H = H; g.W = W;
     g.Wg = W / vec;
     if (g.Wg <= 32) {
-        int lg = 0;
-        while ((1 << lg) < g.Wg) ++lg;
-        g.lgTWp = lg; g.HL = 0; g.IW = g.Wg; g.strips = 1;
+        g.HL = 0; g.IW = g.Wg; g.strips = 1;
     } else {
-        g.lgTWp = 5; g.HL = vec >= 2 ? 1 : 2; g.IW = 32 - 2 * g.HL;
+        g.HL = vec >= 2 ? 1 : 2; g.IW = 32 - 2 * g.HL;
         g.strips = (g.Wg + g.IW - 1) / g.IW;
     }
-    g.RPW = 32 >> g.lgTWp;
-    g.R = SNW * g.RPW;
-    g.RING = g.R + 2;
     // band height: minimise waves x (steps + 1) over the number of bands; a band holds >= 16 rows
     long long best = -1;
     int best_hb = H;
@@ -113,7 +113,7 @@ static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots)
     for (int nb = 1; nb <= max_nb; ++nb) {
         const int hb = (H + nb - 1) / nb;
         const int bands = (H + hb - 1) / hb;
-        const int steps = (hb + 4 + g.R - 1) / g.R;
+        const int steps = (hb + 4 + SNW - 1) / SNW;
         const long long ctas = (long long)B * g.strips * bands;
         const long long waves = (ctas + slots - 1) / slots;
         const long long cost = waves * (steps + 1);
@@ -121,39 +121,47 @@ static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots)
     }
     g.HB = best_hb;
     g.bands = (H + g.HB - 1) / g.HB;
-    g.steps = (g.HB + 4 + g.R - 1) / g.R;
+    g.steps = (g.HB + 4 + SNW - 1) / SNW;
     g.nchunks = g.strips * g.bands;
 }
 
-static size_t rows_smem_bytes(const StepGeom &g, const StepDesc &d, int vec, bool has_mask) {
-    const int TWp = 1 << g.lgTWp;
-    const size_t ringf = (size_t)g.RING * 3 * (TWp + 2) * vec;
+static size_t rows_smem_bytes(const StepDesc &d, int vec, bool has_mask, int SNT) {
+    const int RING = SNT / 32 + 2;
+    const size_t ringf = (size_t)RING * 3 * 34 * vec;
     const size_t ntp = d.sharp > 1 ? d.sharp - 1 : 0;
     const size_t ntq = d.n - d.sharp - 1;
-    return ((has_mask ? 3 : 2) * ringf + ntp * g.RING * 3 * TWp * vec + ntq * 3 * SNT * vec) * sizeof(float);
+    return ((has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
 }
 
-template <int VEC, bool HM>
+// threads per CTA of the step kernels: 256 (default) or 192 (more registers per thread); T2O_STEP_THREADS overrides
+static int step_threads() {
+    static int nth = 0;
+    if (nth == 0) {
+        const char *e = getenv("T2O_STEP_THREADS");
+        nth = (e && atoi(e) == 192) ? 192 : 256;
+    }
+    return nth;
+}
+
+template <int VEC, bool HM, int NTH>
 static int launch_step(StepArgs &a, cudaStream_t stream) {
     const bool rows = a.ch.sharp >= 0;
     const int B = a.g.B, H = a.g.H, W = a.g.W;
     size_t smem;
     if (!rows) {
-        smem = (size_t)a.ch.n * 3 * SNT * VEC * sizeof(float);
-        int st = step_set_smem(step_flat_kernel<VEC, HM>, smem);
+        smem = (size_t)a.ch.n * 3 * NTH * VEC * sizeof(float);
+        int st = step_set_smem(step_flat_kernel<VEC, HM, NTH>, smem);
         if (st) return st;
-        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM>, smem));
+        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH>, NTH, smem), NTH);
         dim3 grid(a.g.nchunks, B);
-        step_flat_kernel<VEC, HM><<<grid, SNT, smem, stream>>>(a);
+        step_flat_kernel<VEC, HM, NTH><<<grid, NTH, smem, stream>>>(a);
     } else {
-        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * 2);
-        smem = rows_smem_bytes(a.g, a.ch, VEC, HM);
-        int st = step_set_smem(step_sharp_kernel<VEC, HM>, smem);
+        smem = rows_smem_bytes(a.ch, VEC, HM, NTH);
+        int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH>, smem);
         if (st) return st;
-        const int res = resident_ctas(step_sharp_kernel<VEC, HM>, smem);
-        if (res != 2) geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * res);     // the ring sizes do not depend on the band split
+        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH>, NTH, smem), NTH);
         dim3 grid(a.g.nchunks, B);
-        step_sharp_kernel<VEC, HM><<<grid, SNT, smem, stream>>>(a);
+        step_sharp_kernel<VEC, HM, NTH><<<grid, NTH, smem, stream>>>(a);
     }
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
@@ -161,9 +169,14 @@ static int launch_step(StepArgs &a, cudaStream_t stream) {
 
 template <bool HM>
 static int launch_step_vec(int vec, StepArgs &a, cudaStream_t stream) {
-    if (vec == 4) return launch_step<4, HM>(a, stream);
-    if (vec == 2) return launch_step<2, HM>(a, stream);
-    return launch_step<1, HM>(a, stream);
+    if (step_threads() == 192) {
+        if (vec == 4) return launch_step<4, HM, 192>(a, stream);
+        if (vec == 2) return launch_step<2, HM, 192>(a, stream);
+        return launch_step<1, HM, 192>(a, stream);
+    }
+    if (vec == 4) return launch_step<4, HM, 256>(a, stream);
+    if (vec == 2) return launch_step<2, HM, 256>(a, stream);
+    return launch_step<1, HM, 256>(a, stream);
 }
 
 int chain_backward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,

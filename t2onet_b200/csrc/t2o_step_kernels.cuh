@@ -28,12 +28,14 @@
 
 namespace t2o {
 
-constexpr int SNT = 256;          // threads per CTA
-constexpr int SNW = SNT / 32;     // warps per CTA = image rows per pipeline step (x rows per warp)
+// Threads per CTA are a template parameter NTH (256 or 192): NTH / 32 warps = image rows per pipeline step (a warp
+// owns one row, a lane one group); the pipeline rings hold NTH / 32 + 2 rows.
+constexpr int SNW_MAX = 8;
 
 struct StepDesc {
     int n, L, sharp;              // operators, curve steps, index of the sharpness operator or -1
     int k_tone, k_color;          // chain position of the tone / color operator or -1 (their 1/S lives in the tables)
+    int clamped;                  // bit k: the input of operator k is the clamped output of another operator (in [0, 1])
     int op[MAX_CHAIN];
     int poff[MAX_CHAIN];
     int slot_col[ACC_SLOTS];      // parameter column fed by each accumulator slot, or -1
@@ -47,11 +49,7 @@ struct StepGeom {
     int nchunks;                  // CTAs per image (both tilings)
     // row pipeline (one stencil)
     int Wg;                       // groups per image row
-    int lgTWp;                    // log2 of the lanes one row occupies (32 lanes unless the image is narrower)
-    int RPW;                      // rows per warp = 32 >> lgTWp
-    int R;                        // rows per step = SNW * RPW
-    int RING;                     // R + 2
-    int HL;                       // halo lanes on each side of a strip (0: the strip spans the image width)
+    int HL;                       // halo lanes on each side of a strip (0: one strip spans the image width, <= 32 groups)
     int IW;                       // interior lanes (groups) per strip
     int strips, bands, HB, steps;
 };
@@ -67,16 +65,21 @@ struct StepArgs {
 };
 
 // ---------------------------------------------------------------- operator dispatch over one pixel group
+// `cl`: the operator's input is known to lie in [0, 1] (lets the curve operators skip their input clamp)
 template <int VEC, bool HM>
-__device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, float (&x)[3][VEC], const float (&m)[3][VEC]) {
-#define T2O_CASE(OPC)                                                                                          \
-    case OPC:                                                                                                  \
+__device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, float (&x)[3][VEC], const float (&m)[3][VEC], bool cl) {
+#define T2O_CASE(OPC, CL)                                                                                      \
         _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                        \
-            op_apply<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);                   \
-        break;
+            op_apply<HM, CL>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);
     switch (op) {
-        T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
-        T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+        case OP_BRIGHTNESS: T2O_CASE(OP_BRIGHTNESS, false) break;
+        case OP_CONTRAST: T2O_CASE(OP_CONTRAST, false) break;
+        case OP_SATURATION: T2O_CASE(OP_SATURATION, false) break;
+        case OP_COLOR: if (cl) { T2O_CASE(OP_COLOR, true) } else { T2O_CASE(OP_COLOR, false) } break;
+        case OP_TONE: if (cl) { T2O_CASE(OP_TONE, true) } else { T2O_CASE(OP_TONE, false) } break;
+        case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
+        case OP_EXPOSURE: T2O_CASE(OP_EXPOSURE, false) break;
+        case OP_WHITEBALANCE: T2O_CASE(OP_WHITEBALANCE, false) break;
         default: break;
     }
 #undef T2O_CASE
@@ -84,16 +87,20 @@ __device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, floa
 
 template <int VEC, bool HM>
 __device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, const float (&x)[3][VEC],
-                                           const float (&m)[3][VEC], float (&g)[3][VEC], GradAcc &A, bool own) {
-#define T2O_CASE(OPC)                                                                                   \
-    case OPC:                                                                                           \
+                                           const float (&m)[3][VEC], float (&g)[3][VEC], GradAcc &A, bool own, bool cl) {
+#define T2O_CASE(OPC, CL)                                                                               \
         _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                 \
-            pointwise_bwd<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],        \
-                              g[0][v], g[1][v], g[2][v], A, own);                                       \
-        break;
+            pointwise_bwd<HM, CL>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],    \
+                                  g[0][v], g[1][v], g[2][v], A, own);
     switch (op) {
-        T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
-        T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+        case OP_BRIGHTNESS: T2O_CASE(OP_BRIGHTNESS, false) break;
+        case OP_CONTRAST: T2O_CASE(OP_CONTRAST, false) break;
+        case OP_SATURATION: T2O_CASE(OP_SATURATION, false) break;
+        case OP_COLOR: if (cl) { T2O_CASE(OP_COLOR, true) } else { T2O_CASE(OP_COLOR, false) } break;
+        case OP_TONE: if (cl) { T2O_CASE(OP_TONE, true) } else { T2O_CASE(OP_TONE, false) } break;
+        case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
+        case OP_EXPOSURE: T2O_CASE(OP_EXPOSURE, false) break;
+        case OP_WHITEBALANCE: T2O_CASE(OP_WHITEBALANCE, false) break;
         default: break;
     }
 #undef T2O_CASE
@@ -114,6 +121,14 @@ template <int VEC>
 __device__ __forceinline__ void tape_ld(const typename VecT<VEC>::type *p, int cstride, float (&x)[3][VEC]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) lds_vec<VEC>(reinterpret_cast<const float *>(p + c * cstride), x[c]);
+}
+
+// L1 prefetch of the three planes of a pixel group: the row pipeline issues it one phase ahead of the load, so
+// the phases (which all warps of a CTA enter together, right after a barrier) do not start on a DRAM round trip
+__device__ __forceinline__ void prefetch_px(const float *base, size_t plane, size_t off) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + off));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + plane + off));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 2 * plane + off));
 }
 
 template <int VEC>
@@ -195,7 +210,7 @@ __device__ __forceinline__ float warp_reduce_multi(float *v, int lane) {
 
 struct StepShared {
     float tabs[MAX_CHAIN][TAB];
-    float wred[SNW][ACC_SLOTS];
+    float wred[SNW_MAX][ACC_SLOTS];
     float tot[ACC_SLOTS];
     float rowbuf[MAX_PSTRIDE];
     float red[32];
@@ -203,7 +218,9 @@ struct StepShared {
 };
 
 // CTA partials of the parameter gradients and the L1, then "the last CTA of the image finishes"
+template <int NTH>
 __device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh, GradAcc &A, float l1, int b, int chunk) {
+    constexpr int SNT = NTH, SNW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunks = a.g.nchunks;
     if (a.grad_params) {
@@ -226,11 +243,11 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh,
             const int col = a.ch.slot_col[tid];
             if (col >= 0) {
                 float val = sh.tot[tid];
-                if (tid < ACC_COLOR_C) {
+                if (tid < ACC_COLOR + 3 * MAX_L) {
                     const int c = tid / MAX_L;
-                    val = curve_param_grad(sh.tabs[a.ch.k_color] + c * CT, val, sh.tot[ACC_COLOR_C + c]);
-                } else if (tid >= ACC_TONE && tid < ACC_TONE_C) {
-                    val = curve_param_grad(sh.tabs[a.ch.k_tone], val, sh.tot[ACC_TONE_C]);
+                    val = curve_param_grad(sh.tabs[a.ch.k_color] + c * CT, a.ch.L, sh.tot + ACC_COLOR + c * MAX_L, tid - c * MAX_L);
+                } else if (tid >= ACC_TONE && tid < ACC_TONE + MAX_L) {
+                    val = curve_param_grad(sh.tabs[a.ch.k_tone], a.ch.L, sh.tot + ACC_TONE, tid - ACC_TONE);
                 }
                 sh.rowbuf[col] = val;
             }
@@ -259,9 +276,10 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh,
 }
 
 // =========================================================================================== flat (no stencil)
-template <int VEC, bool HM>
-__global__ void __launch_bounds__(SNT, 2) step_flat_kernel(const __grid_constant__ StepArgs a) {
+template <int VEC, bool HM, int NTH>
+__global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant__ StepArgs a) {
     using V = typename VecT<VEC>::type;
+    constexpr int SNT = NTH;
     extern __shared__ __align__(16) float dyn_smem[];
     __shared__ __align__(16) StepShared sh;
 
@@ -293,27 +311,37 @@ __global__ void __launch_bounds__(SNT, 2) step_flat_kernel(const __grid_constant
         float x[3][VEC], m[3][VEC], g[3][VEC];
         ld_px<VEC>(img_b, plane, off, x);
         ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+        prefetch_px(go_b ? go_b : tgt_b, plane, off);                       // needed after the forward sweep
+        if (gi + SNT < g1) prefetch_px(img_b, plane, off + (size_t)SNT * VEC);   // next iteration
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
             tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
-            fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+            fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (a.ch.clamped >> k) & 1);
         }
         upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
         if (out_b) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll 1
         for (int k = n - 1; k >= 0; --k) {
             tape_ld<VEC>(tape + k * 3 * SNT, SNT, x);
-            bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true);
+            bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true, (a.ch.clamped >> k) & 1);
         }
         if (gi_b) st_px<VEC>(gi_b, plane, off, g);
     }
-    step_epilogue(a, sh, A, l1, b, chunk);
+    step_epilogue<NTH>(a, sh, A, l1, b, chunk);
 }
 
 // =========================================================================================== row pipeline (one stencil)
-template <int VEC, bool HM>
-__global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
+// Shared-memory layout (compile-time strides): a ring row holds 3 planes of 34 groups (one zero pad group each
+// side of the 32 lanes); the tape of the operators before the stencil holds, per operator 1 .. sp-1, RING rows of
+// 3 x 32 vectors; the operators after the stencil keep a per-thread tape.
+template <int VEC, bool HM, int NTH>
+__global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
     using V = typename VecT<VEC>::type;
+    constexpr int SNT = NTH, SNW = NTH / 32, RING = SNW + 2;
+    constexpr int ROWF = 34 * VEC;                 // floats of one ring row of one plane
+    constexpr int SLOTF = 3 * ROWF;                // floats of one ring row
+    constexpr int RINGF = RING * SLOTF;            // floats of one ring
+    constexpr int TSLOT = 3 * 32;                  // vectors of one tape row
     extern __shared__ __align__(16) float dyn_smem[];
     __shared__ __align__(16) StepShared sh;
 
@@ -331,44 +359,39 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
 
-    // lane -> (row within the warp, group within the strip)
-    const int lgT = a.g.lgTWp, TWp = 1 << lgT;
-    const int lr = lane >> lgT, lg = lane & (TWp - 1);
+    // lane -> group of the strip; HL halo lanes on each side unless one strip spans the image
     const int HL = a.g.HL;
-    const int gx = strip * a.g.IW - HL + lg;                       // group index in the image row
-    const bool lane_on = HL > 0 || lg < Wg;                        // lanes that own a ring column
+    const int gx = strip * a.g.IW - HL + lane;                     // group index in the image row
+    const bool lane_on = HL > 0 || lane < Wg;                      // lanes that own a ring column
     const bool col_ok = lane_on && gx >= 0 && gx < Wg;             // ... whose column is inside the image
-    const bool interior = col_ok && lg >= HL && lg < TWp - HL;     // ... and inside the strip proper
+    const bool interior = col_ok && lane >= HL && lane < 32 - HL;  // ... and inside the strip proper
     const int ya = band * a.g.HB;
     const int yb = ya + a.g.HB < H ? ya + a.g.HB : H;
-    const int R = a.g.R, RING = a.g.RING;
 
-    // shared memory: [X ring][GY ring][GD ring (mask only)][tape of the operators before the stencil][per-thread tape after it]
-    const int rowf = (TWp + 2) * VEC;                              // floats of one ring row of one plane (1 pad group each side)
-    const int ringf = RING * 3 * rowf;
-    float *Xr = dyn_smem;
-    float *GYr = Xr + ringf;
-    float *GDr = GYr + ringf;
-    const int nring = HM ? 3 : 2;
-    V *tapeP = reinterpret_cast<V *>(dyn_smem + nring * ringf);    // [(k-1)][slot][c][TWp], k = 1 .. sp-1
+    float *Xc = dyn_smem + (1 + lane) * VEC;                       // this lane's column in the X / GY / GD rings
+    float *GYc = Xc + RINGF;
+    float *GDc = GYc + RINGF;
+    constexpr int NRING = HM ? 3 : 2;
+    V *tapeP = reinterpret_cast<V *>(dyn_smem + NRING * RINGF) + lane;   // [(k-1) * RING + slot][c][32], k = 1 .. sp-1
     const int ntp = sp > 1 ? sp - 1 : 0;
-    V *tapeQ = tapeP + (size_t)ntp * RING * 3 * TWp + tid;         // [(k-sp-1)][c][SNT], k = sp+1 .. n-1
-    for (int i = tid; i < nring * ringf; i += SNT) dyn_smem[i] = 0.0f;
+    V *tapeQ = reinterpret_cast<V *>(dyn_smem + NRING * RINGF) + ntp * RING * TSLOT + tid;   // [(k-sp-1)][c][SNT]
+    for (int i = tid; i < NRING * RINGF; i += SNT) dyn_smem[i] = 0.0f;
     if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, sh.tabs[tid]);
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
     const bool need_c = gi_b != nullptr || sp > 0;
+    const int clamped = a.ch.clamped;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
 
-    const int o = warp * a.g.RPW + lr;                              // this thread's row within a step
-    const int colf = (1 + lg) * VEC;                               // float offset of the group inside a ring row
-    int rA = ya - 2 + o, sA = o;                                   // row produced in phase A and its ring slot
+    int rA = ya - 2 + warp, sA = warp;                             // row produced in phase A and its ring slot
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
         // ---------------- phase A: X = (operators before the stencil)(img) on row rA
+        if (col_ok && rA >= 1 && rA <= H && rA - 1 >= ya - 1 && rA - 1 <= yb)    // phase B's upstream row, one phase ahead
+            prefetch_px(go_b ? go_b : tgt_b, plane, (size_t)(rA - 1) * W + (size_t)gx * VEC);
         if (lane_on) {
             float x[3][VEC];
             if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) {
@@ -377,25 +400,28 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
                 ld_px<VEC>(img_b, plane, off, x);
                 if (sp > 0) {
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+                    fwd_op_grp<VEC, HM>(a.ch.op[0], sh.tabs[0], L, x, m, false);
 #pragma unroll 1
-                    for (int k = 0; k < sp; ++k) {
-                        if (k >= 1 && interior) tape_st<VEC>(tapeP + (((k - 1) * RING + sA) * 3) * TWp + lg, TWp, x);
-                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+                    for (int k = 1; k < sp; ++k) {
+                        if (interior) tape_st<VEC>(tapeP + ((k - 1) * RING + sA) * TSLOT, 32, x);
+                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
                     }
                 }
             } else {                                               // outside the image: the stencil's zero padding
                 zero3<VEC>(x);
             }
-            float *dst = Xr + (sA * 3) * rowf + colf;
+            float *dst = Xc + sA * SLOTF;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * rowf, x[c]);
+            for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, x[c]);
         }
         __syncthreads();
         // ---------------- phase B: stencil, operators after it, loss, their backward on row rA - 1 -> GY ring
         {
             const int rB = rA - 1;
+            if (col_ok && rA + SNW >= 0 && rA + SNW < H && rA + SNW <= yb + 1)   // phase A's image row of the next step
+                prefetch_px(img_b, plane, (size_t)(rA + SNW) * W + (size_t)gx * VEC);
             if (lane_on && rB >= ya - 1 && rB <= yb) {
-                const int sB = sA >= 1 ? sA - 1 : sA - 1 + RING;
+                const int sB = sA >= 1 ? sA - 1 : RING - 1;
                 float gy[3][VEC], gd[3][VEC];
                 if (col_ok && rB >= 0 && rB < H) {
                     const bool own = interior && rB >= ya && rB < yb;
@@ -403,10 +429,10 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
                     const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
                     float x[3][VEC], m[3][VEC], g[3][VEC], ctr[3][VEC], lap[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+                    const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        stencil_ring<VEC>(Xr + (sB * 3 + c) * rowf + colf, Xr + (sU * 3 + c) * rowf + colf,
-                                          Xr + (sD * 3 + c) * rowf + colf, ctr[c], lap[c]);
+                        stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr[c], lap[c]);
 #pragma unroll
                         for (int v = 0; v < VEC; ++v)
                             x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
@@ -414,14 +440,14 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll 1
                     for (int k = sp + 1; k < n; ++k) {
                         tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m);
+                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
                     }
                     upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
                     if (out_b && own) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll 1
                     for (int k = n - 1; k > sp; --k) {
                         tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, own);
+                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
                     }
                     float accp = 0.0f;
 #pragma unroll
@@ -437,13 +463,13 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
                     zero3<VEC>(gd);
                 }
                 if (need_c) {
-                    float *dst = GYr + (sB * 3) * rowf + colf;
+                    float *dst = GYc + sB * SLOTF;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * rowf, gy[c]);
+                    for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, gy[c]);
                     if constexpr (HM) {
-                        float *dd = GDr + (sB * 3) * rowf + colf;
+                        float *dd = GDc + sB * SLOTF;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) st_vec<VEC>(dd + c * rowf, gd[c]);
+                        for (int c = 0; c < 3; ++c) st_vec<VEC>(dd + c * ROWF, gd[c]);
                     }
                 }
             }
@@ -457,13 +483,13 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
                 const int sU = sC >= 1 ? sC - 1 : RING - 1, sD = sC + 1 < RING ? sC + 1 : 0;
                 const size_t off = (size_t)rC * W + (size_t)gx * VEC;
                 float g[3][VEC];
+                const float *yc = GYc + sC * SLOTF, *yu = GYc + sU * SLOTF, *yd = GYc + sD * SLOTF;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float ctr[VEC], lap[VEC];
-                    stencil_ring<VEC>(GYr + (sC * 3 + c) * rowf + colf, GYr + (sU * 3 + c) * rowf + colf,
-                                      GYr + (sD * 3 + c) * rowf + colf, ctr, lap);
+                    stencil_ring<VEC>(yc + c * ROWF, yu + c * ROWF, yd + c * ROWF, ctr, lap);
                     float gdv[VEC];
-                    if constexpr (HM) lds_vec<VEC>(GDr + (sC * 3 + c) * rowf + colf, gdv);
+                    if constexpr (HM) lds_vec<VEC>(GDc + sC * SLOTF + c * ROWF, gdv);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) g[c][v] = fmaf(p, lap[v], ctr[v]) + (HM ? gdv[v] : 0.0f);
                 }
@@ -471,21 +497,22 @@ __global__ void __launch_bounds__(SNT, 2) step_sharp_kernel(const __grid_constan
                     float x[3][VEC], m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
 #pragma unroll 1
-                    for (int k = sp - 1; k >= 0; --k) {
-                        if (k >= 1) tape_ld<VEC>(tapeP + (((k - 1) * RING + sC) * 3) * TWp + lg, TWp, x);
-                        else ld_px<VEC>(img_b, plane, off, x);
-                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true);
+                    for (int k = sp - 1; k >= 1; --k) {
+                        tape_ld<VEC>(tapeP + ((k - 1) * RING + sC) * TSLOT, 32, x);
+                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
                     }
+                    ld_px<VEC>(img_b, plane, off, x);
+                    bwd_op_grp<VEC, HM>(a.ch.op[0], sh.tabs[0], L, x, m, g, A, true, false);
                 }
                 if (gi_b) st_px<VEC>(gi_b, plane, off, g);
             }
             __syncthreads();                                       // the rings are rewritten by the next step
         }
-        rA += R;
-        sA += R;
+        rA += SNW;
+        sA += SNW;
         if (sA >= RING) sA -= RING;
     }
-    step_epilogue(a, sh, A, l1, b, chunk);
+    step_epilogue<NTH>(a, sh, A, l1, b, chunk);
 }
 
 // Opt in to the dynamic shared memory a launch needs.

@@ -46,8 +46,9 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             } else {
                 for (size_t i = 0; i < plane; ++i) {
                     float r = x[i], gg = x[plane + i], bb = x[2 * plane + i];
-                    if (has_mask) op_apply<true>(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i));
-                    else op_apply<false>(ops[k], tab, L, r, gg, bb, 1.f, 1.f, 1.f);
+                    const bool cl = k > 0 && ops[k - 1] >= 0;      // input = clamped output of the previous operator
+                    if (has_mask) { if (cl) op_apply<true, true>(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i)); else op_apply<true, false>(ops[k], tab, L, r, gg, bb, M(0, i), M(1, i), M(2, i)); }
+                    else { if (cl) op_apply<false, true>(ops[k], tab, L, r, gg, bb, 1.f, 1.f, 1.f); else op_apply<false, false>(ops[k], tab, L, r, gg, bb, 1.f, 1.f, 1.f); }
                     y[i] = r; y[plane + i] = gg; y[2 * plane + i] = bb;
                 }
             }
@@ -109,12 +110,15 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                 float gr = g[i], gg = g[plane + i], gb = g[2 * plane + i];
                 GradAcc A;
                 acc_zero(A);
-                if (has_mask)
-                    pointwise_bwd<true>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], M(0, i), M(1, i), M(2, i),
-                                        gr, gg, gb, A, true);
-                else
-                    pointwise_bwd<false>(ops[k], tab, L, x[i], x[plane + i], x[2 * plane + i], 1.f, 1.f, 1.f,
-                                         gr, gg, gb, A, true);
+                const bool cl = k > 0 && ops[k - 1] >= 0;
+                const float xr = x[i], xg = x[plane + i], xb = x[2 * plane + i];
+                if (has_mask) {
+                    if (cl) pointwise_bwd<true, true>(ops[k], tab, L, xr, xg, xb, M(0, i), M(1, i), M(2, i), gr, gg, gb, A, true);
+                    else pointwise_bwd<true, false>(ops[k], tab, L, xr, xg, xb, M(0, i), M(1, i), M(2, i), gr, gg, gb, A, true);
+                } else {
+                    if (cl) pointwise_bwd<false, true>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
+                    else pointwise_bwd<false, false>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
+                }
                 g[i] = gr; g[plane + i] = gg; g[2 * plane + i] = gb;
                 float v[ACC_SLOTS];
                 acc_to_slots(A, v);
@@ -123,13 +127,18 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             if (grad_params) {
                 float *gp = grad_params + (size_t)b * pstride + poff[k];
                 switch (ops[k]) {
-                    case OP_TONE:
-                        for (int i = 0; i < L; ++i) gp[i] = curve_param_grad(tab, (float)accd[ACC_TONE + i], (float)accd[ACC_TONE_C]);
+                    case OP_TONE: {
+                        float G[MAX_L];
+                        for (int i = 0; i < MAX_L; ++i) G[i] = (float)accd[ACC_TONE + i];
+                        for (int i = 0; i < L; ++i) gp[i] = curve_param_grad(tab, L, G, i);
                         break;
+                    }
                     case OP_COLOR:
-                        for (int c = 0; c < 3; ++c)
-                            for (int i = 0; i < L; ++i)
-                                gp[c * L + i] = curve_param_grad(tab + c * CT, (float)accd[ACC_COLOR + c * MAX_L + i], (float)accd[ACC_COLOR_C + c]);
+                        for (int c = 0; c < 3; ++c) {
+                            float G[MAX_L];
+                            for (int i = 0; i < MAX_L; ++i) G[i] = (float)accd[ACC_COLOR + c * MAX_L + i];
+                            for (int i = 0; i < L; ++i) gp[c * L + i] = curve_param_grad(tab + c * CT, L, G, i);
+                        }
                         break;
                     case OP_BRIGHTNESS: gp[0] = (float)accd[ACC_BRIGHT]; break;
                     case OP_CONTRAST: gp[0] = (float)accd[ACC_CONTRAST]; break;
