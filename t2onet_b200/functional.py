@@ -220,6 +220,70 @@ def chain_forward_backward(img, op_ids, params, target, mask=None, want_out=True
     return out, l1, grads, gi
 
 
+class FusedStep:
+    """A prepared fused training step (one t2o_chain_backward launch) for a fixed chain and batch shape.
+
+    Everything that does not depend on the data -- the host-side operator / offset arrays, the loss scale, the
+    workspace and (with reuse_outputs=True) the output buffers -- is set up once, so a call is one ctypes call:
+        out, l1_sum, grad_packed, grad_img = step(img, packed_params, target)
+    `packed_params` is the (B, sum n_k) row-major parameter table of pack_params(); grad_packed has the same
+    layout (step.split(grad_packed) gives the per-operator views).  With reuse_outputs=True the returned tensors
+    are overwritten by the next call."""
+
+    def __init__(self, op_ids, B, H, W, device, want_out=True, want_grad_img=False, reuse_outputs=False,
+                 curve_steps=CURVE_STEPS):
+        self.op_ids = [int(o) for o in op_ids]
+        if len(split_segments(self.op_ids)) != 1 or any(o < 0 for o in self.op_ids):
+            raise _lib.T2OError('FusedStep takes one launch segment (<= 8 ops, each operator type at most once, no identity)')
+        self.B, self.H, self.W, self.device, self.curve_steps = B, H, W, torch.device(device), curve_steps
+        self.offs, off = [], 0
+        for op in self.op_ids:
+            self.offs.append(off)
+            off += num_params(op, curve_steps)
+        self.pstride = max(off, 1)
+        self.want_out, self.want_grad_img, self.reuse = want_out, want_grad_img, reuse_outputs
+        self._ops_c, self._offs_c = _lib.int_array(self.op_ids), _lib.int_array(self.offs)
+        self._lib = _lib.lib()
+        self._ws_bytes = self._lib.t2o_workspace_bytes(B, H, W, self.pstride)
+        self.loss_scale = torch.full((B,), 1.0 / (B * 3 * H * W), device=self.device, dtype=torch.float32)
+        self._bufs = None
+
+    def _outputs(self):
+        if self._bufs is not None:
+            return self._bufs
+        shape = (self.B, 3, self.H, self.W)
+        gp = torch.empty(self.B, self.pstride, device=self.device, dtype=torch.float32)
+        gi = torch.empty(shape, device=self.device, dtype=torch.float32) if self.want_grad_img else None
+        out = torch.empty(shape, device=self.device, dtype=torch.float32) if self.want_out else None
+        l1 = torch.empty(self.B, device=self.device, dtype=torch.float32)
+        bufs = (out, l1, gp, gi)
+        if self.reuse:
+            self._bufs = bufs
+        return bufs
+
+    def split(self, packed):
+        return [packed[:, o:o + num_params(op, self.curve_steps)] for op, o in zip(self.op_ids, self.offs)]
+
+    def __call__(self, img, packed_params, target, mask=None, loss_scale=None):
+        shape = (self.B, 3, self.H, self.W)
+        if tuple(img.shape) != shape or tuple(target.shape) != shape or tuple(packed_params.shape) != (self.B, self.pstride):
+            raise _lib.T2OError('FusedStep: expected img/target %s and params %s' % (shape, (self.B, self.pstride)))
+        _lib.require_cuda(img, target, packed_params)
+        if not (img.is_contiguous() and target.is_contiguous() and packed_params.is_contiguous()):
+            raise _lib.T2OError('FusedStep: inputs must be contiguous')
+        mask_c, mask_ch = _prep_mask(mask, img)
+        scale = self.loss_scale if loss_scale is None else loss_scale.contiguous().float()
+        out, l1, gp, gi = self._outputs()
+        ws = _lib.workspace(self.device, self._ws_bytes)
+        st = self._lib.t2o_chain_backward(len(self.op_ids), self._ops_c, self._offs_c, _lib.ptr(img), _lib.ptr(mask_c), mask_ch,
+                                          _lib.ptr(packed_params), self.pstride, None, _lib.ptr(target), _lib.ptr(scale),
+                                          _lib.ptr(gp), _lib.ptr(gi), _lib.ptr(out), _lib.ptr(l1),
+                                          self.B, self.H, self.W, self.curve_steps, _lib.ptr(ws), ws.numel(),
+                                          _lib.stream_ptr(self.device))
+        _lib.check(st)
+        return out, l1, gp, gi
+
+
 def process_raw(img, op_id, param, curve_steps=CURVE_STEPS):
     """Operator.process(img, param) itself (no mask blend, no clamp): models/operators.py:128."""
     img = _prep_img(img, 'img')
