@@ -63,7 +63,6 @@ static int pick_vec_flat(const void *const *ptrs, int nptr, size_t plane) {
     return vec;
 }
 
-static inline unsigned int div_magic(int d) { return d <= 1 ? 0u : (unsigned int)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
 
 // flat tiling (no stencil): contiguous ranges of groups
 static void geom_flat(Geom &g, int B, int H, int W, int vec) {
@@ -85,43 +84,42 @@ static void geom_flat(Geom &g, int B, int H, int W, int vec) {
     g.tiles_per_cta = 1;
 }
 
-// 2-D tiling (one stencil in the chain); tile area >= MIN_TILE_PX unless the image is smaller
-static void geom_2d(Geom &g, int B, int H, int W, int vec, int tw_px, int th, int hgx) {
-    memset(&g, 0, sizeof(g));
-    g.B = B; g.H = H; g.W = W; g.Wg = W / vec;
-    int TWg = tw_px / vec;
-    if (TWg > g.Wg) TWg = g.Wg;
-    if (TWg < 1) TWg = 1;
-    int TH = th;
-    if (TH > H) TH = H;
-    while ((long long)TH * TWg * vec < MIN_TILE_PX && TH < H) TH = TH * 2 < H ? TH * 2 : H;
-    g.TH = TH; g.TWg = TWg;
-    g.tiles_x = (g.Wg + TWg - 1) / TWg;
-    g.tiles_y = (H + TH - 1) / TH;
-    g.ntiles = g.tiles_x * g.tiles_y;
-    g.nchunks = g.ntiles;
-    g.tiles_per_cta = 1;
-    g.mul_tiles_x = div_magic(g.tiles_x);
-    g.mul_tw = div_magic(TWg);
-    g.mul_rw = div_magic(TWg + 2);
-    g.mul_gw = div_magic(TWg + 2);
-    g.mul_xw = div_magic(TWg + 2 * hgx);
-}
-
-template <int VEC, bool SHARP, bool HM>
-static int launch_fwd(const FwdArgs &a, size_t smem, cudaStream_t stream) {
-    int st = set_smem(chain_fwd_kernel<VEC, SHARP, HM>, smem);
-    if (st) return st;
+template <int VEC, bool HM>
+static int launch_fwd(const FwdArgs &a, cudaStream_t stream) {
     dim3 grid(a.g.ntiles, a.g.B);
-    chain_fwd_kernel<VEC, SHARP, HM><<<grid, NT, smem, stream>>>(a);
+    chain_fwd_kernel<VEC, HM><<<grid, NT, 0, stream>>>(a);
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
 }
-template <bool SHARP, bool HM>
-static int launch_fwd_vec(int vec, const FwdArgs &a, size_t smem, cudaStream_t stream) {
-    if (vec == 4) return launch_fwd<4, SHARP, HM>(a, smem, stream);
-    if (vec == 2) return launch_fwd<2, SHARP, HM>(a, smem, stream);
-    return launch_fwd<1, SHARP, HM>(a, smem, stream);
+template <bool HM>
+static int launch_fwd_vec(int vec, const FwdArgs &a, cudaStream_t stream) {
+    if (vec == 4) return launch_fwd<4, HM>(a, stream);
+    if (vec == 2) return launch_fwd<2, HM>(a, stream);
+    return launch_fwd<1, HM>(a, stream);
+}
+
+void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT, int rows_extra);
+
+template <int VEC, bool HM>
+static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
+    const size_t smem = (size_t)(NT / 32 + 2) * 3 * 34 * VEC * sizeof(float);
+    static int resident = 0;
+    if (resident == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_fwd_rows_kernel<VEC, HM>, NT, smem) != cudaSuccess || nb < 1) nb = 1;
+        resident = nb;
+    }
+    geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident, NT, 2);
+    dim3 grid(a.g.nchunks, B);
+    chain_fwd_rows_kernel<VEC, HM><<<grid, NT, smem, stream>>>(a);
+    T2O_CUDA_OK(cudaGetLastError());
+    return T2O_OK;
+}
+template <bool HM>
+static int launch_fwd_rows_vec(int vec, FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
+    if (vec == 4) return launch_fwd_rows<4, HM>(a, B, H, W, stream);
+    if (vec == 2) return launch_fwd_rows<2, HM>(a, B, H, W, stream);
+    return launch_fwd_rows<1, HM>(a, B, H, W, stream);
 }
 
 int chain_forward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
@@ -146,12 +144,17 @@ int chain_forward(int n_ops, const int *op_ids, const int *param_off, const floa
     int vec = pick_vec_flat(ptrs, 4, plane);
     if (a.ch.sharp < 0) {
         geom_flat(a.g, B, H, W, vec);
-        return mask ? launch_fwd_vec<false, true>(vec, a, 0, stream) : launch_fwd_vec<false, false>(vec, a, 0, stream);
+        return mask ? launch_fwd_vec<true>(vec, a, stream) : launch_fwd_vec<false>(vec, a, stream);
     }
     while (vec > 1 && W % vec != 0) vec >>= 1;
-    geom_2d(a.g, B, H, W, vec, 256, 32, 1);
-    const size_t smem = (size_t)3 * (a.g.TH + 2) * (a.g.TWg + 2) * vec * sizeof(float);
-    return mask ? launch_fwd_vec<true, true>(vec, a, smem, stream) : launch_fwd_vec<true, false>(vec, a, smem, stream);
+    FwdRowsArgs r;
+    memset(&r, 0, sizeof(r));
+    r.ch = a.ch;
+    r.img = img; r.mask = mask; r.params = params; r.target = target; r.out = out; r.l1_sum = l1_sum;
+    r.part_l1 = w.part_l1; r.counters = w.counters; r.mask_ch = mask_ch; r.pstride = pstride; r.raw = a.raw;
+    for (int k = 1; k < n_ops; ++k)
+        if (a.ch.op[k - 1] >= 0 || ((r.clamped >> (k - 1)) & 1)) r.clamped |= 1 << k;
+    return mask ? launch_fwd_rows_vec<true>(vec, r, B, H, W, stream) : launch_fwd_rows_vec<false>(vec, r, B, H, W, stream);
 }
 
 int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long long n, void *ws, size_t ws_bytes,

@@ -10,17 +10,15 @@
 //
 // Data layout: images NCHW planar fp32; a thread owns VEC consecutive pixels of the three planes
 // (128-bit coalesced accesses for VEC = 4).  Per-(image, op) tables (curve slopes / offsets,
-// scalars) live in shared memory.  A sharpness operator turns the launch into a 2-D tiling with a
-// halo: the operators before it are evaluated on tile + halo into shared memory, the 3x3 stencil
-// and the operators after it run from there, so the chain still makes one pass over HBM.
+// scalars) live in shared memory.  A sharpness operator turns the launch into a row pipeline down a
+// column strip (chain_fwd_rows_kernel), so the chain still makes one pass over HBM.
 // Reductions (L1, parameter gradients) are warp-shuffle -> shared -> one partial per CTA; the last
 // CTA of each image sums the partials in a fixed order (deterministic, no float atomics).
 #pragma once
 #include <cstdio>
 #include <cstring>
 
-#include "t2o_common.cuh"
-#include "../../include/t2o.h"
+#include "t2o_step_kernels.cuh"
 
 namespace t2o {
 
@@ -54,38 +52,6 @@ __device__ __forceinline__ void ld_mask_t(const float *mask_b, int mask_ch, size
     if constexpr (HM) ld_mask<VEC>(mask_b, mask_ch, plane, off, m);
 }
 
-// 5-point stencil of one plane around a VEC-pixel group held in a shared-memory region.
-//   row: pointer to the group's first float in its row;  rstride: floats per region row
-//   lo / hi: first / one-past-last valid float offset relative to `row` within that row
-template <int VEC>
-__device__ __forceinline__ void stencil_group(const float *row, int rstride, int lo, int hi,
-                                              float (&ctr)[VEC], float (&lap)[VEC]) {
-    float up[VEC], dn[VEC];
-    lds_vec<VEC>(row, ctr);
-    lds_vec<VEC>(row - rstride, up);
-    lds_vec<VEC>(row + rstride, dn);
-    const float lf = (-1 >= lo) ? row[-1] : 0.0f;
-    const float rt = (VEC < hi) ? row[VEC] : 0.0f;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        const float l = v > 0 ? ctr[v - 1] : lf;
-        const float r = v < VEC - 1 ? ctr[v + 1] : rt;
-        lap[v] = laplace(ctr[v], up[v], dn[v], l, r);
-    }
-}
-
-// n / d for the small region indices of the 2-D kernels: mul = ceil(2^32 / d), exact for n * d < 2^32
-__device__ __forceinline__ int fast_div(int n, int d, unsigned int mul) {
-    return d == 1 ? n : (int)__umulhi((unsigned int)n, mul);
-}
-
-template <int VEC>
-__device__ __forceinline__ void zero_px(float (&x)[3][VEC]) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) x[c][v] = 0.0f;
-}
 template <int VEC>
 __device__ __forceinline__ float l1_px(const float (&x)[3][VEC], const float (&t)[3][VEC]) {
     float s = 0.0f;
@@ -108,9 +74,8 @@ struct FwdArgs {
     int raw;                // T2O_FLAG_RAW_PROCESS
 };
 
-template <int VEC, bool SHARP, bool HM>
+template <int VEC, bool HM>
 __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ FwdArgs a) {
-    extern __shared__ __align__(16) float dyn_smem[];
     __shared__ __align__(16) float tabs[MAX_CHAIN][TAB];
     __shared__ float red[32];
     __shared__ int last_flag;
@@ -129,7 +94,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
     __syncthreads();
 
     float l1 = 0.0f;
-    if constexpr (!SHARP) {
+    {
         const long long g0 = (long long)tile * a.g.tile_groups;
         long long g1 = g0 + a.g.tile_groups;
         if (g1 > a.g.ngroups) g1 = a.g.ngroups;
@@ -165,63 +130,6 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
             }
             if (out_b) st_px<VEC>(out_b, plane, off, x);
         }
-    } else {
-        const int H = a.g.H, Wg = a.g.Wg, TH = a.g.TH, TWg = a.g.TWg;
-        const int ty = fast_div(tile, a.g.tiles_x, a.g.mul_tiles_x), tx = tile - ty * a.g.tiles_x;
-        const int y0 = ty * TH, xg0 = tx * TWg;
-        const int RH = TH + 2, RWg = TWg + 2;
-        const int rstride = RWg * VEC;                 // floats per region row
-        const int cstride = RH * rstride;              // floats per region plane
-        const int sp = a.ch.sharp;                     // 0 <= sp < n
-        // ---- phase A: operators before the stencil on tile + halo -> shared memory
-        for (int idx = tid; idx < RH * RWg; idx += NT) {
-            const int ry = fast_div(idx, RWg, a.g.mul_rw), rxg = idx - ry * RWg;
-            const int y = y0 - 1 + ry, xg = xg0 - 1 + rxg;
-            float x[3][VEC];
-            if (y >= 0 && y < H && xg >= 0 && xg < Wg) {
-                const size_t off = (size_t)y * a.g.W + (size_t)xg * VEC;
-                float m[3][VEC];
-                ld_px<VEC>(img_b, plane, off, x);
-                if (sp > 0) {
-                    ld_mask_t<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-                    for (int k = 0; k < sp; ++k) apply_op_vec<VEC, HM>(a.ch.op[k], tabs[k], L, x, m);
-                }
-            } else {                                    // zero padding of the stencil input
-                zero_px<VEC>(x);
-            }
-            float *dst = dyn_smem + ry * rstride + rxg * VEC;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * cstride, x[c]);
-        }
-        __syncthreads();
-        // ---- phase B: stencil + remaining operators on the tile interior
-        const float p = tabs[sp][0];
-        for (int idx = tid; idx < TH * TWg; idx += NT) {
-            const int ly = fast_div(idx, TWg, a.g.mul_tw), lxg = idx - ly * TWg;
-            const int y = y0 + ly, xg = xg0 + lxg;
-            if (y >= H || xg >= Wg) continue;
-            const size_t off = (size_t)y * a.g.W + (size_t)xg * VEC;
-            float x[3][VEC], m[3][VEC];
-            ld_mask_t<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-            const float *src = dyn_smem + (ly + 1) * rstride + (lxg + 1) * VEC;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float ctr[VEC], lap[VEC];
-                stencil_group<VEC>(src + c * cstride, rstride, -(lxg + 1) * VEC, (RWg - lxg - 1) * VEC, ctr, lap);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float yv = fmaf(p, lap[v], ctr[v]);
-                    x[c][v] = raw ? yv : sat01(blend<HM>(yv, ctr[v], m[c][v]));
-                }
-            }
-            for (int k = sp + 1; k < n; ++k) apply_op_vec<VEC, HM>(a.ch.op[k], tabs[k], L, x, m);
-            if (tgt_b) {
-                float t[3][VEC];
-                ld_px<VEC>(tgt_b, plane, off, t);
-                l1 += l1_px<VEC>(x, t);
-            }
-            if (out_b) st_px<VEC>(out_b, plane, off, x);
-        }
     }
 
     if (a.l1_sum) {
@@ -231,6 +139,132 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
         if (arrive_is_last(a.counters + b, (unsigned)ntiles, &last_flag)) {
             float v = 0.0f;
             for (int t = tid; t < ntiles; t += NT) v += __ldcg(a.part_l1 + (size_t)b * ntiles + t);
+            v = block_sum(v, red);
+            if (tid == 0) a.l1_sum[b] = v;
+        }
+    }
+}
+
+// =========================================================================================== forward, one stencil
+// Row pipeline down a column strip (same layout as step_sharp_kernel): every warp owns one image row per step;
+// phase A writes X = (operators before the stencil)(img) of row rA into a ring of NW + 2 rows, phase B applies
+// the stencil and the remaining operators to row rA - 1 and stores / scores it.  One pass over HBM; only the two
+// halo rows per band and the two halo lanes per strip are recomputed.
+struct FwdRowsArgs {
+    ChainDesc ch;
+    StepGeom g;
+    const float *img, *mask, *params, *target;
+    float *out, *l1_sum;
+    float *part_l1;
+    unsigned int *counters;
+    int mask_ch, pstride;
+    int raw;                // T2O_FLAG_RAW_PROCESS
+    int clamped;            // bit k: the input of operator k lies in [0, 1]
+};
+
+template <int VEC, bool HM>
+__global__ void __launch_bounds__(NT) chain_fwd_rows_kernel(const __grid_constant__ FwdRowsArgs a) {
+    constexpr int NW = NT / 32, RING = NW + 2;
+    constexpr int ROWF = 34 * VEC, SLOTF = 3 * ROWF, RINGF = RING * SLOTF;
+    extern __shared__ __align__(16) float dyn_smem[];           // the X ring
+    __shared__ __align__(16) float tabs[MAX_CHAIN][TAB];
+    __shared__ float red[32];
+    __shared__ int last_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int strip = chunk % a.g.strips, band = chunk / a.g.strips;
+    const int n = a.ch.n, L = a.ch.L, sp = a.ch.sharp;
+    const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
+    const size_t plane = (size_t)H * W;
+    const float *img_b = a.img + (size_t)b * 3 * plane;
+    const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
+    float *out_b = a.out ? a.out + (size_t)b * 3 * plane : nullptr;
+    const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
+    const bool raw = a.raw != 0;
+
+    const int HL = a.g.HL;
+    const int gx = strip * a.g.IW - HL + lane;
+    const bool lane_on = HL > 0 || lane < Wg;
+    const bool col_ok = lane_on && gx >= 0 && gx < Wg;
+    const bool interior = col_ok && lane >= HL && lane < 32 - HL;
+    const int ya = band * a.g.HB;
+    const int yb = ya + a.g.HB < H ? ya + a.g.HB : H;
+
+    float *Xc = dyn_smem + (1 + lane) * VEC;
+    for (int i = tid; i < RINGF; i += NT) dyn_smem[i] = 0.0f;
+    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, tabs[tid]);
+    __syncthreads();
+
+    const float p = tabs[sp][0];
+    const int clamped = a.clamped;
+    float l1 = 0.0f;
+    int rA = ya - 1 + warp, sA = warp;
+#pragma unroll 1
+    for (int s = 0; s < a.g.steps; ++s) {
+        // ---------------- phase A: X on row rA
+        if (lane_on) {
+            float x[3][VEC];
+            if (col_ok && rA >= 0 && rA < H && rA <= yb) {
+                const size_t off = (size_t)rA * W + (size_t)gx * VEC;
+                float m[3][VEC];
+                ld_px<VEC>(img_b, plane, off, x);
+                if (sp > 0) {
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+#pragma unroll 1
+                    for (int k = 0; k < sp; ++k) fwd_op_grp<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+                }
+            } else {
+                zero3<VEC>(x);
+            }
+            float *dst = Xc + sA * SLOTF;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, x[c]);
+        }
+        __syncthreads();
+        // ---------------- phase B: stencil + remaining operators on row rA - 1
+        {
+            const int rB = rA - 1;
+            if (interior && rB >= ya && rB < yb) {
+                const int sB = sA >= 1 ? sA - 1 : RING - 1;
+                const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
+                const size_t off = (size_t)rB * W + (size_t)gx * VEC;
+                float x[3][VEC], m[3][VEC];
+                ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+                const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float ctr[VEC], lap[VEC];
+                    stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr, lap);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float yv = fmaf(p, lap[v], ctr[v]);
+                        x[c][v] = raw ? yv : sat01(blend<HM>(yv, ctr[v], m[c][v]));
+                    }
+                }
+#pragma unroll 1
+                for (int k = sp + 1; k < n; ++k) fwd_op_grp<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+                if (tgt_b) {
+                    float t[3][VEC];
+                    ld_px<VEC>(tgt_b, plane, off, t);
+                    l1 += l1_px<VEC>(x, t);
+                }
+                if (out_b) st_px<VEC>(out_b, plane, off, x);
+            }
+        }
+        __syncthreads();
+        rA += NW;
+        sA += NW;
+        if (sA >= RING) sA -= RING;
+    }
+
+    if (a.l1_sum) {
+        const float s = block_sum(l1, red);
+        const int nchunks = a.g.nchunks;
+        if (tid == 0) a.part_l1[(size_t)b * nchunks + chunk] = s;
+        if (arrive_is_last(a.counters + b, (unsigned)nchunks, &last_flag)) {
+            float v = 0.0f;
+            for (int t = tid; t < nchunks; t += NT) v += __ldcg(a.part_l1 + (size_t)b * nchunks + t);
             v = block_sum(v, red);
             if (tid == 0) a.l1_sum[b] = v;
         }
@@ -272,17 +306,6 @@ __global__ void __launch_bounds__(NT) l1_sum_kernel(const __grid_constant__ L1Ar
         v = block_sum(v, red);
         if (tid == 0) a.l1_sum[b] = v;
     }
-}
-
-// Opt in to the dynamic shared memory a launch needs.  The 48 KB default limit counts static +
-// dynamic bytes, so anything above 32 KB is configured explicitly.
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    if (bytes > 32 * 1024) {
-        if (bytes > 227 * 1024) return T2O_ERR_UNSUPPORTED;
-        T2O_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    }
-    return T2O_OK;
 }
 
 }  // namespace t2o

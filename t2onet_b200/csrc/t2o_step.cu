@@ -95,7 +95,8 @@ static void geom_step_flat(StepGeom &g, int B, int H, int W, int vec, int slots,
     if (g.nchunks < 1) g.nchunks = 1;
 }
 
-static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT) {
+// rows_extra: halo rows a band computes beyond its own (4 for the forward + backward pipeline, 2 for the forward one)
+void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT, int rows_extra) {
     const int SNW = SNT / 32;
     memset(&g, 0, sizeof(g));
     g.B = B; g.H = H; g.W = W;
@@ -113,7 +114,7 @@ static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots,
     for (int nb = 1; nb <= max_nb; ++nb) {
         const int hb = (H + nb - 1) / nb;
         const int bands = (H + hb - 1) / hb;
-        const int steps = (hb + 4 + SNW - 1) / SNW;
+        const int steps = (hb + rows_extra + SNW - 1) / SNW;
         const long long ctas = (long long)B * g.strips * bands;
         const long long waves = (ctas + slots - 1) / slots;
         const long long cost = waves * (steps + 1);
@@ -121,7 +122,7 @@ static void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots,
     }
     g.HB = best_hb;
     g.bands = (H + g.HB - 1) / g.HB;
-    g.steps = (g.HB + 4 + SNW - 1) / SNW;
+    g.steps = (g.HB + rows_extra + SNW - 1) / SNW;
     g.nchunks = g.strips * g.bands;
 }
 
@@ -159,7 +160,7 @@ static int launch_step(StepArgs &a, cudaStream_t stream) {
         smem = rows_smem_bytes(a.ch, VEC, HM, NTH);
         int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH>, smem);
         if (st) return st;
-        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH>, NTH, smem), NTH);
+        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH>, NTH, smem), NTH, 4);
         dim3 grid(a.g.nchunks, B);
         step_sharp_kernel<VEC, HM, NTH><<<grid, NTH, smem, stream>>>(a);
     }
