@@ -102,7 +102,7 @@ void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SN
 
 template <int VEC, bool HM>
 static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
-    const size_t smem = (size_t)(NT / 32 + 2) * 3 * 34 * VEC * sizeof(float);
+    const size_t smem = (size_t)(2 * (NT / 32) + 2) * 3 * 34 * VEC * sizeof(float);
     static int resident = 0;
     if (resident == 0) {
         int nb = 0;

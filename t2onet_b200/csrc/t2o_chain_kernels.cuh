@@ -163,8 +163,10 @@ struct FwdRowsArgs {
 };
 
 template <int VEC, bool HM>
-__global__ void __launch_bounds__(NT) chain_fwd_rows_kernel(const __grid_constant__ FwdRowsArgs a) {
-    constexpr int NW = NT / 32, RING = NW + 2;
+__global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_constant__ FwdRowsArgs a) {
+    // ring of 2 NW + 2 rows: phase A of the next step never overwrites a row phase B of this step still reads,
+    // so one barrier per step (after phase A) is enough
+    constexpr int NW = NT / 32, RING = 2 * NW + 2;
     constexpr int ROWF = 34 * VEC, SLOTF = 3 * ROWF, RINGF = RING * SLOTF;
     extern __shared__ __align__(16) float dyn_smem[];           // the X ring
     __shared__ __align__(16) float tabs[MAX_CHAIN][TAB];
@@ -190,32 +192,38 @@ __global__ void __launch_bounds__(NT) chain_fwd_rows_kernel(const __grid_constan
     const bool interior = col_ok && lane >= HL && lane < 32 - HL;
     const int ya = band * a.g.HB;
     const int yb = ya + a.g.HB < H ? ya + a.g.HB : H;
+    const size_t coff = (size_t)gx * VEC;
 
     float *Xc = dyn_smem + (1 + lane) * VEC;
     for (int i = tid; i < RINGF; i += NT) dyn_smem[i] = 0.0f;
     if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, tabs[tid]);
-    __syncthreads();
 
-    const float p = tabs[sp][0];
     const int clamped = a.clamped;
     float l1 = 0.0f;
     int rA = ya - 1 + warp, sA = warp;
+    // L1 prefetches one phase ahead (this kernel keeps ~5 CTAs per SM and a small ring, so the L1 has room)
+    if (col_ok && rA >= 0 && rA < H && rA <= yb) prefetch_px(img_b, plane, (size_t)rA * W + coff);
+    __syncthreads();
+    const float p = tabs[sp][0];
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
+        const int rB = rA - 1;
+        const bool do_b = interior && rB >= ya && rB < yb;
         // ---------------- phase A: X on row rA
         if (lane_on) {
             float x[3][VEC];
+            if (do_b && tgt_b) prefetch_px(tgt_b, plane, (size_t)rB * W + coff);           // phase B's target row
             if (col_ok && rA >= 0 && rA < H && rA <= yb) {
-                const size_t off = (size_t)rA * W + (size_t)gx * VEC;
-                float m[3][VEC];
+                const size_t off = (size_t)rA * W + coff;
                 ld_px<VEC>(img_b, plane, off, x);
                 if (sp > 0) {
+                    float m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
 #pragma unroll 1
                     for (int k = 0; k < sp; ++k) fwd_op_grp<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
                 }
             } else {
-                zero3<VEC>(x);
+                zero3<VEC>(x);                                              // outside the image: the stencil's zero padding
             }
             float *dst = Xc + sA * SLOTF;
 #pragma unroll
@@ -224,11 +232,12 @@ __global__ void __launch_bounds__(NT) chain_fwd_rows_kernel(const __grid_constan
         __syncthreads();
         // ---------------- phase B: stencil + remaining operators on row rA - 1
         {
-            const int rB = rA - 1;
-            if (interior && rB >= ya && rB < yb) {
+            const int rN = rA + NW;                                         // phase A's row of the next step
+            if (col_ok && rN >= 0 && rN < H && rN <= yb) prefetch_px(img_b, plane, (size_t)rN * W + coff);
+            if (do_b) {
                 const int sB = sA >= 1 ? sA - 1 : RING - 1;
                 const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
-                const size_t off = (size_t)rB * W + (size_t)gx * VEC;
+                const size_t off = (size_t)rB * W + coff;
                 float x[3][VEC], m[3][VEC];
                 ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
                 const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
@@ -252,7 +261,6 @@ __global__ void __launch_bounds__(NT) chain_fwd_rows_kernel(const __grid_constan
                 if (out_b) st_px<VEC>(out_b, plane, off, x);
             }
         }
-        __syncthreads();
         rA += NW;
         sA += NW;
         if (sA >= RING) sA -= RING;
