@@ -103,6 +103,16 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(clocks)}
 
 
+def profiled_traffic(key):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            e = json.load(f)[key]
+        return e['dram_read_bytes'] + e['dram_write_bytes'], e['source']
+    except Exception:
+        return None, None
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -241,33 +251,64 @@ def run_ours(args, wl):
         ms, ms_eager = t.tolist()
     value = world * px_step * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the public API from pinned host memory
+    # ---- end to end through the public API from pinned host memory: every step copies its inputs host -> device,
+    # runs the prepared step, and copies the loss terms and parameter gradients back; two steps are in flight (two
+    # streams with their own device buffers), the host consumes the result of step i before it issues step i + 2
+    NSLOT = 2
     himg = [b[0].cpu().pin_memory() for b in batches[:2]]
     htgt = [b[1].cpu().pin_memory() for b in batches[:2]]
-    hparams = [[p.cpu().pin_memory() for p in b[2]] for b in batches[:2]]
-    res_l1 = torch.empty(B, pin_memory=True)
-    res_gp = torch.empty(B, 36, pin_memory=True)
+    hpar = [p.cpu().pin_memory() for p in packed[:2]]
+    streams = [torch.cuda.Stream() for _ in range(NSLOT)]
+    dimg = [torch.empty_like(batches[0][0]) for _ in range(NSLOT)]
+    dtgt = [torch.empty_like(batches[0][1]) for _ in range(NSLOT)]
+    dpar = [torch.empty_like(packed[0]) for _ in range(NSLOT)]
+    res_l1 = [torch.empty(B, pin_memory=True) for _ in range(NSLOT)]
+    res_gp = [torch.empty(B, 36, pin_memory=True) for _ in range(NSLOT)]
+    fused_e2e = [TF.FusedStep(CHAIN, B, H, W, dev, want_out=True, want_grad_img=False, reuse_outputs=True) for _ in range(NSLOT)]
+    done = [None] * NSLOT
+    losses = []
 
     def e2e_step(i):
-        j = i % len(himg)
-        img = himg[j].to(dev, non_blocking=True)
-        tgt = htgt[j].to(dev, non_blocking=True)
-        params = [p.to(dev, non_blocking=True) for p in hparams[j]]
-        _, l1, gp, _ = fused[j](img, torch.cat(params, 1), tgt)
-        res_l1.copy_(l1, non_blocking=True)
-        res_gp.copy_(gp, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller consumes the loss every step
+        s, j = i % NSLOT, i % len(himg)
+        if done[s] is not None:
+            done[s].synchronize()                       # the caller consumes the loss of step i - NSLOT
+            losses.append(float(res_l1[s][0]))
+        with torch.cuda.stream(streams[s]):
+            dimg[s].copy_(himg[j], non_blocking=True)
+            dtgt[s].copy_(htgt[j], non_blocking=True)
+            dpar[s].copy_(hpar[j], non_blocking=True)
+            _, l1, gp, _ = fused_e2e[s](dimg[s], dpar[s], dtgt[s])
+            res_l1[s].copy_(l1, non_blocking=True)
+            res_gp[s].copy_(gp, non_blocking=True)
+            done[s] = torch.cuda.Event()
+            done[s].record()
 
-    for i in range(3):
-        e2e_step(i)
-    e2e_steps = max(3, min(args.steps, 50))
-    ms_e2e = timed_region(e2e_step, e2e_steps, barrier)
+    def e2e_region(steps):
+        cur = torch.cuda.current_stream()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for st in streams:
+            st.wait_event(start)
+        for i in range(steps):
+            e2e_step(i)
+        for st in streams:
+            cur.wait_stream(st)
+        end.record()
+        barrier()
+        for s in range(NSLOT):
+            done[s] = None
+        return start.elapsed_time(end)
+
+    e2e_region(4)
+    e2e_steps = max(4, min(args.steps, 50))
+    ms_e2e = e2e_region(e2e_steps)
     if dist is not None:
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = t.item()
     e2e_value = world * px_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
-    h2d = 2 * px_step * 12 + sum(p.numel() * 4 for p in hparams[0])
+    h2d = 2 * px_step * 12 + hpar[0].numel() * 4
     d2h = B * 4 + B * 36 * 4
 
     if rank != 0:
@@ -277,6 +318,7 @@ def run_ours(args, wl):
     peak, peak_src = measured_peak_hbm()
     kernel_ms = ms / args.steps
     achieved = BYTES_PER_PX_FUSED * px_step / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(args.workload)
     line = {
         'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': value, 'unit': 'Mpixel/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': kernel_ms, 'higher_is_better': True,
@@ -289,12 +331,15 @@ def run_ours(args, wl):
                    'eager_ms_per_step': ms_eager / args.steps},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'Mpixel/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
+                'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps,
+                'how': 'FusedStep from pinned host buffers, %d steps in flight on %d streams' % (NSLOT, NSLOT)},
         'gpu_launches': args.steps,
-        'roofline': {'bound': 'hbm', 'kernel': 'chain_bwd_kernel (fused forward + L1 + backward, one launch per step)',
+        'roofline': {'bound': 'hbm', 'kernel': 'step_sharp_kernel<4,0,256,0> (fused forward + L1 + backward, one launch per step)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0},
+                     'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram read + write)', 'traffic_source': traffic_src,
+                     'algorithmic_bytes': BYTES_PER_PX_FUSED * px_step, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0,
+                     'note': 'FP32-issue-bound in practice (DESIGN.md section 4): ~730 thread-instructions per pixel'},
     }
     if world == 1 and not args.no_extras:
         line['cpu_baseline'] = cpu_baseline(wl)
@@ -318,6 +363,10 @@ def cpu_baseline(wl):
     dt = time.perf_counter() - t0
     return {'value': B * H * W * n / dt / 1e6, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': 'port',
             'sample': '%d steps of %dx3x%dx%d, 6-op chain fwd+L1+bwd (oracle/ops.py, torch CPU fp32 autograd)' % (n, B, H, W)}
+
+
+def fused_scale(B, H, W, dev):
+    return torch.full((B,), 1.0 / (B * 3 * H * W), device=dev, dtype=torch.float32)
 
 
 def extras(TF, dev, wl):
@@ -357,6 +406,62 @@ def extras(TF, dev, wl):
         torch.cuda.empty_cache()
     except Exception as exc:   # report, never hide
         ex['c4'] = {'error': repr(exc)}
+    # ---- single operators at the C4 shape: Executor.execute forward (24 B/px) and its autograd backward (36 B/px:
+    # img + grad_out read, grad_img written) -- the launches the Actor actually issues, one operator per decoding step
+    try:
+        B, H, W = 16, 2048, 3072
+        px = B * H * W
+        gen = torch.Generator().manual_seed(10 + 5000)
+        dgen = torch.Generator(device=dev).manual_seed(10 + 5000)
+        img = torch.rand(B, 3, H, W, generator=dgen, device=dev)
+        gout = torch.randn(B, 3, H, W, generator=dgen, device=dev)
+        ops_tab = {}
+        names = {0: 'brightness', 1: 'contrast', 2: 'saturation', 3: 'color', 5: 'tone', 6: 'sharpness', 8: 'exposure', 9: 'whitebalance'}
+        prm = dict(zip(CHAIN, make_params(B, gen, dev)))
+        prm[8] = torch.rand(B, 1, generator=gen).to(dev) * 2 - 1
+        prm[9] = 0.4 + 1.4 * torch.rand(B, 3, generator=gen).to(dev)
+        for op, name in names.items():
+            p = prm[op].contiguous()
+            n = p.shape[1]
+            t_f = bench(lambda: TF._forward_raw([op], [0], img, None, 0, p, n, None, True, False, 8), 5)
+            t_b = bench(lambda: TF._backward_raw([op], [0], img, None, 0, p, n, gout, None, None, True, False, False, 8), 5)
+            ops_tab[name] = {'fwd_ms': t_f, 'fwd_GBps_at_24B_px': 24 * px / t_f / 1e6, 'fwd_frac_of_measured_peak': 24 * px / t_f / 1e6 / peak,
+                             'bwd_ms': t_b, 'bwd_GBps_at_36B_px': 36 * px / t_b / 1e6, 'bwd_frac_of_measured_peak': 36 * px / t_b / 1e6 / peak}
+        ex['c4_single_ops'] = ops_tab
+        del img, gout
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        ex['c4_single_ops'] = {'error': repr(exc)}
+    # ---- per-row operator steps (Actor call sites models/actor.py:156-170): every row its own operator
+    try:
+        import random
+        rnd = random.Random(10 + 6000)
+        for tag, (B, H, W) in (('c2', (64, 128, 128)), ('b64_512', (64, 512, 512))):
+            px = B * H * W
+            gen = torch.Generator().manual_seed(10 + 6000)
+            img = torch.rand(B, 3, H, W, generator=gen).to(dev)
+            tgt = torch.rand(B, 3, H, W, generator=gen).to(dev)
+            gout = torch.randn(B, 3, H, W, generator=gen).to(dev)
+            plist = dict(zip(CHAIN, make_params(B, gen, 'cpu')))
+            res, scale = {}, fused_scale(B, H, W, dev)
+            for K in (1, 5):
+                rows = [rnd.sample(CHAIN, K) for _ in range(B)]
+                params = torch.zeros(B, K * 24)
+                for b in range(B):
+                    for k, op in enumerate(rows[b]):
+                        v = plist[op][b]
+                        params[b, k * 24:k * 24 + v.numel()] = v
+                params = params.to(dev)
+                ops_dev, ops_host = TF._prep_row_ops(rows, B, torch.device(dev))
+                t_f = bench(lambda: TF._rows_forward_raw(ops_dev, ops_host, img, None, 0, params, None, True, False, 8), 10)
+                t_b = bench(lambda: TF._rows_backward_raw(ops_dev, ops_host, img, None, 0, params, gout, None, None, True, False, False, 8), 10)
+                t_s = bench(lambda: TF._rows_backward_raw(ops_dev, ops_host, img, None, 0, params, None, tgt, scale, False, True, True, 8), 10)
+                res['K%d' % K] = {'forward_ms': t_f, 'forward_GBps_at_24B_px': 24 * px / t_f / 1e6,
+                                  'backward_ms': t_b, 'backward_GBps_at_36B_px': 36 * px / t_b / 1e6,
+                                  'fused_step_ms': t_s, 'fused_step_Mpixel_per_s': px / t_s / 1e3}
+            ex['per_row_ops_' + tag] = {'workload': '%dx3x%dx%d, a random operator (K=1) / a random 5-operator order (K=5) per row' % (B, H, W), **res}
+    except Exception as exc:
+        ex['per_row_ops'] = {'error': repr(exc)}
     # ---- planner candidate scoring: 64 images x 8 states x 168 candidates per state (SURVEY.md section 8d, C3 sweep)
     try:
         S, H, W = 512, 128, 128

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define T2O_VERSION 100          /* major*100 + minor */
+#define T2O_VERSION 101          /* major*100 + minor */
 #define T2O_MAX_CHAIN 8          /* operators fused in one launch */
 #define T2O_MAX_CURVE_STEPS 8    /* cfg.curve_steps (options/fiveK_base_options.py:50) */
 #define T2O_MAX_OP_PARAMS 24     /* color: 3 * curve_steps */
@@ -116,6 +116,35 @@ int t2o_chain_backward(int n_ops, const int *op_ids /*host*/, const int *param_o
                        float *grad_params, float *grad_img, float *out, float *l1_sum,
                        int B, int H, int W, int curve_steps,
                        void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
+ * Per-row chains: the Actor call sites (models/actor.py:100-114 divide_op_group + :165,252,340): every batch row
+ * applies its OWN operator (K = 1 per decoding step; K > 1 = K decoding steps with known parameters).  Replaces
+ * the reference's group-by-operator loop (torch.unique + index_select gathers + one Executor.execute per group +
+ * cat + index_select back) by one launch per tiling over the original tensors: no image copies, no host sync.
+ *   row_ops       (B, K) int32, DEVICE: operator id of step k of row b (T2O_OP_IDENTITY = <END>, passes through)
+ *   row_ops_host  the same ids on the HOST, or NULL.  With a host copy the rows are validated up front (an
+ *                 operator type twice in one row of a backward call, inpaint, a second stencil -> error status)
+ *                 and only the tilings some row needs are launched.  NULL requires K == 1; the kernels then
+ *                 treat an invalid id as identity and set bit 0 of *status (DEVICE uint32, may be NULL).
+ *   params        (B, param_stride): step k of a row reads its parameters at column k * param_slot
+ *                 (param_slot >= 3 * curve_steps; 24 = the Actor's zero-padded parameter rows, models/actor.py:166)
+ *   grad_params   same layout, every column written (0 outside the row's used slots)
+ * Everything else as in t2o_chain_forward / t2o_chain_backward.
+ */
+int t2o_rows_forward(int K, const int32_t *row_ops, const int32_t *row_ops_host /*host*/, int param_slot,
+                     const float *img, const float *mask, int mask_ch,
+                     const float *params, int param_stride,
+                     const float *target, float *out, float *l1_sum, uint32_t *status,
+                     int B, int H, int W, int curve_steps,
+                     void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+int t2o_rows_backward(int K, const int32_t *row_ops, const int32_t *row_ops_host /*host*/, int param_slot,
+                      const float *img, const float *mask, int mask_ch,
+                      const float *params, int param_stride,
+                      const float *grad_out, const float *target, const float *grad_l1,
+                      float *grad_params, float *grad_img, float *out, float *l1_sum, uint32_t *status,
+                      int B, int H, int W, int curve_steps,
+                      void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 
 /* Per-image sum |a - b| over n floats per image: get_dist(x1, x2, 'L1') * numel, utils/beam_search.py:170-173. */
 int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_per_image,

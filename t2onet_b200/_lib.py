@@ -47,6 +47,12 @@ def _declare(lib):
     lib.t2o_chain_backward.restype = ci
     lib.t2o_chain_backward.argtypes = [ci, c_int_p, c_int_p, vp, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp,
                                        ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
+    lib.t2o_rows_forward.restype = ci
+    lib.t2o_rows_forward.argtypes = [ci, vp, c_int_p, ci, vp, vp, ci, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci,
+                                     vp, ctypes.c_size_t, vp]
+    lib.t2o_rows_backward.restype = ci
+    lib.t2o_rows_backward.argtypes = [ci, vp, c_int_p, ci, vp, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp,
+                                      ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
     lib.t2o_l1_sum.restype = ci
     lib.t2o_l1_sum.argtypes = [vp, vp, vp, ci, ctypes.c_int64, vp, ctypes.c_size_t, vp]
     lib.t2o_score_candidates.restype = ci
@@ -55,7 +61,8 @@ def _declare(lib):
 
 
 EXPORTS = ['t2o_version', 't2o_status_string', 't2o_last_cuda_error', 't2o_num_params', 't2o_workspace_bytes',
-           't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_l1_sum',
+           't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_rows_forward',
+           't2o_rows_backward', 't2o_l1_sum',
            't2o_score_candidates']
 
 
@@ -106,6 +113,19 @@ def workspace(device, nbytes):
         ws = torch.zeros(size, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+_status_words = {}
+
+
+def status_word(device):
+    """Per-device uint32 the per-row kernels flag invalid rows in (bit 0); see functional.rows_status()."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    w = _status_words.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=device)
+        _status_words[key] = w
+    return w
 
 
 def require_cuda(*tensors):

@@ -14,6 +14,13 @@ int chain_backward(int n_ops, const int *op_ids, const int *param_off, const flo
                    const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
                    float *grad_params, float *grad_img, float *out, float *l1_sum,
                    int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int rows_forward(int K, const int *row_ops, const int *row_ops_host, int slot, const float *img, const float *mask, int mask_ch,
+                 const float *params, int pstride, const float *target, float *out, float *l1_sum, unsigned int *status,
+                 int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int rows_backward(int K, const int *row_ops, const int *row_ops_host, int slot, const float *img, const float *mask, int mask_ch,
+                  const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
+                  float *grad_params, float *grad_img, float *out, float *l1_sum, unsigned int *status,
+                  int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
 int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long long n, void *ws, size_t ws_bytes,
                   cudaStream_t stream);
 size_t score_workspace_bytes(int S, int C, int H, int W);
@@ -71,6 +78,24 @@ int t2o_chain_backward(int n_ops, const int *op_ids, const int *param_off, const
     return t2o::chain_backward(n_ops, op_ids, param_off, img, mask, mask_ch, params, param_stride, grad_out, target, grad_l1,
                                grad_params, grad_img, out, l1_sum, B, H, W, curve_steps, workspace, workspace_bytes,
                                (cudaStream_t)stream);
+}
+
+int t2o_rows_forward(int K, const int32_t *row_ops, const int32_t *row_ops_host, int param_slot, const float *img,
+                     const float *mask, int mask_ch, const float *params, int param_stride, const float *target, float *out,
+                     float *l1_sum, uint32_t *status, int B, int H, int W, int curve_steps, void *workspace,
+                     size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::rows_forward(K, row_ops, row_ops_host, param_slot, img, mask, mask_ch, params, param_stride, target, out,
+                             l1_sum, status, B, H, W, curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_rows_backward(int K, const int32_t *row_ops, const int32_t *row_ops_host, int param_slot, const float *img,
+                      const float *mask, int mask_ch, const float *params, int param_stride, const float *grad_out,
+                      const float *target, const float *grad_l1, float *grad_params, float *grad_img, float *out,
+                      float *l1_sum, uint32_t *status, int B, int H, int W, int curve_steps, void *workspace,
+                      size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::rows_backward(K, row_ops, row_ops_host, param_slot, img, mask, mask_ch, params, param_stride, grad_out,
+                              target, grad_l1, grad_params, grad_img, out, l1_sum, status, B, H, W, curve_steps, workspace,
+                              workspace_bytes, (cudaStream_t)stream);
 }
 
 int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_per_image, void *workspace,

@@ -34,23 +34,8 @@ Workspace carve_workspace(void *ws, int B, int H, int W) {
 }
 
 static int make_desc(int n_ops, const int *op_ids, const int *param_off, int L, int pstride, ChainDesc &d) {
-    if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids || !param_off) return T2O_ERR_INVALID_ARG;
-    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
-    if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
-    d.n = n_ops; d.L = L; d.sharp = -1;
-    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
-    for (int k = 0; k < n_ops; ++k) {
-        const int op = op_ids[k];
-        if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
-        if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
-        if (param_off[k] < 0 || param_off[k] + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
-        if (op == OP_SHARPNESS) {
-            if (d.sharp >= 0) return T2O_ERR_UNSUPPORTED;
-            d.sharp = k;
-        }
-        d.op[k] = op; d.poff[k] = param_off[k];
-    }
-    return T2O_OK;
+    if (!param_off) return T2O_ERR_INVALID_ARG;
+    return build_chain_desc(n_ops, op_ids, param_off, 0, L, pstride, d);
 }
 
 static int pick_vec_flat(const void *const *ptrs, int nptr, size_t plane) {
@@ -84,48 +69,49 @@ static void geom_flat(Geom &g, int B, int H, int W, int vec) {
     g.tiles_per_cta = 1;
 }
 
-template <int VEC, bool HM>
+template <int VEC, bool HM, bool ROWS>
 static int launch_fwd(const FwdArgs &a, cudaStream_t stream) {
     dim3 grid(a.g.ntiles, a.g.B);
-    chain_fwd_kernel<VEC, HM><<<grid, NT, 0, stream>>>(a);
+    chain_fwd_kernel<VEC, HM, ROWS><<<grid, NT, 0, stream>>>(a);
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
 }
-template <bool HM>
+template <bool HM, bool ROWS>
 static int launch_fwd_vec(int vec, const FwdArgs &a, cudaStream_t stream) {
-    if (vec == 4) return launch_fwd<4, HM>(a, stream);
-    if (vec == 2) return launch_fwd<2, HM>(a, stream);
-    return launch_fwd<1, HM>(a, stream);
+    if (vec == 4) return launch_fwd<4, HM, ROWS>(a, stream);
+    if (vec == 2) return launch_fwd<2, HM, ROWS>(a, stream);
+    return launch_fwd<1, HM, ROWS>(a, stream);
 }
 
 void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT, int rows_extra);
 
-template <int VEC, bool HM>
+template <int VEC, bool HM, bool ROWS>
 static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
     const size_t smem = (size_t)(2 * (NT / 32) + 2) * 3 * 34 * VEC * sizeof(float);
     static int resident = 0;
     if (resident == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_fwd_rows_kernel<VEC, HM>, NT, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_fwd_rows_kernel<VEC, HM, ROWS>, NT, smem) != cudaSuccess || nb < 1) nb = 1;
         resident = nb;
     }
     geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident, NT, 2);
     dim3 grid(a.g.nchunks, B);
-    chain_fwd_rows_kernel<VEC, HM><<<grid, NT, smem, stream>>>(a);
+    chain_fwd_rows_kernel<VEC, HM, ROWS><<<grid, NT, smem, stream>>>(a);
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
 }
-template <bool HM>
+template <bool HM, bool ROWS>
 static int launch_fwd_rows_vec(int vec, FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
-    if (vec == 4) return launch_fwd_rows<4, HM>(a, B, H, W, stream);
-    if (vec == 2) return launch_fwd_rows<2, HM>(a, B, H, W, stream);
-    return launch_fwd_rows<1, HM>(a, B, H, W, stream);
+    if (vec == 4) return launch_fwd_rows<4, HM, ROWS>(a, B, H, W, stream);
+    if (vec == 2) return launch_fwd_rows<2, HM, ROWS>(a, B, H, W, stream);
+    return launch_fwd_rows<1, HM, ROWS>(a, B, H, W, stream);
 }
 
 int chain_forward(int n_ops, const int *op_ids, const int *param_off, const float *img, const float *mask, int mask_ch,
                   const float *params, int pstride, const float *target, float *out, float *l1_sum,
                   int B, int H, int W, int L, int flags, void *ws, size_t ws_bytes, cudaStream_t stream) {
     FwdArgs a;
+    memset(&a, 0, sizeof(a));
     if ((flags & ~T2O_FLAG_RAW_PROCESS) != 0 || ((flags & T2O_FLAG_RAW_PROCESS) && n_ops != 1)) return T2O_ERR_INVALID_ARG;
     a.raw = (flags & T2O_FLAG_RAW_PROCESS) ? 1 : 0;
     int st = make_desc(n_ops, op_ids, param_off, L, pstride, a.ch);
@@ -144,7 +130,7 @@ int chain_forward(int n_ops, const int *op_ids, const int *param_off, const floa
     int vec = pick_vec_flat(ptrs, 4, plane);
     if (a.ch.sharp < 0) {
         geom_flat(a.g, B, H, W, vec);
-        return mask ? launch_fwd_vec<true>(vec, a, stream) : launch_fwd_vec<false>(vec, a, stream);
+        return mask ? launch_fwd_vec<true, false>(vec, a, stream) : launch_fwd_vec<false, false>(vec, a, stream);
     }
     while (vec > 1 && W % vec != 0) vec >>= 1;
     FwdRowsArgs r;
@@ -152,9 +138,81 @@ int chain_forward(int n_ops, const int *op_ids, const int *param_off, const floa
     r.ch = a.ch;
     r.img = img; r.mask = mask; r.params = params; r.target = target; r.out = out; r.l1_sum = l1_sum;
     r.part_l1 = w.part_l1; r.counters = w.counters; r.mask_ch = mask_ch; r.pstride = pstride; r.raw = a.raw;
-    for (int k = 1; k < n_ops; ++k)
-        if (a.ch.op[k - 1] >= 0 || ((r.clamped >> (k - 1)) & 1)) r.clamped |= 1 << k;
-    return mask ? launch_fwd_rows_vec<true>(vec, r, B, H, W, stream) : launch_fwd_rows_vec<false>(vec, r, B, H, W, stream);
+    r.clamped = chain_clamped_bits(a.ch.op, n_ops);
+    return mask ? launch_fwd_rows_vec<true, false>(vec, r, B, H, W, stream) : launch_fwd_rows_vec<false, false>(vec, r, B, H, W, stream);
+}
+
+// Host-side check of per-row chains when the caller also has the operator ids on the host: validates every row and
+// reports which tilings are needed (bit 0: rows without a stencil, bit 1: rows with one).  Without a host copy only
+// single-operator rows are accepted (nothing but the id range can be wrong; the kernels flag that in *status).
+int rows_paths(int K, const int *row_ops_host, int B, int slot, int L, int pstride, bool backward, int &paths) {
+    if (K < 1 || K > MAX_CHAIN || slot < 1 || (long long)K * slot > pstride) return T2O_ERR_INVALID_ARG;
+    if (pstride > MAX_PSTRIDE || L < 1 || L > MAX_L || slot < 3 * L) return T2O_ERR_UNSUPPORTED;
+    if (!row_ops_host) {
+        if (K != 1) return T2O_ERR_INVALID_ARG;
+        paths = 3;
+        return T2O_OK;
+    }
+    paths = 0;
+    for (int b = 0; b < B; ++b) {
+        int st;
+        int sharp;
+        if (backward) {
+            StepDesc d;
+            st = build_step_desc(K, row_ops_host + (size_t)b * K, nullptr, slot, L, pstride, d);
+            sharp = d.sharp;
+        } else {
+            ChainDesc d;
+            st = build_chain_desc(K, row_ops_host + (size_t)b * K, nullptr, slot, L, pstride, d);
+            sharp = d.sharp;
+        }
+        if (st != T2O_OK) return st;
+        paths |= sharp >= 0 ? 2 : 1;
+    }
+    return T2O_OK;
+}
+
+// Per-row chains, forward (Actor call sites models/actor.py:165,252,340: one operator per batch row and decoding step).
+int rows_forward(int K, const int *row_ops, const int *row_ops_host, int slot, const float *img, const float *mask, int mask_ch,
+                 const float *params, int pstride, const float *target, float *out, float *l1_sum, unsigned int *status,
+                 int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!row_ops || !img || !params || B < 1 || H < 1 || W < 1) return T2O_ERR_INVALID_ARG;
+    if (mask && mask_ch != 1 && mask_ch != 3) return T2O_ERR_INVALID_ARG;
+    if (l1_sum && !target) return T2O_ERR_INVALID_ARG;
+    if (!out && !l1_sum) return T2O_ERR_INVALID_ARG;
+    if (l1_sum && (!ws || ws_bytes < chain_workspace_bytes(B, H, W, pstride))) return T2O_ERR_WORKSPACE;
+    if (B > 65535) return T2O_ERR_UNSUPPORTED;
+    int paths = 0;
+    int st = rows_paths(K, row_ops_host, B, slot, L, pstride, false, paths);
+    if (st != T2O_OK) return st;
+    Workspace w = carve_workspace(ws, B, H, W);
+    const size_t plane = (size_t)H * W;
+    const void *ptrs[] = {img, mask, target, out};
+    int vec = pick_vec_flat(ptrs, 4, plane);
+    if (paths & 2)
+        while (vec > 1 && W % vec != 0) vec >>= 1;
+    if (paths & 1) {
+        FwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ch.n = K; a.ch.L = L; a.ch.sharp = -1;
+        a.img = img; a.mask = mask; a.params = params; a.target = target; a.out = out; a.l1_sum = l1_sum;
+        a.part_l1 = w.part_l1; a.counters = w.counters; a.mask_ch = mask_ch; a.pstride = pstride;
+        a.row_ops = row_ops; a.rows_K = K; a.rows_slot = slot; a.status = status;
+        geom_flat(a.g, B, H, W, vec);
+        st = mask ? launch_fwd_vec<true, true>(vec, a, stream) : launch_fwd_vec<false, true>(vec, a, stream);
+        if (st != T2O_OK) return st;
+    }
+    if (paths & 2) {
+        FwdRowsArgs r;
+        memset(&r, 0, sizeof(r));
+        r.ch.n = K; r.ch.L = L; r.ch.sharp = -1;
+        r.img = img; r.mask = mask; r.params = params; r.target = target; r.out = out; r.l1_sum = l1_sum;
+        r.part_l1 = w.part_l1; r.counters = w.counters; r.mask_ch = mask_ch; r.pstride = pstride;
+        r.row_ops = row_ops; r.rows_K = K; r.rows_slot = slot; r.status = status;
+        st = mask ? launch_fwd_rows_vec<true, true>(vec, r, B, H, W, stream) : launch_fwd_rows_vec<false, true>(vec, r, B, H, W, stream);
+        if (st != T2O_OK) return st;
+    }
+    return T2O_OK;
 }
 
 int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long long n, void *ws, size_t ws_bytes,

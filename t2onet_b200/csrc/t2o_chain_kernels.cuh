@@ -62,6 +62,50 @@ __device__ __forceinline__ float l1_px(const float (&x)[3][VEC], const float (&t
     return s;
 }
 
+// Forward launch descriptor of one chain; host for uniform chains (t2o_chain.cu), device (once per CTA) for
+// per-row chains.  param_off == nullptr: operator k reads its parameters at column k * slot.
+T2O_HD int build_chain_desc(int n_ops, const int *op_ids, const int *param_off, int slot, int L, int pstride, ChainDesc &d) {
+    if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids) return T2O_ERR_INVALID_ARG;
+    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
+    if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
+    d.n = n_ops; d.L = L; d.sharp = -1;
+    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
+    for (int k = 0; k < n_ops; ++k) {
+        const int op = op_ids[k];
+        if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
+        if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
+        const int po = param_off ? param_off[k] : k * slot;
+        if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
+        if (op == OP_SHARPNESS) {
+            if (d.sharp >= 0) return T2O_ERR_UNSUPPORTED;
+            d.sharp = k;
+        }
+        d.op[k] = op; d.poff[k] = po;
+    }
+    return T2O_OK;
+}
+// bit k: the input of operator k lies in [0, 1] (some operator before it clamped its output)
+T2O_HD int chain_clamped_bits(const int *op, int n) {
+    int bits = 0;
+    for (int k = 1; k < n; ++k)
+        if (op[k - 1] >= 0 || ((bits >> (k - 1)) & 1)) bits |= 1 << k;
+    return bits;
+}
+// per-row chains: the row's descriptor, built by thread 0 (an invalid row becomes an identity chain and flags *status)
+__device__ __forceinline__ void rows_build_chain_desc(const int *row_ops, int K, int slot, int L, int pstride,
+                                                      unsigned int *status, int b, ChainDesc &d) {
+    if (threadIdx.x == 0) {
+        int ops[MAX_CHAIN];
+        for (int k = 0; k < MAX_CHAIN; ++k) ops[k] = k < K ? row_ops[(size_t)b * K + k] : OP_IDENTITY;
+        if (build_chain_desc(K, ops, nullptr, slot, L, pstride, d) != T2O_OK) {
+            for (int k = 0; k < MAX_CHAIN; ++k) ops[k] = OP_IDENTITY;
+            build_chain_desc(K, ops, nullptr, 0, L, pstride, d);
+            if (status) atomicOr(status, 1u);
+        }
+    }
+    __syncthreads();
+}
+
 // =========================================================================================== forward
 struct FwdArgs {
     ChainDesc ch;
@@ -72,17 +116,26 @@ struct FwdArgs {
     unsigned int *counters;
     int mask_ch, pstride;
     int raw;                // T2O_FLAG_RAW_PROCESS
+    const int *row_ops;     // per-row chains (ROWS kernels): (B, rows_K) operator ids in device memory
+    int rows_K, rows_slot;
+    unsigned int *status;
 };
 
-template <int VEC, bool HM>
+template <int VEC, bool HM, bool ROWS>
 __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ FwdArgs a) {
     __shared__ __align__(16) float tabs[MAX_CHAIN][TAB];
     __shared__ float red[32];
     __shared__ int last_flag;
+    __shared__ ChainDesc rdesc;
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y, tile = blockIdx.x;
-    const int n = a.ch.n, L = a.ch.L;
+    if constexpr (ROWS) {
+        rows_build_chain_desc(a.row_ops, a.rows_K, a.rows_slot, a.ch.L, a.pstride, a.status, b, rdesc);
+        if (rdesc.sharp >= 0) return;                       // rows with a stencil belong to chain_fwd_rows_kernel
+    }
+    const ChainDesc &ch = ROWS ? rdesc : a.ch;
+    const int n = ch.n, L = ch.L;
     const size_t plane = (size_t)a.g.H * a.g.W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
     const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
@@ -90,7 +143,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const bool raw = a.raw != 0;
 
-    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, tabs[tid]);
+    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, tabs[tid]);
     __syncthreads();
 
     float l1 = 0.0f;
@@ -107,7 +160,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
             ld_px<VEC>(img_b, plane, off1, x[1]);
             ld_mask_t<VEC, HM>(mask_b, a.mask_ch, plane, off0, m[0]);
             ld_mask_t<VEC, HM>(mask_b, a.mask_ch, plane, off1, m[1]);
-            for (int k = 0; k < n; ++k) apply_op_grp<VEC, 2, HM>(a.ch.op[k], tabs[k], L, x, m, raw);
+            for (int k = 0; k < n; ++k) apply_op_grp<VEC, 2, HM>(ch.op[k], tabs[k], L, x, m, raw);
             if (tgt_b) {
                 float t[3][VEC];
                 ld_px<VEC>(tgt_b, plane, off0, t);
@@ -122,7 +175,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
             float x[3][VEC], m[3][VEC];
             ld_px<VEC>(img_b, plane, off, x);
             ld_mask_t<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-            for (int k = 0; k < n; ++k) apply_op_vec<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, raw);
+            for (int k = 0; k < n; ++k) apply_op_vec<VEC, HM>(ch.op[k], tabs[k], L, x, m, raw);
             if (tgt_b) {
                 float t[3][VEC];
                 ld_px<VEC>(tgt_b, plane, off, t);
@@ -160,9 +213,12 @@ struct FwdRowsArgs {
     int mask_ch, pstride;
     int raw;                // T2O_FLAG_RAW_PROCESS
     int clamped;            // bit k: the input of operator k lies in [0, 1]
+    const int *row_ops;     // per-row chains (ROWS kernels)
+    int rows_K, rows_slot;
+    unsigned int *status;
 };
 
-template <int VEC, bool HM>
+template <int VEC, bool HM, bool ROWS>
 __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_constant__ FwdRowsArgs a) {
     // ring of 2 NW + 2 rows: phase A of the next step never overwrites a row phase B of this step still reads,
     // so one barrier per step (after phase A) is enough
@@ -172,11 +228,17 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
     __shared__ __align__(16) float tabs[MAX_CHAIN][TAB];
     __shared__ float red[32];
     __shared__ int last_flag;
+    __shared__ ChainDesc rdesc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int strip = chunk % a.g.strips, band = chunk / a.g.strips;
-    const int n = a.ch.n, L = a.ch.L, sp = a.ch.sharp;
+    if constexpr (ROWS) {
+        rows_build_chain_desc(a.row_ops, a.rows_K, a.rows_slot, a.ch.L, a.pstride, a.status, b, rdesc);
+        if (rdesc.sharp < 0) return;                        // rows without a stencil belong to chain_fwd_kernel
+    }
+    const ChainDesc &ch = ROWS ? rdesc : a.ch;
+    const int n = ch.n, L = ch.L, sp = ch.sharp;
     const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
     const size_t plane = (size_t)H * W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
@@ -196,9 +258,9 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
 
     float *Xc = dyn_smem + (1 + lane) * VEC;
     for (int i = tid; i < RINGF; i += NT) dyn_smem[i] = 0.0f;
-    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, tabs[tid]);
+    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, tabs[tid]);
 
-    const int clamped = a.clamped;
+    const int clamped = ROWS ? chain_clamped_bits(ch.op, n) : a.clamped;
     float l1 = 0.0f;
     int rA = ya - 1 + warp, sA = warp;
     // L1 prefetches one phase ahead (this kernel keeps ~5 CTAs per SM and a small ring, so the L1 has room)
@@ -220,7 +282,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
                     float m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
 #pragma unroll 1
-                    for (int k = 0; k < sp; ++k) fwd_op_grp<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+                    for (int k = 0; k < sp; ++k) fwd_op_grp<VEC, HM>(ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
                 }
             } else {
                 zero3<VEC>(x);                                              // outside the image: the stencil's zero padding
@@ -252,7 +314,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
                     }
                 }
 #pragma unroll 1
-                for (int k = sp + 1; k < n; ++k) fwd_op_grp<VEC, HM>(a.ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+                for (int k = sp + 1; k < n; ++k) fwd_op_grp<VEC, HM>(ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
                 if (tgt_b) {
                     float t[3][VEC];
                     ld_px<VEC>(tgt_b, plane, off, t);

@@ -15,46 +15,8 @@ Workspace carve_workspace(void *ws, int B, int H, int W);
 size_t max_tiles(int H, int W);
 
 static int make_step_desc(int n_ops, const int *op_ids, const int *param_off, int L, int pstride, StepDesc &d) {
-    if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids || !param_off) return T2O_ERR_INVALID_ARG;
-    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
-    if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
-    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1; d.clamped = 0;
-    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
-    for (int i = 0; i < ACC_SLOTS; ++i) d.slot_col[i] = -1;
-    bool seen[OP_COUNT] = {false};
-    for (int k = 0; k < n_ops; ++k) {
-        const int op = op_ids[k];
-        if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
-        if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
-        const int po = param_off[k];
-        if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
-        d.op[k] = op; d.poff[k] = po;
-        // the input of operator k lies in [0, 1] if the last non-identity operator before it exists (its output is clamped)
-        if (k > 0 && (d.op[k - 1] >= 0 || ((d.clamped >> (k - 1)) & 1))) d.clamped |= 1 << k;
-        if (op < 0) continue;
-        // one accumulator slot per operator type: a launch holds each type at most once (the binding splits)
-        if (seen[op]) return T2O_ERR_UNSUPPORTED;
-        seen[op] = true;
-        switch (op) {
-            case OP_SHARPNESS: d.sharp = k; d.slot_col[ACC_SHARP] = po; break;
-            case OP_BRIGHTNESS: d.slot_col[ACC_BRIGHT] = po; break;
-            case OP_CONTRAST: d.slot_col[ACC_CONTRAST] = po; break;
-            case OP_SATURATION: d.slot_col[ACC_SATUR] = po; break;
-            case OP_EXPOSURE: d.slot_col[ACC_EXPO] = po; break;
-            case OP_WHITEBALANCE: for (int c = 0; c < 3; ++c) d.slot_col[ACC_WB + c] = po + c; break;
-            case OP_TONE:
-                d.k_tone = k;
-                for (int i = 0; i < L; ++i) d.slot_col[ACC_TONE + i] = po + i;
-                break;
-            case OP_COLOR:
-                d.k_color = k;
-                for (int c = 0; c < 3; ++c)
-                    for (int i = 0; i < L; ++i) d.slot_col[ACC_COLOR + c * MAX_L + i] = po + c * L + i;
-                break;
-            default: break;     // white: no parameter gradient (models/operators.py:510-512 ignores the parameter)
-        }
-    }
-    return T2O_OK;
+    if (!param_off) return T2O_ERR_INVALID_ARG;
+    return build_step_desc(n_ops, op_ids, param_off, 0, L, pstride, d);
 }
 
 static int pick_vec(const void *const *ptrs, int nptr, size_t plane) {
@@ -126,22 +88,12 @@ void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SN
     g.nchunks = g.strips * g.bands;
 }
 
-static size_t rows_smem_bytes(const StepDesc &d, int vec, bool has_mask, int SNT) {
+static size_t rows_smem_bytes(int n, int sharp, int vec, bool has_mask, int SNT) {
     const int RING = SNT / 32 + 2;
     const size_t ringf = (size_t)RING * 3 * 34 * vec;
-    const size_t ntp = d.sharp > 1 ? d.sharp - 1 : 0;
-    const size_t ntq = d.n - d.sharp - 1;
+    const size_t ntp = sharp > 1 ? sharp - 1 : 0;
+    const size_t ntq = n - sharp - 1;
     return ((has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
-}
-
-// threads per CTA of the step kernels: 256 (default) or 192 (more registers per thread); T2O_STEP_THREADS overrides
-static int step_threads() {
-    static int nth = 0;
-    if (nth == 0) {
-        const char *e = getenv("T2O_STEP_THREADS");
-        nth = (e && atoi(e) == 192) ? 192 : 256;
-    }
-    return nth;
 }
 
 template <int VEC, bool HM, int NTH>
@@ -151,29 +103,57 @@ static int launch_step(StepArgs &a, cudaStream_t stream) {
     size_t smem;
     if (!rows) {
         smem = (size_t)a.ch.n * 3 * NTH * VEC * sizeof(float);
-        int st = step_set_smem(step_flat_kernel<VEC, HM, NTH>, smem);
+        int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, false>, smem);
         if (st) return st;
-        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH>, NTH, smem), NTH);
+        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, false>, NTH, smem), NTH);
         dim3 grid(a.g.nchunks, B);
-        step_flat_kernel<VEC, HM, NTH><<<grid, NTH, smem, stream>>>(a);
+        step_flat_kernel<VEC, HM, NTH, false><<<grid, NTH, smem, stream>>>(a);
     } else {
-        smem = rows_smem_bytes(a.ch, VEC, HM, NTH);
-        int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH>, smem);
+        smem = rows_smem_bytes(a.ch.n, a.ch.sharp, VEC, HM, NTH);
+        int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, false>, smem);
         if (st) return st;
-        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH>, NTH, smem), NTH, 4);
+        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, false>, NTH, smem), NTH, 4);
         dim3 grid(a.g.nchunks, B);
-        step_sharp_kernel<VEC, HM, NTH><<<grid, NTH, smem, stream>>>(a);
+        step_sharp_kernel<VEC, HM, NTH, false><<<grid, NTH, smem, stream>>>(a);
     }
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
 }
 
+// Per-row chains: one launch of each tiling; a CTA whose row belongs to the other tiling exits at once.
+// `paths` bit 0: some row has no stencil, bit 1: some row has one (3 when the host does not know the rows).
+template <int VEC, bool HM, int NTH>
+static int launch_step_rows(StepArgs &a, int paths, cudaStream_t stream) {
+    const int B = a.g.B, H = a.g.H, W = a.g.W, K = a.rows_K;
+    if (paths & 1) {
+        const size_t smem = (size_t)K * 3 * NTH * VEC * sizeof(float);
+        int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, true>, smem);
+        if (st) return st;
+        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, true>, NTH, smem), NTH);
+        dim3 grid(a.g.nchunks, B);
+        step_flat_kernel<VEC, HM, NTH, true><<<grid, NTH, smem, stream>>>(a);
+        T2O_CUDA_OK(cudaGetLastError());
+    }
+    if (paths & 2) {
+        // shared memory for the worst row: the stencil last (K - 1 operators on the ring tape) or first (K - 1 per-thread tapes)
+        const size_t s_last = rows_smem_bytes(K, K - 1, VEC, HM, NTH), s_first = rows_smem_bytes(K, 0, VEC, HM, NTH);
+        const size_t smem = s_last > s_first ? s_last : s_first;
+        int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, true>, smem);
+        if (st) return st;
+        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, true>, NTH, smem), NTH, 4);
+        dim3 grid(a.g.nchunks, B);
+        step_sharp_kernel<VEC, HM, NTH, true><<<grid, NTH, smem, stream>>>(a);
+        T2O_CUDA_OK(cudaGetLastError());
+    }
+    return T2O_OK;
+}
+
 template <bool HM>
-static int launch_step_vec(int vec, StepArgs &a, cudaStream_t stream) {
-    if (step_threads() == 192) {
-        if (vec == 4) return launch_step<4, HM, 192>(a, stream);
-        if (vec == 2) return launch_step<2, HM, 192>(a, stream);
-        return launch_step<1, HM, 192>(a, stream);
+static int launch_step_vec(int vec, StepArgs &a, int rows_paths, cudaStream_t stream) {
+    if (rows_paths) {
+        if (vec == 4) return launch_step_rows<4, HM, 256>(a, rows_paths, stream);
+        if (vec == 2) return launch_step_rows<2, HM, 256>(a, rows_paths, stream);
+        return launch_step_rows<1, HM, 256>(a, rows_paths, stream);
     }
     if (vec == 4) return launch_step<4, HM, 256>(a, stream);
     if (vec == 2) return launch_step<2, HM, 256>(a, stream);
@@ -205,7 +185,41 @@ int chain_backward(int n_ops, const int *op_ids, const int *param_off, const flo
     int vec = pick_vec(ptrs, 6, plane);
     if (a.ch.sharp >= 0)
         while (vec > 1 && W % vec != 0) vec >>= 1;
-    return mask ? launch_step_vec<true>(vec, a, stream) : launch_step_vec<false>(vec, a, stream);
+    return mask ? launch_step_vec<true>(vec, a, 0, stream) : launch_step_vec<false>(vec, a, 0, stream);
+}
+
+int rows_paths(int K, const int *row_ops_host, int B, int slot, int L, int pstride, bool backward, int &paths);
+
+// Per-row chains, backward (+ optional fused forward outputs): autograd through the Actor's per-row operator step.
+int rows_backward(int K, const int *row_ops, const int *row_ops_host, int slot, const float *img, const float *mask, int mask_ch,
+                  const float *params, int pstride, const float *grad_out, const float *target, const float *grad_l1,
+                  float *grad_params, float *grad_img, float *out, float *l1_sum, unsigned int *status,
+                  int B, int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!row_ops || !img || !params || B < 1 || H < 1 || W < 1) return T2O_ERR_INVALID_ARG;
+    if (mask && mask_ch != 1 && mask_ch != 3) return T2O_ERR_INVALID_ARG;
+    if (!grad_out && (!target || !grad_l1)) return T2O_ERR_INVALID_ARG;
+    if (l1_sum && !target) return T2O_ERR_INVALID_ARG;
+    if (!grad_params && !grad_img) return T2O_ERR_INVALID_ARG;
+    if (!ws || ws_bytes < chain_workspace_bytes(B, H, W, pstride)) return T2O_ERR_WORKSPACE;
+    if (B > 65535) return T2O_ERR_UNSUPPORTED;
+    int paths = 0;
+    int st = rows_paths(K, row_ops_host, B, slot, L, pstride, true, paths);
+    if (st != T2O_OK) return st;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ch.n = K; a.ch.L = L; a.ch.sharp = -1;
+    Workspace w = carve_workspace(ws, B, H, W);
+    a.img = img; a.mask = mask; a.params = params; a.grad_out = grad_out; a.target = target; a.grad_l1 = grad_l1;
+    a.grad_params = grad_params; a.grad_img = grad_img; a.out = out; a.l1_sum = l1_sum;
+    a.part_l1 = w.part_l1; a.part_gp = w.part_gp; a.counters = w.counters; a.mask_ch = mask_ch; a.pstride = pstride;
+    a.row_ops = row_ops; a.rows_K = K; a.rows_slot = slot; a.status = status;
+    a.g.B = B; a.g.H = H; a.g.W = W;
+    const size_t plane = (size_t)H * W;
+    const void *ptrs[] = {img, mask, target, out, grad_out, grad_img};
+    int vec = pick_vec(ptrs, 6, plane);
+    if (paths & 2)
+        while (vec > 1 && W % vec != 0) vec >>= 1;
+    return mask ? launch_step_vec<true>(vec, a, paths, stream) : launch_step_vec<false>(vec, a, paths, stream);
 }
 
 }  // namespace t2o

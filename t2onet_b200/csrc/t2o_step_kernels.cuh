@@ -62,7 +62,57 @@ struct StepArgs {
     float *part_l1, *part_gp;
     unsigned int *counters;
     int mask_ch, pstride;
+    // per-row chains (ROWS kernels): operator ids (B, rows_K) in device memory, operator k of a row reads its
+    // parameters at column k * rows_slot; *status gets bit 0 set if a row holds an invalid chain
+    const int *row_ops;
+    int rows_K, rows_slot;
+    unsigned int *status;
 };
+
+// Launch descriptor of one chain; runs on the host for uniform chains (t2o_step.cu) and on the device, once per
+// CTA, for per-row chains.  param_off == nullptr: operator k reads its parameters at column k * slot.
+T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, int slot, int L, int pstride, StepDesc &d) {
+    if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids) return T2O_ERR_INVALID_ARG;
+    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
+    if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
+    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1; d.clamped = 0;
+    for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
+    for (int i = 0; i < ACC_SLOTS; ++i) d.slot_col[i] = -1;
+    unsigned seen = 0u;
+    for (int k = 0; k < n_ops; ++k) {
+        const int op = op_ids[k];
+        if (op == OP_INPAINT) return T2O_ERR_UNSUPPORTED;
+        if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
+        const int po = param_off ? param_off[k] : k * slot;
+        if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
+        d.op[k] = op; d.poff[k] = po;
+        // the input of operator k lies in [0, 1] if the last non-identity operator before it exists (its output is clamped)
+        if (k > 0 && (d.op[k - 1] >= 0 || ((d.clamped >> (k - 1)) & 1))) d.clamped |= 1 << k;
+        if (op < 0) continue;
+        // one accumulator slot per operator type: a launch holds each type at most once (the binding splits)
+        if ((seen >> op) & 1u) return T2O_ERR_UNSUPPORTED;
+        seen |= 1u << op;
+        switch (op) {
+            case OP_SHARPNESS: d.sharp = k; d.slot_col[ACC_SHARP] = po; break;
+            case OP_BRIGHTNESS: d.slot_col[ACC_BRIGHT] = po; break;
+            case OP_CONTRAST: d.slot_col[ACC_CONTRAST] = po; break;
+            case OP_SATURATION: d.slot_col[ACC_SATUR] = po; break;
+            case OP_EXPOSURE: d.slot_col[ACC_EXPO] = po; break;
+            case OP_WHITEBALANCE: for (int c = 0; c < 3; ++c) d.slot_col[ACC_WB + c] = po + c; break;
+            case OP_TONE:
+                d.k_tone = k;
+                for (int i = 0; i < L; ++i) d.slot_col[ACC_TONE + i] = po + i;
+                break;
+            case OP_COLOR:
+                d.k_color = k;
+                for (int c = 0; c < 3; ++c)
+                    for (int i = 0; i < L; ++i) d.slot_col[ACC_COLOR + c * MAX_L + i] = po + c * L + i;
+                break;
+            default: break;     // white: no parameter gradient (models/operators.py:510-512 ignores the parameter)
+        }
+    }
+    return T2O_OK;
+}
 
 // ---------------------------------------------------------------- operator dispatch over one pixel group
 // `cl`: the operator's input is known to lie in [0, 1] (lets the curve operators skip their input clamp)
@@ -215,11 +265,27 @@ struct StepShared {
     float rowbuf[MAX_PSTRIDE];
     float red[32];
     int last_flag;
+    StepDesc rdesc;               // per-row chains: this row's descriptor (ROWS kernels)
 };
+
+// Per-row chains: thread 0 builds the row's descriptor; an invalid row becomes an identity chain and flags *status.
+// Ends with a barrier; every thread then reads sh.rdesc.
+__device__ __forceinline__ void rows_build_desc(const StepArgs &a, StepShared &sh, int b) {
+    if (threadIdx.x == 0) {
+        int ops[MAX_CHAIN];
+        for (int k = 0; k < MAX_CHAIN; ++k) ops[k] = k < a.rows_K ? a.row_ops[(size_t)b * a.rows_K + k] : OP_IDENTITY;
+        if (build_step_desc(a.rows_K, ops, nullptr, a.rows_slot, a.ch.L, a.pstride, sh.rdesc) != T2O_OK) {
+            for (int k = 0; k < MAX_CHAIN; ++k) ops[k] = OP_IDENTITY;
+            build_step_desc(a.rows_K, ops, nullptr, 0, a.ch.L, a.pstride, sh.rdesc);
+            if (a.status) atomicOr(a.status, 1u);
+        }
+    }
+    __syncthreads();
+}
 
 // CTA partials of the parameter gradients and the L1, then "the last CTA of the image finishes"
 template <int NTH>
-__device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh, GradAcc &A, float l1, int b, int chunk) {
+__device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepDesc &ch, StepShared &sh, GradAcc &A, float l1, int b, int chunk) {
     constexpr int SNT = NTH, SNW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunks = a.g.nchunks;
@@ -240,14 +306,14 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh,
         }
         __syncthreads();
         if (tid < ACC_SLOTS) {
-            const int col = a.ch.slot_col[tid];
+            const int col = ch.slot_col[tid];
             if (col >= 0) {
                 float val = sh.tot[tid];
                 if (tid < ACC_COLOR + 3 * MAX_L) {
                     const int c = tid / MAX_L;
-                    val = curve_param_grad(sh.tabs[a.ch.k_color] + c * CT, a.ch.L, sh.tot + ACC_COLOR + c * MAX_L, tid - c * MAX_L);
+                    val = curve_param_grad(sh.tabs[ch.k_color] + c * CT, ch.L, sh.tot + ACC_COLOR + c * MAX_L, tid - c * MAX_L);
                 } else if (tid >= ACC_TONE && tid < ACC_TONE + MAX_L) {
-                    val = curve_param_grad(sh.tabs[a.ch.k_tone], a.ch.L, sh.tot + ACC_TONE, tid - ACC_TONE);
+                    val = curve_param_grad(sh.tabs[ch.k_tone], ch.L, sh.tot + ACC_TONE, tid - ACC_TONE);
                 }
                 sh.rowbuf[col] = val;
             }
@@ -276,7 +342,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, StepShared &sh,
 }
 
 // =========================================================================================== flat (no stencil)
-template <int VEC, bool HM, int NTH>
+template <int VEC, bool HM, int NTH, bool ROWS>
 __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant__ StepArgs a) {
     using V = typename VecT<VEC>::type;
     constexpr int SNT = NTH;
@@ -285,7 +351,12 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int n = a.ch.n, L = a.ch.L;
+    if constexpr (ROWS) {
+        rows_build_desc(a, sh, b);
+        if (sh.rdesc.sharp >= 0) return;                    // rows with a stencil belong to step_sharp_kernel
+    }
+    const StepDesc &ch = ROWS ? sh.rdesc : a.ch;
+    const int n = ch.n, L = ch.L;
     const size_t plane = (size_t)a.g.H * a.g.W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
     const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
@@ -295,7 +366,7 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
 
-    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, sh.tabs[tid]);
+    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
     __syncthreads();
 
     V *tape = reinterpret_cast<V *>(dyn_smem) + tid;       // input of operator k, plane c: tape[(k*3 + c) * SNT]
@@ -316,25 +387,25 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
             tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
-            fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (a.ch.clamped >> k) & 1);
+            fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (ch.clamped >> k) & 1);
         }
         upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
         if (out_b) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll 1
         for (int k = n - 1; k >= 0; --k) {
             tape_ld<VEC>(tape + k * 3 * SNT, SNT, x);
-            bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true, (a.ch.clamped >> k) & 1);
+            bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, true, (ch.clamped >> k) & 1);
         }
         if (gi_b) st_px<VEC>(gi_b, plane, off, g);
     }
-    step_epilogue<NTH>(a, sh, A, l1, b, chunk);
+    step_epilogue<NTH>(a, ch, sh, A, l1, b, chunk);
 }
 
 // =========================================================================================== row pipeline (one stencil)
 // Shared-memory layout (compile-time strides): a ring row holds 3 planes of 34 groups (one zero pad group each
 // side of the 32 lanes); the tape of the operators before the stencil holds, per operator 1 .. sp-1, RING rows of
 // 3 x 32 vectors; the operators after the stencil keep a per-thread tape.
-template <int VEC, bool HM, int NTH>
+template <int VEC, bool HM, int NTH, bool ROWS>
 __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
     using V = typename VecT<VEC>::type;
     constexpr int SNT = NTH, SNW = NTH / 32, RING = SNW + 2;
@@ -348,7 +419,12 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int strip = chunk % a.g.strips, band = chunk / a.g.strips;
-    const int n = a.ch.n, L = a.ch.L, sp = a.ch.sharp;
+    if constexpr (ROWS) {
+        rows_build_desc(a, sh, b);
+        if (sh.rdesc.sharp < 0) return;                     // rows without a stencil belong to step_flat_kernel
+    }
+    const StepDesc &ch = ROWS ? sh.rdesc : a.ch;
+    const int n = ch.n, L = ch.L, sp = ch.sharp;
     const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
     const size_t plane = (size_t)H * W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
@@ -376,12 +452,12 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     const int ntp = sp > 1 ? sp - 1 : 0;
     V *tapeQ = reinterpret_cast<V *>(dyn_smem + NRING * RINGF) + ntp * RING * TSLOT + tid;   // [(k-sp-1)][c][SNT]
     for (int i = tid; i < NRING * RINGF; i += SNT) dyn_smem[i] = 0.0f;
-    if (tid < n) build_table(a.ch.op[tid], a.params + (size_t)b * a.pstride + a.ch.poff[tid], L, sh.tabs[tid]);
+    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
     const bool need_c = gi_b != nullptr || sp > 0;
-    const int clamped = a.ch.clamped;
+    const int clamped = ch.clamped;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
@@ -400,11 +476,11 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                 ld_px<VEC>(img_b, plane, off, x);
                 if (sp > 0) {
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-                    fwd_op_grp<VEC, HM>(a.ch.op[0], sh.tabs[0], L, x, m, false);
+                    fwd_op_grp<VEC, HM>(ch.op[0], sh.tabs[0], L, x, m, false);
 #pragma unroll 1
                     for (int k = 1; k < sp; ++k) {
                         if (interior) tape_st<VEC>(tapeP + ((k - 1) * RING + sA) * TSLOT, 32, x);
-                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
+                        fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
                     }
                 }
             } else {                                               // outside the image: the stencil's zero padding
@@ -440,14 +516,14 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll 1
                     for (int k = sp + 1; k < n; ++k) {
                         tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        fwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
+                        fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
                     }
                     upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
                     if (out_b && own) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll 1
                     for (int k = n - 1; k > sp; --k) {
                         tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
+                        bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
                     }
                     float accp = 0.0f;
 #pragma unroll
@@ -499,10 +575,10 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll 1
                     for (int k = sp - 1; k >= 1; --k) {
                         tape_ld<VEC>(tapeP + ((k - 1) * RING + sC) * TSLOT, 32, x);
-                        bwd_op_grp<VEC, HM>(a.ch.op[k], sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
+                        bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
                     }
                     ld_px<VEC>(img_b, plane, off, x);
-                    bwd_op_grp<VEC, HM>(a.ch.op[0], sh.tabs[0], L, x, m, g, A, true, false);
+                    bwd_op_grp<VEC, HM>(ch.op[0], sh.tabs[0], L, x, m, g, A, true, false);
                 }
                 if (gi_b) st_px<VEC>(gi_b, plane, off, g);
             }
@@ -512,7 +588,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
         sA += SNW;
         if (sA >= RING) sA -= RING;
     }
-    step_epilogue<NTH>(a, sh, A, l1, b, chunk);
+    step_epilogue<NTH>(a, ch, sh, A, l1, b, chunk);
 }
 
 // Opt in to the dynamic shared memory a launch needs.

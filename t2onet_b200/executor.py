@@ -48,6 +48,54 @@ class Executor(nn.Module):
         (what the planner replays and what BASELINE configs 1/4 measure)."""
         return TF.chain(img, list(op_inds), list(params), mask, getattr(self.opt, 'curve_steps', 8))
 
+    def _row_param(self, Op, features, specified_param, has_noise, n_rows, device):
+        """What Operator.execute does to obtain its parameters (models/operators.py:114-125), zero-padded to 24 columns
+        like the Actor pads them (models/actor.py:166)."""
+        param = Op.extract_parameters(features) if features is not None else specified_param[:, :Op.num_op_param]
+        if has_noise:
+            param = torch.clamp(param + Op.get_param_noise(n_rows).to(device), Op.lb, Op.ub)
+        param = param.float().to(device)
+        return torch.nn.functional.pad(param, (0, TF.PARAM_SLOT - param.shape[1]))
+
+    def execute_rows(self, img, op_inds, mask, features=None, specified_param=None, has_noise=False):
+        """Extension: ONE operator step for a batch whose rows use DIFFERENT operators
+        -- the Actor's divide_op_group loop (models/actor.py:100-114, 156-170, 245-259) as a single call:
+            out, param = executor.execute_rows(img_x, pred_op.view(-1) - 3, mask, context)
+        :param op_inds: (bs,) Executor index per row (-1 = <END>: the row passes through, its param row is zeros,
+                        executors/executor.py:44-46).  A list / CPU tensor groups the rows per operator for the FC
+                        heads exactly like the reference; a CUDA tensor keeps the whole step free of host syncs
+                        (every operator head runs on the full batch and the rows select theirs).
+        :param features: (bs, 2*hidden) or None   :param specified_param: (bs, >= n) zero-padded rows or None
+        :return out (bs, 3, h, w), param (bs, 24) zero-padded -- both differentiable."""
+        assert (features is None) ^ (specified_param is None)
+        bs, dev = img.shape[0], img.device
+        on_device = isinstance(op_inds, torch.Tensor) and op_inds.is_cuda
+        ops_t = op_inds.view(-1) if isinstance(op_inds, torch.Tensor) else torch.as_tensor(op_inds).view(-1)
+        assert ops_t.numel() == bs
+        if on_device:
+            params = torch.zeros(bs, TF.PARAM_SLOT, device=dev)
+            for ind, Op in enumerate(self.ops):
+                if isinstance(Op, InpaintOperator):
+                    continue
+                p = self._row_param(Op, features, specified_param, has_noise, bs, dev)
+                params = torch.where((ops_t == ind).view(bs, 1), p, params)
+        else:
+            ops_l = [int(v) for v in ops_t.tolist()]
+            params = torch.zeros(bs, TF.PARAM_SLOT, device=dev)
+            for ind in sorted(set(ops_l)):
+                if ind < 0:
+                    continue
+                Op = self.ops[ind]
+                if isinstance(Op, InpaintOperator):
+                    raise NotImplementedError('InpaintOperator (EdgeConnect) is outside the B200 hot path')
+                rows = torch.tensor([b for b, v in enumerate(ops_l) if v == ind], device=dev)
+                f_g = None if features is None else features.index_select(0, rows)
+                s_g = None if specified_param is None else specified_param.to(dev).index_select(0, rows)
+                params = params.index_copy(0, rows, self._row_param(Op, f_g, s_g, has_noise, rows.numel(), dev))
+            ops_t = ops_l
+        out = TF.execute_rows(img, ops_t, params, mask, getattr(self.opt, 'curve_steps', 8))
+        return out, params
+
     def get_param_bnd(self, op_ind):
         return self.ops[op_ind].get_param_range()
 

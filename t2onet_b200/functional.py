@@ -284,6 +284,123 @@ class FusedStep:
         return out, l1, gp, gi
 
 
+# ------------------------------------------------------------------------------------------ per-row chains
+PARAM_SLOT = _lib.MAX_OP_PARAMS      # the Actor's zero-padded parameter rows (models/actor.py:166)
+
+
+def _prep_row_ops(row_ops, B, device):
+    """-> (device int32 (B, K) tensor, ctypes host copy or None).  A list / CPU tensor is known on the host (validated
+    up front, any K); a CUDA tensor stays on the device (K == 1, no host sync)."""
+    if isinstance(row_ops, torch.Tensor) and row_ops.is_cuda:
+        t = row_ops.reshape(B, -1).to(torch.int32).contiguous()
+        return t, None
+    t = torch.as_tensor(row_ops, dtype=torch.int32).reshape(B, -1).contiguous()
+    host = _lib.int_array(t.flatten().tolist())
+    return t.to(device, non_blocking=True), host
+
+
+def _rows_forward_raw(ops_dev, ops_host, img, mask, mask_ch, params, target, want_out, want_l1, curve_steps):
+    B, _, H, W = img.shape
+    K, pstride = ops_dev.shape[1], params.shape[1]
+    lib = _lib.lib()
+    out = torch.empty_like(img) if want_out else None
+    l1 = torch.empty(B, device=img.device, dtype=torch.float32) if want_l1 else None
+    ws = _lib.workspace(img.device, lib.t2o_workspace_bytes(B, H, W, pstride))
+    st = lib.t2o_rows_forward(K, _lib.ptr(ops_dev), ops_host, PARAM_SLOT, _lib.ptr(img), _lib.ptr(mask), mask_ch,
+                              _lib.ptr(params), pstride, _lib.ptr(target), _lib.ptr(out), _lib.ptr(l1),
+                              _lib.ptr(_lib.status_word(img.device)), B, H, W, curve_steps,
+                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(img.device))
+    _lib.check(st)
+    return out, l1
+
+
+def _rows_backward_raw(ops_dev, ops_host, img, mask, mask_ch, params, grad_out, target, grad_l1, want_gimg, want_out,
+                       want_l1, curve_steps):
+    B, _, H, W = img.shape
+    K, pstride = ops_dev.shape[1], params.shape[1]
+    lib = _lib.lib()
+    gp = torch.empty(B, pstride, device=img.device, dtype=torch.float32)
+    gi = torch.empty_like(img) if want_gimg else None
+    out = torch.empty_like(img) if want_out else None
+    l1 = torch.empty(B, device=img.device, dtype=torch.float32) if want_l1 else None
+    ws = _lib.workspace(img.device, lib.t2o_workspace_bytes(B, H, W, pstride))
+    st = lib.t2o_rows_backward(K, _lib.ptr(ops_dev), ops_host, PARAM_SLOT, _lib.ptr(img), _lib.ptr(mask), mask_ch,
+                               _lib.ptr(params), pstride, _lib.ptr(grad_out), _lib.ptr(target), _lib.ptr(grad_l1),
+                               _lib.ptr(gp), _lib.ptr(gi), _lib.ptr(out), _lib.ptr(l1),
+                               _lib.ptr(_lib.status_word(img.device)), B, H, W, curve_steps,
+                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr(img.device))
+    _lib.check(st)
+    return gp, gi, out, l1
+
+
+class _RowsFn(torch.autograd.Function):
+    """out[b] = chain_b(img[b]; params[b]) with a per-row operator chain.  Backward recomputes in-kernel."""
+
+    @staticmethod
+    def forward(ctx, img, params, mask, ops_dev, ops_host, curve_steps):
+        mask_c, mask_ch = _prep_mask(mask, img)
+        out, _ = _rows_forward_raw(ops_dev, ops_host, img, mask_c, mask_ch, params, None, True, False, curve_steps)
+        ctx.save_for_backward(img, params, ops_dev, mask_c if mask_c is not None else torch.empty(0, device=img.device))
+        ctx.meta = (ops_host, mask_ch, curve_steps)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, params, ops_dev, mask_c = ctx.saved_tensors
+        ops_host, mask_ch, curve_steps = ctx.meta
+        mask_c = mask_c if mask_ch else None
+        gp, gi, _, _ = _rows_backward_raw(ops_dev, ops_host, img, mask_c, mask_ch, params, grad_out.contiguous(), None, None,
+                                          ctx.needs_input_grad[0], False, False, curve_steps)
+        return gi, (gp if ctx.needs_input_grad[1] else None), None, None, None, None
+
+
+def _prep_row_params(params, B, K):
+    _lib.require_cuda(params)
+    if params.dim() != 2 or params.shape[0] != B or params.shape[1] != K * PARAM_SLOT:
+        raise _lib.T2OError('per-row parameters must be (B=%d, K*%d=%d), got %s' % (B, PARAM_SLOT, K * PARAM_SLOT, tuple(params.shape)))
+    return params.contiguous()
+
+
+def execute_rows(img, row_ops, params, mask=None, curve_steps=CURVE_STEPS):
+    """Every batch row applies its OWN operator chain: row b runs operators row_ops[b, 0..K) (Executor indices,
+    -1 = <END> = pass through) with parameters params[b, k*24 : k*24 + n] (zero-padded 24-float slots, the Actor's
+    layout).  One launch per tiling over the original tensors -- replaces divide_op_group + index_select + per-group
+    Executor.execute + cat + index_select (models/actor.py:100-114, 156-170, 245-259).  Differentiable w.r.t. img
+    and params.  row_ops: (B,) / (B, K) list, CPU tensor (validated on the host) or CUDA tensor (K == 1, sync-free)."""
+    img = _prep_img(img, 'img')
+    B = img.shape[0]
+    ops_dev, ops_host = _prep_row_ops(row_ops, B, img.device)
+    params = _prep_row_params(params, B, ops_dev.shape[1])
+    return _RowsFn.apply(img, params, mask, ops_dev, ops_host, curve_steps)
+
+
+def rows_forward_backward(img, row_ops, params, target, mask=None, want_out=True, want_grad_img=False, loss_scale=None,
+                          curve_steps=CURVE_STEPS):
+    """The fused training-style step of chain_forward_backward for per-row chains: edited image, per-image L1 sums and
+    the gradients of  sum_b loss_scale[b] * l1_sum[b]  (default: the mean L1) in one launch per tiling.
+    Returns (out, l1_sum, grad_params (B, K*24), grad_img)."""
+    img, target = _prep_img(img, 'img'), _prep_img(target, 'target')
+    B = img.shape[0]
+    ops_dev, ops_host = _prep_row_ops(row_ops, B, img.device)
+    params = _prep_row_params(params, B, ops_dev.shape[1])
+    mask_c, mask_ch = _prep_mask(mask, img)
+    if loss_scale is None:
+        loss_scale = torch.full((B,), 1.0 / img.numel(), device=img.device, dtype=torch.float32)
+    gp, gi, out, l1 = _rows_backward_raw(ops_dev, ops_host, img, mask_c, mask_ch, params, None, target,
+                                         loss_scale.contiguous().float(), want_grad_img, want_out, True, curve_steps)
+    return out, l1, gp, gi
+
+
+def rows_status(device, clear=True):
+    """Bit 0 set: a per-row kernel met an invalid operator id since the last clear (it treated the row as identity).
+    Reading synchronises; only device-resident row_ops (no host copy) can trip it."""
+    w = _lib.status_word(torch.device(device))
+    v = int(w.item())
+    if clear and v:
+        w.zero_()
+    return v
+
+
 def process_raw(img, op_id, param, curve_steps=CURVE_STEPS):
     """Operator.process(img, param) itself (no mask blend, no clamp): models/operators.py:128."""
     img = _prep_img(img, 'img')

@@ -23,7 +23,7 @@ def test_library_exports_every_symbol_declared_in_the_header():
     lib = _lib.lib()                               # builds if stale; loads without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.t2o_version() == 100
+    assert lib.t2o_version() == 101
     assert lib.t2o_status_string(2) == b'unsupported configuration'
     assert [lib.t2o_num_params(op, 8) for op in (-1, 0, 1, 2, 3, 5, 6, 7, 8, 9)] == [0, 1, 1, 1, 24, 8, 1, 1, 1, 3]
     assert lib.t2o_num_params(42, 8) == -1
@@ -56,6 +56,19 @@ def test_argument_validation_without_a_gpu():
     bwd = lib.t2o_chain_backward(1, ops, offs, fake, None, 0, fake, 1, fake, None, None, fake, None, None, None,
                                  1, 8, 8, 8, None, 0, None)
     assert bwd == 3                                          # workspace missing
+    # per-row chains: host-known rows are validated before any launch
+    def rows_fwd(ops, K, pstride=48, slot=24, host=True, B=2):
+        return lib.t2o_rows_forward(K, fake, _lib.int_array(ops) if host else None, slot, fake, None, 0, fake, pstride, None,
+                                    fake, None, None, B, 8, 8, 8, None, 0, None)
+    assert rows_fwd([0, 4, 1, 2], 2) == 2                    # inpaint in a row
+    assert rows_fwd([0, 1, 6, 6], 2) == 2                    # two stencils in one row
+    assert rows_fwd([0, 42, 1, 2], 2) == 1
+    assert rows_fwd([0, 1, 1, 2], 2, pstride=24) == 1        # parameter table narrower than K slots
+    assert rows_fwd([0, 1, 1, 2], 2, slot=8, pstride=16) == 2   # slot too small for the color curve
+    assert rows_fwd([0, 1, 1, 2], 2, host=False) == 1        # device-only ids need K == 1
+    rows_bwd = lib.t2o_rows_backward(2, fake, _lib.int_array([0, 0, 1, 2]), 24, fake, None, 0, fake, 48, fake, None, None,
+                                     fake, None, None, None, None, 2, 8, 8, 8, fake, 1 << 30, None)
+    assert rows_bwd == 2                                     # an operator type twice in one row of a backward call
 
 
 def test_cpu_tensors_are_rejected_loudly():
