@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Attribute executed instructions of an .ncu-rep kernel to source lines (via nvdisasm -g on the built library).
-Usage: python scripts/ncu_lines.py <report.ncu-rep> <mangled kernel name substring> [pixels] [top]"""
+"""Attribute executed instructions (and warp-stall samples) of an .ncu-rep kernel to source lines (via nvdisasm -g on
+the built library).  Usage: python scripts/ncu_lines.py <report.ncu-rep> <mangled kernel name substring> [pixels] [top] [stall]
+With a 5th argument the lines are ranked by not-issued stall samples and the dominant stall reasons are shown."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, kname = sys.argv[1], sys.argv[2]
 px = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+by_stall = len(sys.argv) > 5
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.join(ROOT, 't2onet_b200/lib/libt2o_b200.so')], cwd=tmp, capture_output=True)
@@ -35,12 +37,19 @@ ix, ia, isrc = h.index('Instructions Executed'), h.index('Address'), h.index('So
 base = int(rows[2][ia], 16)
 by, tot = collections.Counter(), 0
 byop = collections.defaultdict(collections.Counter)
+ins = h.index('Warp Stall Sampling (Not-issued Samples)')
+stall_cols = [(i, c[len('stall_'):-len(' (Not Issued)')]) for i, c in enumerate(h) if c.startswith('stall_') and c.endswith('(Not Issued)')]
+st_by, st_tot = collections.Counter(), 0
+st_reason = collections.defaultdict(collections.Counter)
 for r in rows[2:]:
     if len(r) <= ix:
         continue
     n = int(r[ix]); off = int(r[ia], 16) - base
     loc = line_of.get(off)
     by[loc] += n; tot += n
+    st_by[loc] += int(r[ins]); st_tot += int(r[ins])
+    for i, name in stall_cols:
+        if int(r[i]): st_reason[loc][name] += int(r[i])
     mm = re.match(r'\s*(@!?U?P\w+\s+)?([A-Z0-9_]+)', r[isrc])
     byop[loc][mm.group(2) if mm else '?'] += n
 srccache = {}
@@ -60,3 +69,13 @@ for f, n in byfile.most_common(): print('  %-28s %7.1f /px' % (f, n*32/px))
 for loc, n in by.most_common(top):
     ops = ' '.join('%s:%.0f' % (o, c*32/px) for o, c in byop[loc].most_common(4))
     print('%6.1f  %-24s %-90s | %s' % (n*32/px, '%s:%d' % loc if loc else '?', text(loc), ops))
+
+if by_stall:
+    print('---- lines by not-issued stall samples (total %d)' % st_tot)
+    allr = collections.Counter()
+    for loc in st_reason:
+        allr.update(st_reason[loc])
+    print('   reasons: ' + ' '.join('%s:%.1f%%' % (k, 100 * v / st_tot) for k, v in allr.most_common(10)))
+    for loc, n in st_by.most_common(top):
+        rs = ' '.join('%s:%.0f%%' % (k, 100 * v / max(n, 1)) for k, v in st_reason[loc].most_common(3))
+        print('%5.1f%%  %6.1f i/px  %-24s %-80s | %s' % (100 * n / st_tot, by[loc] * 32 / px, '%s:%d' % loc if loc else '?', text(loc)[:80], rs))

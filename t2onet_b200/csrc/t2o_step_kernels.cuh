@@ -36,6 +36,7 @@ struct StepDesc {
     int n, L, sharp;              // operators, curve steps, index of the sharpness operator or -1
     int k_tone, k_color;          // chain position of the tone / color operator or -1 (their 1/S lives in the tables)
     int clamped;                  // bit k: the input of operator k is the clamped output of another operator (in [0, 1])
+    unsigned int ops_packed;      // 4 bits per operator: op[k] + 1 (register-resident copy of op[] for the dispatch loops)
     int op[MAX_CHAIN];
     int poff[MAX_CHAIN];
     int slot_col[ACC_SLOTS];      // parameter column fed by each accumulator slot, or -1
@@ -75,7 +76,7 @@ T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, i
     if (n_ops < 1 || n_ops > MAX_CHAIN || !op_ids) return T2O_ERR_INVALID_ARG;
     if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
     if (pstride < 0 || pstride > MAX_PSTRIDE) return T2O_ERR_UNSUPPORTED;
-    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1; d.clamped = 0;
+    d.n = n_ops; d.L = L; d.sharp = -1; d.k_tone = -1; d.k_color = -1; d.clamped = 0; d.ops_packed = 0u;
     for (int k = 0; k < MAX_CHAIN; ++k) { d.op[k] = OP_IDENTITY; d.poff[k] = 0; }
     for (int i = 0; i < ACC_SLOTS; ++i) d.slot_col[i] = -1;
     unsigned seen = 0u;
@@ -86,6 +87,7 @@ T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, i
         const int po = param_off ? param_off[k] : k * slot;
         if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
         d.op[k] = op; d.poff[k] = po;
+        d.ops_packed |= (unsigned)(op + 1) << (4 * k);
         // the input of operator k lies in [0, 1] if the last non-identity operator before it exists (its output is clamped)
         if (k > 0 && (d.op[k - 1] >= 0 || ((d.clamped >> (k - 1)) & 1))) d.clamped |= 1 << k;
         if (op < 0) continue;
@@ -113,6 +115,10 @@ T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, i
     }
     return T2O_OK;
 }
+
+// operator id of chain position k from the packed register copy (two ALU instructions; a c[][] / shared-memory
+// load indexed by k would put its latency in front of every dispatch branch)
+__device__ __forceinline__ int packed_op(unsigned int ops_packed, int k) { return (int)((ops_packed >> (4 * k)) & 15u) - 1; }
 
 // ---------------------------------------------------------------- operator dispatch over one pixel group
 // `cl`: the operator's input is known to lie in [0, 1] (lets the curve operators skip their input clamp)
@@ -214,7 +220,8 @@ __device__ __forceinline__ void upstream_grad(const float *go_b, const float *tg
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const float d = x[c][v] - t[c][v];
-                g[c][v] = d != 0.0f ? copysignf(gl1, gl1 < 0.0f ? -d : d) : 0.0f;
+                const float sg = __uint_as_float(__float_as_uint(gl1) ^ (__float_as_uint(d) & 0x80000000u));   // gl1 * sign(d)
+                g[c][v] = d != 0.0f ? sg : 0.0f;
                 s += fabsf(d);
             }
         if (own) l1 += s;
@@ -370,6 +377,8 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     __syncthreads();
 
     V *tape = reinterpret_cast<V *>(dyn_smem) + tid;       // input of operator k, plane c: tape[(k*3 + c) * SNT]
+    const unsigned int opsp = ch.ops_packed;
+    const int clamped = ch.clamped;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
@@ -387,14 +396,14 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
             tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
-            fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (ch.clamped >> k) & 1);
+            fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
         }
         upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
         if (out_b) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll 1
         for (int k = n - 1; k >= 0; --k) {
             tape_ld<VEC>(tape + k * 3 * SNT, SNT, x);
-            bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, true, (ch.clamped >> k) & 1);
+            bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
         }
         if (gi_b) st_px<VEC>(gi_b, plane, off, g);
     }
@@ -458,6 +467,9 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     const float p = sh.tabs[sp][0];
     const bool need_c = gi_b != nullptr || sp > 0;
     const int clamped = ch.clamped;
+    const unsigned int opsp = ch.ops_packed;
+    const float *up_b = go_b ? go_b : tgt_b;                       // phase B's upstream operand: grad_out, else the target
+    const size_t coff = (size_t)gx * VEC;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
@@ -465,22 +477,22 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     int rA = ya - 2 + warp, sA = warp;                             // row produced in phase A and its ring slot
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
+        const int rB = rA - 1;
+        const bool in_b = lane_on && rB >= ya - 1 && rB <= yb;                       // phase B works on this lane's row
+        const bool img_b_ok = in_b && col_ok && rB >= 0 && rB < H;                   // ... and the row is inside the image
         // ---------------- phase A: X = (operators before the stencil)(img) on row rA
-        if (col_ok && rA >= 1 && rA <= H && rA - 1 >= ya - 1 && rA - 1 <= yb)    // phase B's upstream row, one phase ahead
-            prefetch_px(go_b ? go_b : tgt_b, plane, (size_t)(rA - 1) * W + (size_t)gx * VEC);
+        if (img_b_ok) prefetch_px(up_b, plane, (size_t)rB * W + coff);               // phase B's upstream row, one phase ahead
         if (lane_on) {
             float x[3][VEC];
             if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) {
-                const size_t off = (size_t)rA * W + (size_t)gx * VEC;
-                float m[3][VEC];
-                ld_px<VEC>(img_b, plane, off, x);
+                ld_px<VEC>(img_b, plane, (size_t)rA * W + coff, x);
                 if (sp > 0) {
-                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-                    fwd_op_grp<VEC, HM>(ch.op[0], sh.tabs[0], L, x, m, false);
+                    float m[3][VEC];
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, (size_t)rA * W + coff, m);
 #pragma unroll 1
-                    for (int k = 1; k < sp; ++k) {
-                        if (interior) tape_st<VEC>(tapeP + ((k - 1) * RING + sA) * TSLOT, 32, x);
-                        fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
+                    for (int k = 0; k < sp; ++k) {
+                        if (k > 0 && interior) tape_st<VEC>(tapeP + ((k - 1) * RING + sA) * TSLOT, 32, x);
+                        fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
                     }
                 }
             } else {                                               // outside the image: the stencil's zero padding
@@ -492,61 +504,58 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
         }
         __syncthreads();
         // ---------------- phase B: stencil, operators after it, loss, their backward on row rA - 1 -> GY ring
-        {
-            const int rB = rA - 1;
-            if (col_ok && rA + SNW >= 0 && rA + SNW < H && rA + SNW <= yb + 1)   // phase A's image row of the next step
-                prefetch_px(img_b, plane, (size_t)(rA + SNW) * W + (size_t)gx * VEC);
-            if (lane_on && rB >= ya - 1 && rB <= yb) {
-                const int sB = sA >= 1 ? sA - 1 : RING - 1;
-                float gy[3][VEC], gd[3][VEC];
-                if (col_ok && rB >= 0 && rB < H) {
-                    const bool own = interior && rB >= ya && rB < yb;
-                    const size_t off = (size_t)rB * W + (size_t)gx * VEC;
-                    const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
-                    float x[3][VEC], m[3][VEC], g[3][VEC], ctr[3][VEC], lap[3][VEC];
-                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-                    const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
+        if (col_ok && rA + SNW >= 0 && rA + SNW < H && rA + SNW <= yb + 1)           // phase A's image row of the next step
+            prefetch_px(img_b, plane, (size_t)(rA + SNW) * W + coff);
+        if (in_b) {
+            const int sB = sA >= 1 ? sA - 1 : RING - 1;
+            float gy[3][VEC], gd[3][VEC];
+            if (img_b_ok) {
+                const bool own = interior && rB >= ya && rB < yb;
+                const size_t off = (size_t)rB * W + coff;
+                const int sU = sB >= 1 ? sB - 1 : RING - 1, sD = sB + 1 < RING ? sB + 1 : 0;
+                float x[3][VEC], m[3][VEC], g[3][VEC], ctr[3][VEC], lap[3][VEC];
+                ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
+                const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr[c], lap[c]);
+                for (int c = 0; c < 3; ++c) {
+                    stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr[c], lap[c]);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v)
-                            x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
-                    }
-#pragma unroll 1
-                    for (int k = sp + 1; k < n; ++k) {
-                        tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        fwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, (clamped >> k) & 1);
-                    }
-                    upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
-                    if (out_b && own) st_px<VEC>(out_b, plane, off, x);
-#pragma unroll 1
-                    for (int k = n - 1; k > sp; --k) {
-                        tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
-                        bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
-                    }
-                    float accp = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            blend_bwd<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v], g[c][v], gy[c][v], gd[c][v]);
-                            accp = fmaf(gy[c][v], lap[c][v], accp);
-                        }
-                    if (own) A.sharp += accp;
-                } else {                                           // outside the image: no stencil output there
-                    zero3<VEC>(gy);
-                    zero3<VEC>(gd);
+                    for (int v = 0; v < VEC; ++v)
+                        x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
                 }
-                if (need_c) {
-                    float *dst = GYc + sB * SLOTF;
+#pragma unroll 1
+                for (int k = sp + 1; k < n; ++k) {
+                    tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
+                    fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
+                }
+                upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
+                if (out_b && own) st_px<VEC>(out_b, plane, off, x);
+#pragma unroll 1
+                for (int k = n - 1; k > sp; --k) {
+                    tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
+                    bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
+                }
+                float accp = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, gy[c]);
-                    if constexpr (HM) {
-                        float *dd = GDc + sB * SLOTF;
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) st_vec<VEC>(dd + c * ROWF, gd[c]);
+                    for (int v = 0; v < VEC; ++v) {
+                        blend_bwd<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v], g[c][v], gy[c][v], gd[c][v]);
+                        accp = fmaf(gy[c][v], lap[c][v], accp);
                     }
+                if (own) A.sharp += accp;
+            } else {                                               // outside the image: no stencil output there
+                zero3<VEC>(gy);
+                zero3<VEC>(gd);
+            }
+            if (need_c) {
+                float *dst = GYc + sB * SLOTF;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, gy[c]);
+                if constexpr (HM) {
+                    float *dd = GDc + sB * SLOTF;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) st_vec<VEC>(dd + c * ROWF, gd[c]);
                 }
             }
         }
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
             if (interior && rC >= ya && rC < yb) {
                 const int sC = sA >= 2 ? sA - 2 : sA - 2 + RING;
                 const int sU = sC >= 1 ? sC - 1 : RING - 1, sD = sC + 1 < RING ? sC + 1 : 0;
-                const size_t off = (size_t)rC * W + (size_t)gx * VEC;
+                const size_t off = (size_t)rC * W + coff;
                 float g[3][VEC];
                 const float *yc = GYc + sC * SLOTF, *yu = GYc + sU * SLOTF, *yd = GYc + sD * SLOTF;
 #pragma unroll
@@ -575,10 +584,10 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll 1
                     for (int k = sp - 1; k >= 1; --k) {
                         tape_ld<VEC>(tapeP + ((k - 1) * RING + sC) * TSLOT, 32, x);
-                        bwd_op_grp<VEC, HM>(ch.op[k], sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
+                        bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
                     }
                     ld_px<VEC>(img_b, plane, off, x);
-                    bwd_op_grp<VEC, HM>(ch.op[0], sh.tabs[0], L, x, m, g, A, true, false);
+                    bwd_op_grp<VEC, HM>(packed_op(opsp, 0), sh.tabs[0], L, x, m, g, A, true, false);
                 }
                 if (gi_b) st_px<VEC>(gi_b, plane, off, g);
             }

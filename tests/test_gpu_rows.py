@@ -95,15 +95,16 @@ def test_rows_chains_host_ops(TF, shape, mask_ch):
     out = TF.execute_rows(x, CHAIN_ROWS, p, mc)
     (out - target.cuda()).abs().mean().backward()
     assert max_abs(out.detach().cpu(), out_o) <= TOL_PIX
-    # one kink pixel (see rel_err_kinks) moves a mean-L1 parameter gradient by ~1/numel: absolute slack of 1e-6
-    assert rel_err(p.grad.cpu(), gp_o, atol=1e-6) <= TOL_GRAD
+    # one kink pixel (see rel_err_kinks) moves a mean-L1 parameter gradient by up to ~1/numel = 1.3e-5 * |dy/dp|:
+    # absolute slack of 5e-6 (row 0 of shape0 has two such pixels, measured 2e-6)
+    assert rel_err(p.grad.cpu(), gp_o, atol=5e-6) <= TOL_GRAD
     assert rel_err_kinks(x.grad.cpu(), gi_o) <= TOL_GRAD
     # fused step: forward + L1 + backward in one launch per tiling
     out2, l1, gp, gi = TF.rows_forward_backward(img.cuda(), CHAIN_ROWS, params.cuda(), target.cuda(), mc, want_grad_img=True)
     assert max_abs(out2.cpu(), out_o) <= TOL_PIX
     assert np.allclose(l1.cpu().numpy(), l1_o.numpy(), rtol=3e-6, atol=1e-4)
     for b, ops in enumerate(CHAIN_ROWS):
-        assert rel_err(gp[b].cpu(), gp_o[b], atol=1e-6) <= TOL_GRAD, 'row %d ops %s' % (b, ops)
+        assert rel_err(gp[b].cpu(), gp_o[b], atol=5e-6) <= TOL_GRAD, 'row %d ops %s' % (b, ops)
     assert rel_err_kinks(gi.cpu(), gi_o) <= TOL_GRAD
 
 
