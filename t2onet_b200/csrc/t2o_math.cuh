@@ -143,9 +143,9 @@ T2O_HD float lum_rn(float r, float g, float b) {
 // whitebal.  : tab[0..2]
 // tone       : one curve table at tab[0]
 // color      : three curve tables at tab[0], tab[CT], tab[2*CT]
-// curve table: segment j = 0..L at ct[4j]: (k'_j, Q_j, K_j, 0) with K_j = k'_{j-1} for 0 < j < L, else 0: at an
-//              exact knot x = j/L both neighbouring clamp terms of the reference pass the gradient (closed
-//              intervals), so dy/dx = k'_j + K_j there.  Segment L repeats L-1 and serves x == 1.0.
+// curve table: segment j = 0..L at ct[4j]: (k'_j, Q_j, K_j, 0) with K_j = k'_j + k'_{j-1} for 0 < j < L, else k'_j:
+//              at an exact knot x = j/L both neighbouring clamp terms of the reference pass the gradient (closed
+//              intervals), so dy/dx = K_j there.  Segment L repeats L-1 and serves x == 1.0.
 //              ct[CT_INVS] = 1/S, ct[CT_SCALE] = L/S
 T2O_HD void build_curve(const float *k, int L, float *ct) {
     float S = 0.0f;
@@ -163,7 +163,7 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
         }
         ct[4 * j] = kp;
         ct[4 * j + 1] = q;
-        ct[4 * j + 2] = (j > 0 && j < L) ? k[j - 1] * scale : 0.0f;
+        ct[4 * j + 2] = (j > 0 && j < L) ? kp + k[j - 1] * scale : kp;
         ct[4 * j + 3] = 0.0f;
     }
     // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
@@ -177,7 +177,7 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     }
     ct[4 * L] = ct[4 * (L - 1)];
     ct[4 * L + 1] = ct[4 * (L - 1) + 1];
-    ct[4 * L + 2] = 0.0f;
+    ct[4 * L + 2] = ct[4 * (L - 1)];
     ct[4 * L + 3] = 0.0f;
     ct[CT_INVS] = 1.0f / S;
     ct[CT_SCALE] = scale;
@@ -228,16 +228,19 @@ T2O_HD void contrast_y(const float *tab, float r, float g, float b, float &yr, f
     yr = r * F; yg = g * F; yb = b * F;
 }
 
-// bin of a clamped input xs in [0, 1]: j = floor(L xs) in 0..L, t = L xs, tf = float(j)
-T2O_HD int curve_bin(float xs, int L, float &t, float &tf) {
+// bin of a clamped input xs in [0, 1]: j = floor(L xs) in 0..L, t = L xs, tf = float(j); returns the segment
+// record of bin j.  On the device the record's address comes straight from the bit pattern of 2^23 + floor(t)
+// (0x4B000000 + j): one shift-add, no mask (xs is clamped, so j <= L always).
+T2O_HD const float *curve_seg(const float *ct, float xs, int L, float &t, float &tf) {
     t = xs * (float)L;
 #if defined(__CUDA_ARCH__)
     const float u = __fadd_rd(t, 8388608.0f);       // 2^23 + floor(t): the low mantissa bits are the bin
     tf = u - 8388608.0f;
-    return __float_as_int(u) & 15;
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(ct) +
+                                           (((unsigned)__float_as_int(u) << 4) - (0x4B000000u << 4)));
 #else
     tf = floorf(t);
-    return (int)tf;
+    return ct + 4 * (int)tf;
 #endif
 }
 struct F4 { float a, b, c, d; };   // == float4
@@ -246,8 +249,7 @@ template <bool CL>
 T2O_HD float curve_y(const float *ct, int L, float x) {
     const float xs = CL ? x : sat01(x);
     float t, tf;
-    const int j = curve_bin(xs, L, t, tf);
-    const F2 seg = *reinterpret_cast<const F2 *>(ct + 4 * j);
+    const F2 seg = *reinterpret_cast<const F2 *>(curve_seg(ct, xs, L, t, tf));
     return fmaf(seg.a, xs, seg.b);
 }
 
@@ -437,8 +439,7 @@ template <bool HM, bool CL>
 T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, F2 *G, bool own) {
     const float xs = CL ? x : sat01(x);
     float t, tf;
-    const int j = curve_bin(xs, L, t, tf);
-    const F4 seg = *reinterpret_cast<const F4 *>(ct + 4 * j);
+    const F4 seg = *reinterpret_cast<const F4 *>(curve_seg(ct, xs, L, t, tf));
     const float y = fmaf(seg.a, xs, seg.b);
     float gy, gd;
     blend_bwd<HM>(y, x, m, g, gy, gd);
@@ -448,7 +449,7 @@ T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, F2 *G,
 #endif
     for (int i = 0; i < MAX_L / 2; ++i)
         G[i] = fma2(F2{ga, ga}, F2{sat01(t - (float)(2 * i)), sat01(t - (float)(2 * i + 1))}, G[i]);
-    const float slope = t == tf ? seg.a + seg.c : seg.a;            // exact knot: both clamp terms pass
+    const float slope = t == tf ? seg.c : seg.a;                    // exact knot: both clamp terms pass
     const float gx = gy * slope;
     return gd + ((CL || in01(x)) ? gx : 0.0f);
 }

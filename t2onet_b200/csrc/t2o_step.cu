@@ -96,28 +96,50 @@ static size_t rows_smem_bytes(int n, int sharp, int vec, bool has_mask, int SNT)
     return ((has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
 }
 
-template <int VEC, bool HM, int NTH>
-static int launch_step(StepArgs &a, cudaStream_t stream) {
+template <int VEC, bool HM, int NTH, unsigned int SP>
+static int launch_step_sp(StepArgs &a, cudaStream_t stream) {
     const bool rows = a.ch.sharp >= 0;
     const int B = a.g.B, H = a.g.H, W = a.g.W;
     size_t smem;
     if (!rows) {
-        smem = (size_t)a.ch.n * 3 * NTH * VEC * sizeof(float);
-        int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, false>, smem);
-        if (st) return st;
-        geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, false>, NTH, smem), NTH);
-        dim3 grid(a.g.nchunks, B);
-        step_flat_kernel<VEC, HM, NTH, false><<<grid, NTH, smem, stream>>>(a);
+        if constexpr (SP == 0u || sp_sharp(SP) < 0) {
+            smem = (size_t)a.ch.n * 3 * NTH * VEC * sizeof(float);
+            int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, false, SP>, smem);
+            if (st) return st;
+            geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, false, SP>, NTH, smem), NTH);
+            dim3 grid(a.g.nchunks, B);
+            step_flat_kernel<VEC, HM, NTH, false, SP><<<grid, NTH, smem, stream>>>(a);
+        }
     } else {
-        smem = rows_smem_bytes(a.ch.n, a.ch.sharp, VEC, HM, NTH);
-        int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, false>, smem);
-        if (st) return st;
-        geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, false>, NTH, smem), NTH, 4);
-        dim3 grid(a.g.nchunks, B);
-        step_sharp_kernel<VEC, HM, NTH, false><<<grid, NTH, smem, stream>>>(a);
+        if constexpr (SP == 0u || sp_sharp(SP) >= 0) {
+            smem = rows_smem_bytes(a.ch.n, a.ch.sharp, VEC, HM, NTH);
+            int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, false, SP>, smem);
+            if (st) return st;
+            geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, false, SP>, NTH, smem), NTH, 4);
+            dim3 grid(a.g.nchunks, B);
+            step_sharp_kernel<VEC, HM, NTH, false, SP><<<grid, NTH, smem, stream>>>(a);
+        }
     }
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
+}
+
+// T2O_NO_SPECIALIZED=1 in the environment forces the run-time dispatched kernels; read at every launch so that
+// the parity tests can compare both paths in one process.
+static bool use_specialized() {
+    const char *e = getenv("T2O_NO_SPECIALIZED");
+    return !(e && e[0] == '1');
+}
+
+template <int VEC, bool HM, int NTH>
+static int launch_step(StepArgs &a, cudaStream_t stream) {
+    if constexpr (VEC == 4 && !HM) {       // chain-specialised instantiations (unmasked, 128-bit groups)
+        if (use_specialized()) {
+            if (a.ch.ops_packed == SP_C6) return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
+            if (a.ch.ops_packed == SP_P5) return launch_step_sp<VEC, HM, NTH, SP_P5>(a, stream);
+        }
+    }
+    return launch_step_sp<VEC, HM, NTH, 0u>(a, stream);
 }
 
 // Per-row chains: one launch of each tiling; a CTA whose row belongs to the other tiling exits at once.

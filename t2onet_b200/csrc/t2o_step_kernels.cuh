@@ -118,7 +118,25 @@ T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, i
 
 // operator id of chain position k from the packed register copy (two ALU instructions; a c[][] / shared-memory
 // load indexed by k would put its latency in front of every dispatch branch)
-__device__ __forceinline__ int packed_op(unsigned int ops_packed, int k) { return (int)((ops_packed >> (4 * k)) & 15u) - 1; }
+__host__ __device__ __forceinline__ constexpr int packed_op(unsigned int ops_packed, int k) { return (int)((ops_packed >> (4 * k)) & 15u) - 1; }
+
+// Chain-specialised instantiations: a kernel's SP template argument is the ops_packed word of ONE chain known at
+// compile time (0 = any chain, dispatched at run time).  With SP != 0 the operator loops unroll completely, every
+// operator switch folds away and the compiler schedules across operator boundaries.  The canonical FiveK order
+// brightness, contrast, saturation, color, tone, sharpness (preprocess/gen_greedy_seqs_FiveK.py:39) is instantiated.
+__host__ __device__ constexpr unsigned int pack_ops(int o0 = -1, int o1 = -1, int o2 = -1, int o3 = -1, int o4 = -1, int o5 = -1, int o6 = -1, int o7 = -1) {
+    return (unsigned)(o0 + 1) | (unsigned)(o1 + 1) << 4 | (unsigned)(o2 + 1) << 8 | (unsigned)(o3 + 1) << 12 |
+           (unsigned)(o4 + 1) << 16 | (unsigned)(o5 + 1) << 20 | (unsigned)(o6 + 1) << 24 | (unsigned)(o7 + 1) << 28;
+}
+__host__ __device__ constexpr int sp_count(unsigned int sp) { int n = 0; for (int k = 0; k < MAX_CHAIN; ++k) if ((sp >> (4 * k)) & 15u) n = k + 1; return n; }
+__host__ __device__ constexpr int sp_sharp(unsigned int sp) { for (int k = 0; k < MAX_CHAIN; ++k) if (packed_op(sp, k) == OP_SHARPNESS) return k; return -1; }
+__host__ __device__ constexpr int sp_clamped(unsigned int sp) {
+    int c = 0;
+    for (int k = 1; k < MAX_CHAIN; ++k) if (packed_op(sp, k - 1) >= 0 || ((c >> (k - 1)) & 1)) c |= 1 << k;
+    return c;
+}
+constexpr unsigned int SP_C6 = pack_ops(OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_TONE, OP_SHARPNESS);
+constexpr unsigned int SP_P5 = pack_ops(OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_TONE);
 
 // ---------------------------------------------------------------- operator dispatch over one pixel group
 // `cl`: the operator's input is known to lie in [0, 1] (lets the curve operators skip their input clamp)
@@ -349,8 +367,11 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepDesc 
 }
 
 // =========================================================================================== flat (no stencil)
-template <int VEC, bool HM, int NTH, bool ROWS>
+template <int VEC, bool HM, int NTH, bool ROWS, unsigned int SP = 0u>
 __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!(ROWS && SP), "per-row chains are dispatched at run time");
+    constexpr int UNR = SP ? MAX_CHAIN : 1;
+    constexpr int SPN = sp_count(SP), SPS = sp_sharp(SP), SPC = sp_clamped(SP);   // compile-time chain facts (SP != 0)
     using V = typename VecT<VEC>::type;
     constexpr int SNT = NTH;
     extern __shared__ __align__(16) float dyn_smem[];
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
         if (sh.rdesc.sharp >= 0) return;                    // rows with a stencil belong to step_sharp_kernel
     }
     const StepDesc &ch = ROWS ? sh.rdesc : a.ch;
-    const int n = ch.n, L = ch.L;
+    const int n = SP ? SPN : ch.n, L = ch.L;
     const size_t plane = (size_t)a.g.H * a.g.W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
     const float *tgt_b = a.target ? a.target + (size_t)b * 3 * plane : nullptr;
@@ -377,8 +398,8 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     __syncthreads();
 
     V *tape = reinterpret_cast<V *>(dyn_smem) + tid;       // input of operator k, plane c: tape[(k*3 + c) * SNT]
-    const unsigned int opsp = ch.ops_packed;
-    const int clamped = ch.clamped;
+    const unsigned int opsp = SP ? SP : ch.ops_packed;
+    const int clamped = SP ? SPC : ch.clamped;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
@@ -393,14 +414,14 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
         ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
         prefetch_px(go_b ? go_b : tgt_b, plane, off);                       // needed after the forward sweep
         if (gi + SNT < g1) prefetch_px(img_b, plane, off + (size_t)SNT * VEC);   // next iteration
-#pragma unroll 1
+#pragma unroll UNR
         for (int k = 0; k < n; ++k) {
             tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
             fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
         }
         upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
         if (out_b) st_px<VEC>(out_b, plane, off, x);
-#pragma unroll 1
+#pragma unroll UNR
         for (int k = n - 1; k >= 0; --k) {
             tape_ld<VEC>(tape + k * 3 * SNT, SNT, x);
             bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);
@@ -414,8 +435,11 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
 // Shared-memory layout (compile-time strides): a ring row holds 3 planes of 34 groups (one zero pad group each
 // side of the 32 lanes); the tape of the operators before the stencil holds, per operator 1 .. sp-1, RING rows of
 // 3 x 32 vectors; the operators after the stencil keep a per-thread tape.
-template <int VEC, bool HM, int NTH, bool ROWS>
+template <int VEC, bool HM, int NTH, bool ROWS, unsigned int SP = 0u>
 __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!(ROWS && SP), "per-row chains are dispatched at run time");
+    constexpr int UNR = SP ? MAX_CHAIN : 1;
+    constexpr int SPN = sp_count(SP), SPS = sp_sharp(SP), SPC = sp_clamped(SP);   // compile-time chain facts (SP != 0)
     using V = typename VecT<VEC>::type;
     constexpr int SNT = NTH, SNW = NTH / 32, RING = SNW + 2;
     constexpr int ROWF = 34 * VEC;                 // floats of one ring row of one plane
@@ -433,7 +457,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
         if (sh.rdesc.sharp < 0) return;                     // rows without a stencil belong to step_flat_kernel
     }
     const StepDesc &ch = ROWS ? sh.rdesc : a.ch;
-    const int n = ch.n, L = ch.L, sp = ch.sharp;
+    const int n = SP ? SPN : ch.n, L = ch.L, sp = SP ? SPS : ch.sharp;
     const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
     const size_t plane = (size_t)H * W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
@@ -466,8 +490,8 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 
     const float p = sh.tabs[sp][0];
     const bool need_c = gi_b != nullptr || sp > 0;
-    const int clamped = ch.clamped;
-    const unsigned int opsp = ch.ops_packed;
+    const int clamped = SP ? SPC : ch.clamped;
+    const unsigned int opsp = SP ? SP : ch.ops_packed;
     const float *up_b = go_b ? go_b : tgt_b;                       // phase B's upstream operand: grad_out, else the target
     const size_t coff = (size_t)gx * VEC;
     GradAcc A;
@@ -489,7 +513,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                 if (sp > 0) {
                     float m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, (size_t)rA * W + coff, m);
-#pragma unroll 1
+#pragma unroll UNR
                     for (int k = 0; k < sp; ++k) {
                         if (k > 0 && interior) tape_st<VEC>(tapeP + ((k - 1) * RING + sA) * TSLOT, 32, x);
                         fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
@@ -523,14 +547,14 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                     for (int v = 0; v < VEC; ++v)
                         x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
                 }
-#pragma unroll 1
+#pragma unroll UNR
                 for (int k = sp + 1; k < n; ++k) {
                     tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
                     fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
                 }
                 upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
                 if (out_b && own) st_px<VEC>(out_b, plane, off, x);
-#pragma unroll 1
+#pragma unroll UNR
                 for (int k = n - 1; k > sp; --k) {
                     tape_ld<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
                     bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, own, (clamped >> k) & 1);
@@ -581,7 +605,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                 if (sp > 0) {
                     float x[3][VEC], m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-#pragma unroll 1
+#pragma unroll UNR
                     for (int k = sp - 1; k >= 1; --k) {
                         tape_ld<VEC>(tapeP + ((k - 1) * RING + sC) * TSLOT, 32, x);
                         bwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, g, A, true, (clamped >> k) & 1);

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import ops as O
-from parity_util import TOL_GRAD, TOL_PIX, max_abs, oracle_chain_with_grads, rel_err, sample_params
+from parity_util import TOL_GRAD, TOL_PIX, max_abs, oracle_chain_with_grads, rel_err, rel_err_kinks, sample_params
 
 pytestmark = pytest.mark.gpu
 
@@ -204,6 +204,37 @@ def test_determinism_bitwise(TF):
     assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1]) and torch.equal(r1[3], r2[3])
     for a, b in zip(r1[2], r2[2]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('ops', [[0, 1, 2, 3, 5, 6], [0, 1, 2, 3, 5]], ids=['c6', 'p5'])
+@pytest.mark.parametrize('shape', [(2, 40, 64), (1, 96, 260), (3, 128, 128)])
+def test_specialized_chain_kernels_match_generic_and_oracle(TF, ops, shape, monkeypatch):
+    """The chain-specialised instantiations (t2o_step.cu: SP_C6 / SP_P5) against the run-time dispatched kernels
+    (T2O_NO_SPECIALIZED=1, read at every launch) and against the oracle."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(79 + H + len(ops))
+    img = torch.rand(B, 3, H, W, generator=g)
+    params = [sample_params(op, B, g) for op in ops]
+    with torch.no_grad():
+        target = O.chain(img, ops, [sample_params(op, B, g) for op in ops])
+    out_o, l1_o, gp_o, gi_o = oracle_chain_with_grads(img, ops, params, target)
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('T2O_NO_SPECIALIZED', mode)
+        res[mode] = TF.chain_forward_backward(img.cuda(), ops, [p.cuda() for p in params], target.cuda(), want_grad_img=True)
+        torch.cuda.synchronize()
+    for mode, (out, l1, grads, gimg) in res.items():
+        assert max_abs(out.cpu(), out_o) <= TOL_PIX
+        assert np.allclose(l1.cpu().numpy(), l1_o.numpy(), rtol=3e-6, atol=1e-4)
+        # a pixel whose forward value sits within an ulp of a kink (clamp edge, curve knot, out == target of the L1)
+        # moves a mean-L1 parameter gradient by ~1/numel * |dy/dp|: absolute slack 5e-6, as in test_gpu_rows
+        for k in range(len(ops)):
+            assert rel_err(grads[k].cpu(), gp_o[k], atol=5e-6) <= TOL_GRAD, (mode, k)
+        assert rel_err_kinks(gimg.cpu(), gi_o) <= TOL_GRAD, mode
+    (o0, l0, g0, i0), (o1, l1_, g1, i1) = res['0'], res['1']
+    assert max_abs(o0.cpu(), o1.cpu()) <= 1e-6 and rel_err_kinks(i0.cpu(), i1.cpu()) <= 1e-5
+    for a, b in zip(g0, g1):
+        assert rel_err(a.cpu(), b.cpu()) <= 1e-5
 
 
 def test_score_candidates_oracle(TF):
