@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import ops as O
-from parity_util import TOL_GRAD, TOL_PIX, max_abs, oracle_chain_with_grads, rel_err, rel_err_kinks, sample_params
+from parity_util import TOL_GRAD, TOL_PIX, kink_slack, max_abs, oracle_chain_with_grads, rel_err, rel_err_kinks, sample_params
 
 pytestmark = pytest.mark.gpu
 
@@ -227,9 +227,11 @@ def test_specialized_chain_kernels_match_generic_and_oracle(TF, ops, shape, monk
         assert max_abs(out.cpu(), out_o) <= TOL_PIX
         assert np.allclose(l1.cpu().numpy(), l1_o.numpy(), rtol=3e-6, atol=1e-4)
         # a pixel whose forward value sits within an ulp of a kink (clamp edge, curve knot, out == target of the L1)
-        # moves a mean-L1 parameter gradient by ~1/numel * |dy/dp|: absolute slack 5e-6, as in test_gpu_rows
+        # moves a mean-L1 parameter gradient by ~1/numel * |dy/dp|; the kink pixels are counted from the image
+        # gradients (<= 2 allowed) and only they buy absolute slack -- a kink-free run is held to TOL_GRAD as is
+        slack = kink_slack(gimg.cpu(), gi_o, img.numel())
         for k in range(len(ops)):
-            assert rel_err(grads[k].cpu(), gp_o[k], atol=5e-6) <= TOL_GRAD, (mode, k)
+            assert rel_err(grads[k].cpu(), gp_o[k], atol=slack) <= TOL_GRAD, (mode, k)
         assert rel_err_kinks(gimg.cpu(), gi_o) <= TOL_GRAD, mode
     (o0, l0, g0, i0), (o1, l1_, g1, i1) = res['0'], res['1']
     assert max_abs(o0.cpu(), o1.cpu()) <= 1e-6 and rel_err_kinks(i0.cpu(), i1.cpu()) <= 1e-5
