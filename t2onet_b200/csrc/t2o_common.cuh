@@ -62,6 +62,31 @@ __device__ __forceinline__ void lds_vec(const float *p, float (&v)[VEC]) {
     else { v[0] = *p; }
 }
 
+// asynchronous global -> shared copy of one VEC-float vector (LDGSTS: the data never passes through registers, so a
+// thread can have its next rows in flight while it computes); a thread only ever reads back what it copied itself,
+// hence cp_async_wait_all() alone -- no barrier -- makes the data visible to it
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(float *smem_dst, const float *gsrc) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    if constexpr (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// three planes of a pixel group -> a thread's staging slots (`sstride` floats between the planes)
+template <int VEC>
+__device__ __forceinline__ void cp_async_px(float *stg, int sstride, const float *base, size_t plane, size_t off) {
+    cp_async_vec<VEC>(stg, base + off);
+    cp_async_vec<VEC>(stg + sstride, base + plane + off);
+    cp_async_vec<VEC>(stg + 2 * sstride, base + 2 * plane + off);
+}
+template <int VEC>
+__device__ __forceinline__ void lds_px(const float *stg, int sstride, float (&x)[3][VEC]) {
+    lds_vec<VEC>(stg, x[0]);
+    lds_vec<VEC>(stg + sstride, x[1]);
+    lds_vec<VEC>(stg + 2 * sstride, x[2]);
+}
+
 // pixel-group loads: three planes (+ optional mask planes)
 template <int VEC>
 __device__ __forceinline__ void ld_px(const float *base, size_t plane, size_t off, float (&x)[3][VEC]) {

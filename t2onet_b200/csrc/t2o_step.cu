@@ -93,7 +93,8 @@ static size_t rows_smem_bytes(int n, int sharp, int vec, bool has_mask, int SNT)
     const size_t ringf = (size_t)RING * 3 * 34 * vec;
     const size_t ntp = sharp > 1 ? sharp - 1 : 0;
     const size_t ntq = n - sharp - 1;
-    return ((has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
+    const size_t stage = (size_t)3 * SNT * vec;            // per-thread staging slots of the asynchronous row copies
+    return (stage + (has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
 }
 
 template <int VEC, bool HM, int NTH, unsigned int SP>

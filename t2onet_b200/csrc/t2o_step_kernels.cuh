@@ -213,12 +213,16 @@ __device__ __forceinline__ void zero3(float (&x)[3][VEC]) {
         for (int v = 0; v < VEC; ++v) x[c][v] = 0.0f;
 }
 
-// upstream gradient of a pixel group: explicit grad_out, or the fused L1: gl1 * sign(out - target)
+// upstream gradient of a pixel group: explicit grad_out, or the fused L1: gl1 * sign(out - target).
+// `u` holds the group's values of the upstream operand (grad_out if there is one, else the target), already loaded.
 template <int VEC>
-__device__ __forceinline__ void upstream_grad(const float *go_b, const float *tgt_b, size_t plane, size_t off, float gl1,
-                                              const float (&x)[3][VEC], float (&g)[3][VEC], float &l1, bool own) {
-    if (go_b) {
-        ld_px<VEC>(go_b, plane, off, g);
+__device__ __forceinline__ void upstream_grad_ld(bool has_go, const float (&u)[3][VEC], const float *tgt_b, size_t plane, size_t off,
+                                                 float gl1, const float (&x)[3][VEC], float (&g)[3][VEC], float &l1, bool own) {
+    if (has_go) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) g[c][v] = u[c][v];
         if (tgt_b && own) {
             float t[3][VEC];
             ld_px<VEC>(tgt_b, plane, off, t);
@@ -230,20 +234,25 @@ __device__ __forceinline__ void upstream_grad(const float *go_b, const float *tg
             l1 += s;
         }
     } else {
-        float t[3][VEC];
-        ld_px<VEC>(tgt_b, plane, off, t);
         float s = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float d = x[c][v] - t[c][v];
+                const float d = x[c][v] - u[c][v];
                 const float sg = __uint_as_float(__float_as_uint(gl1) ^ (__float_as_uint(d) & 0x80000000u));   // gl1 * sign(d)
                 g[c][v] = d != 0.0f ? sg : 0.0f;
                 s += fabsf(d);
             }
         if (own) l1 += s;
     }
+}
+template <int VEC>
+__device__ __forceinline__ void upstream_grad(const float *go_b, const float *tgt_b, size_t plane, size_t off, float gl1,
+                                              const float (&x)[3][VEC], float (&g)[3][VEC], float &l1, bool own) {
+    float u[3][VEC];
+    ld_px<VEC>(go_b ? go_b : tgt_b, plane, off, u);
+    upstream_grad_ld<VEC>(go_b != nullptr, u, tgt_b, plane, off, gl1, x, g, l1, own);
 }
 
 // 5-point stencil of one plane around a VEC-pixel group of a ring row.  `row` points at the group's first
@@ -477,14 +486,18 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     const int ya = band * a.g.HB;
     const int yb = ya + a.g.HB < H ? ya + a.g.HB : H;
 
-    float *Xc = dyn_smem + (1 + lane) * VEC;                       // this lane's column in the X / GY / GD rings
+    // dynamic shared memory: [staging slots 3 x SNT vectors][rings][tapes]
+    float *stg = dyn_smem + tid * VEC;                             // this thread's staging slots (planes STGF floats apart)
+    constexpr int STGF = SNT * VEC;
+    float *rings = dyn_smem + 3 * STGF;
+    float *Xc = rings + (1 + lane) * VEC;                          // this lane's column in the X / GY / GD rings
     float *GYc = Xc + RINGF;
     float *GDc = GYc + RINGF;
     constexpr int NRING = HM ? 3 : 2;
-    V *tapeP = reinterpret_cast<V *>(dyn_smem + NRING * RINGF) + lane;   // [(k-1) * RING + slot][c][32], k = 1 .. sp-1
+    V *tapeP = reinterpret_cast<V *>(rings + NRING * RINGF) + lane;      // [(k-1) * RING + slot][c][32], k = 1 .. sp-1
     const int ntp = sp > 1 ? sp - 1 : 0;
-    V *tapeQ = reinterpret_cast<V *>(dyn_smem + NRING * RINGF) + ntp * RING * TSLOT + tid;   // [(k-sp-1)][c][SNT]
-    for (int i = tid; i < NRING * RINGF; i += SNT) dyn_smem[i] = 0.0f;
+    V *tapeQ = reinterpret_cast<V *>(rings + NRING * RINGF) + ntp * RING * TSLOT + tid;      // [(k-sp-1)][c][SNT]
+    for (int i = tid; i < NRING * RINGF; i += SNT) rings[i] = 0.0f;
     if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
     __syncthreads();
 
@@ -498,18 +511,22 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     acc_zero(A);
     float l1 = 0.0f;
 
+    // Global rows travel through the staging slots as asynchronous copies: the image row of phase A is requested a
+    // whole phase C ahead, the upstream row of phase B a phase A ahead.  A thread reads back only its own slots
+    // (cp.async.wait_all, no barrier), and requests the next row only after it has read the previous one.
     int rA = ya - 2 + warp, sA = warp;                             // row produced in phase A and its ring slot
+    if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) cp_async_px<VEC>(stg, STGF, img_b, plane, (size_t)rA * W + coff);
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
         const int rB = rA - 1;
         const bool in_b = lane_on && rB >= ya - 1 && rB <= yb;                       // phase B works on this lane's row
         const bool img_b_ok = in_b && col_ok && rB >= 0 && rB < H;                   // ... and the row is inside the image
         // ---------------- phase A: X = (operators before the stencil)(img) on row rA
-        if (img_b_ok) prefetch_px(up_b, plane, (size_t)rB * W + coff);               // phase B's upstream row, one phase ahead
         if (lane_on) {
             float x[3][VEC];
             if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) {
-                ld_px<VEC>(img_b, plane, (size_t)rA * W + coff, x);
+                cp_async_wait_all();
+                lds_px<VEC>(stg, STGF, x);
                 if (sp > 0) {
                     float m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, (size_t)rA * W + coff, m);
@@ -526,10 +543,9 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll
             for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, x[c]);
         }
+        if (img_b_ok) cp_async_px<VEC>(stg, STGF, up_b, plane, (size_t)rB * W + coff);   // phase B's upstream row
         __syncthreads();
         // ---------------- phase B: stencil, operators after it, loss, their backward on row rA - 1 -> GY ring
-        if (col_ok && rA + SNW >= 0 && rA + SNW < H && rA + SNW <= yb + 1)           // phase A's image row of the next step
-            prefetch_px(img_b, plane, (size_t)(rA + SNW) * W + coff);
         if (in_b) {
             const int sB = sA >= 1 ? sA - 1 : RING - 1;
             float gy[3][VEC], gd[3][VEC];
@@ -552,7 +568,12 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                     tape_st<VEC>(tapeQ + (k - sp - 1) * 3 * SNT, SNT, x);
                     fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
                 }
-                upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, own);
+                {
+                    float u[3][VEC];
+                    cp_async_wait_all();
+                    lds_px<VEC>(stg, STGF, u);
+                    upstream_grad_ld<VEC>(go_b != nullptr, u, tgt_b, plane, off, gl1, x, g, l1, own);
+                }
                 if (out_b && own) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll UNR
                 for (int k = n - 1; k > sp; --k) {
@@ -584,7 +605,14 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
             }
         }
         __syncthreads();
-        // ---------------- phase C: transposed stencil, backward of the operators before it, on row rA - 2
+        // ---------------- phase C: transposed stencil, backward of the operators before it, on row rA - 2.
+        // No barrier closes it: phase A of the next step writes ring / tape slots that phase C either does not read
+        // (X ring) or reads from the same thread earlier in program order (tape slot sC == next sA); the GY ring is
+        // rewritten only after the next step's first barrier.
+        {
+            const int rN = rA + SNW;                               // phase A's image row of the next step
+            if (col_ok && rN >= 0 && rN < H && rN <= yb + 1) cp_async_px<VEC>(stg, STGF, img_b, plane, (size_t)rN * W + coff);
+        }
         if (need_c) {
             const int rC = rA - 2;
             if (interior && rC >= ya && rC < yb) {
@@ -615,12 +643,12 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                 }
                 if (gi_b) st_px<VEC>(gi_b, plane, off, g);
             }
-            __syncthreads();                                       // the rings are rewritten by the next step
         }
         rA += SNW;
         sA += SNW;
         if (sA >= RING) sA -= RING;
     }
+    cp_async_wait_all();
     step_epilogue<NTH>(a, ch, sh, A, l1, b, chunk);
 }
 
