@@ -19,7 +19,13 @@ gout = torch.randn_like(img)
 print('C4 fused 6-op step      %.3f ms' % t(lambda: TF.chain_forward_backward(img, bench.CHAIN, params, tgt)))
 print('C4 fused 5-op flat step %.3f ms' % t(lambda: TF.chain_forward_backward(img, bench.CHAIN[:5], params[:5], tgt)))
 print('C4 sharp-first 6-op     %.3f ms' % t(lambda: TF.chain_forward_backward(img, [6, 0, 1, 2, 3, 5], [params[5]] + params[:5], tgt)))
+packed6 = torch.cat(params, 1).contiguous()
+offs6 = [0, 1, 2, 3, 27, 35]
+ms = t(lambda: TF._forward_raw(bench.CHAIN, offs6, img, None, 0, packed6, packed6.shape[1], tgt, True, True, 8))
+print('C4 forward 6-op + L1    %.3f ms  %.0f GB/s (36 B/px)' % (ms, 36 * px / ms / 1e6))
 p6 = params[5].contiguous()
+ms = t(lambda: TF._forward_raw([6], [0], img, None, 0, p6, 1, tgt, True, True, 8))
+print('C4 sharpness fwd + L1   %.3f ms  %.0f GB/s (36 B/px)' % (ms, 36 * px / ms / 1e6))
 ms = t(lambda: TF._backward_raw([6], [0], img, None, 0, p6, 1, gout, None, None, True, False, False, 8))
 print('C4 sharpness bwd        %.3f ms  %.0f GB/s (36 B/px)' % (ms, 36 * px / ms / 1e6))
 ms = t(lambda: TF._backward_raw([6], [0], img, None, 0, p6, 1, None, tgt, bench.fused_scale(16, 2048, 3072, dev), False, True, True, 8))

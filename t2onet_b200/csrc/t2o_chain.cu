@@ -1,5 +1,7 @@
 // t2o_chain.cu -- host side of the fused operator-chain kernels: geometry, workspace, launch selection.
 // The kernels live in t2o_chain_kernels.cuh; the backward instantiations are spread over t2o_chain_bwd_*.cu.
+#include <cstdlib>
+
 #include "t2o_chain_kernels.cuh"
 
 namespace t2o {
@@ -85,20 +87,34 @@ static int launch_fwd_vec(int vec, const FwdArgs &a, cudaStream_t stream) {
 
 void geom_step_rows(StepGeom &g, int B, int H, int W, int vec, int slots, int SNT, int rows_extra);
 
-template <int VEC, bool HM, bool ROWS>
-static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
-    const size_t smem = (size_t)(2 * (NT / 32) + 2) * 3 * 34 * VEC * sizeof(float);
+template <int VEC, bool HM, bool ROWS, unsigned int SP>
+static int launch_fwd_rows_sp(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
+    const size_t smem = (size_t)(2 * (NT / 32) + 2) * 3 * 34 * VEC * sizeof(float);        // the X ring
     static int resident = 0;
     if (resident == 0) {
+        if (smem > 40 * 1024)
+            T2O_CUDA_OK(cudaFuncSetAttribute(chain_fwd_rows_kernel<VEC, HM, ROWS, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_fwd_rows_kernel<VEC, HM, ROWS>, NT, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chain_fwd_rows_kernel<VEC, HM, ROWS, SP>, NT, smem) != cudaSuccess || nb < 1) nb = 1;
         resident = nb;
     }
     geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident, NT, 2);
     dim3 grid(a.g.nchunks, B);
-    chain_fwd_rows_kernel<VEC, HM, ROWS><<<grid, NT, smem, stream>>>(a);
+    chain_fwd_rows_kernel<VEC, HM, ROWS, SP><<<grid, NT, smem, stream>>>(a);
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
+}
+template <int VEC, bool HM, bool ROWS>
+static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {
+    if constexpr (VEC == 4 && !HM && !ROWS) {      // chain-specialised instantiation (unmasked, 128-bit groups)
+        const char *e = getenv("T2O_NO_SPECIALIZED");
+        if (!(e && e[0] == '1') && a.ch.n <= MAX_CHAIN) {
+            unsigned int packed = 0u;
+            for (int k = 0; k < a.ch.n; ++k) packed |= (unsigned)(a.ch.op[k] + 1) << (4 * k);
+            if (packed == SP_C6) return launch_fwd_rows_sp<VEC, HM, ROWS, SP_C6>(a, B, H, W, stream);
+        }
+    }
+    return launch_fwd_rows_sp<VEC, HM, ROWS, 0u>(a, B, H, W, stream);
 }
 template <bool HM, bool ROWS>
 static int launch_fwd_rows_vec(int vec, FwdRowsArgs &a, int B, int H, int W, cudaStream_t stream) {

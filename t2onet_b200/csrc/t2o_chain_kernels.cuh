@@ -218,8 +218,13 @@ struct FwdRowsArgs {
     unsigned int *status;
 };
 
-template <int VEC, bool HM, bool ROWS>
+// SP != 0: the chain is known at compile time (its ops_packed word, see t2o_step_kernels.cuh): the operator loops
+// unroll and every operator switch folds away.
+template <int VEC, bool HM, bool ROWS, unsigned int SP = 0u>
 __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_constant__ FwdRowsArgs a) {
+    static_assert(!(ROWS && SP), "per-row chains are dispatched at run time");
+    constexpr int UNR = SP ? MAX_CHAIN : 1;
+    constexpr int SPN = sp_count(SP), SPS = sp_sharp(SP), SPC = sp_clamped(SP);
     // ring of 2 NW + 2 rows: phase A of the next step never overwrites a row phase B of this step still reads,
     // so one barrier per step (after phase A) is enough
     constexpr int NW = NT / 32, RING = 2 * NW + 2;
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
         if (rdesc.sharp < 0) return;                        // rows without a stencil belong to chain_fwd_kernel
     }
     const ChainDesc &ch = ROWS ? rdesc : a.ch;
-    const int n = ch.n, L = ch.L, sp = ch.sharp;
+    const int n = SP ? SPN : ch.n, L = ch.L, sp = SP ? SPS : ch.sharp;
     const int H = a.g.H, W = a.g.W, Wg = a.g.Wg;
     const size_t plane = (size_t)H * W;
     const float *img_b = a.img + (size_t)b * 3 * plane;
@@ -260,10 +265,11 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
     for (int i = tid; i < RINGF; i += NT) dyn_smem[i] = 0.0f;
     if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, tabs[tid]);
 
-    const int clamped = ROWS ? chain_clamped_bits(ch.op, n) : a.clamped;
+    const int clamped = SP ? SPC : (ROWS ? chain_clamped_bits(ch.op, n) : a.clamped);
     float l1 = 0.0f;
     int rA = ya - 1 + warp, sA = warp;
-    // L1 prefetches one phase ahead (this kernel keeps ~5 CTAs per SM and a small ring, so the L1 has room)
+    // L1 prefetches one phase ahead (this kernel keeps 4 CTAs per SM and a small ring, so the L1 has room; the
+    // cp.async staging of the step kernels costs a CTA of occupancy here and measured slower)
     if (col_ok && rA >= 0 && rA < H && rA <= yb) prefetch_px(img_b, plane, (size_t)rA * W + coff);
     __syncthreads();
     const float p = tabs[sp][0];
@@ -272,17 +278,17 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
         const int rB = rA - 1;
         const bool do_b = interior && rB >= ya && rB < yb;
         // ---------------- phase A: X on row rA
+        if (do_b && tgt_b) prefetch_px(tgt_b, plane, (size_t)rB * W + coff);                     // phase B's target row
         if (lane_on) {
             float x[3][VEC];
-            if (do_b && tgt_b) prefetch_px(tgt_b, plane, (size_t)rB * W + coff);           // phase B's target row
             if (col_ok && rA >= 0 && rA < H && rA <= yb) {
-                const size_t off = (size_t)rA * W + coff;
-                ld_px<VEC>(img_b, plane, off, x);
+                ld_px<VEC>(img_b, plane, (size_t)rA * W + coff, x);
                 if (sp > 0) {
                     float m[3][VEC];
-                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-#pragma unroll 1
-                    for (int k = 0; k < sp; ++k) fwd_op_grp<VEC, HM>(ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+                    ldm<VEC, HM>(mask_b, a.mask_ch, plane, (size_t)rA * W + coff, m);
+#pragma unroll UNR
+                    for (int k = 0; k < sp; ++k)
+                        fwd_op_grp<VEC, HM>(SP ? packed_op(SP, k) : ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
                 }
             } else {
                 zero3<VEC>(x);                                              // outside the image: the stencil's zero padding
@@ -313,8 +319,9 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
                         x[c][v] = raw ? yv : sat01(blend<HM>(yv, ctr[v], m[c][v]));
                     }
                 }
-#pragma unroll 1
-                for (int k = sp + 1; k < n; ++k) fwd_op_grp<VEC, HM>(ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
+#pragma unroll UNR
+                for (int k = sp + 1; k < n; ++k)
+                    fwd_op_grp<VEC, HM>(SP ? packed_op(SP, k) : ch.op[k], tabs[k], L, x, m, (clamped >> k) & 1);
                 if (tgt_b) {
                     float t[3][VEC];
                     ld_px<VEC>(tgt_b, plane, off, t);

@@ -73,6 +73,11 @@ __device__ __forceinline__ void cp_async_vec(float *smem_dst, const float *gsrc)
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// explicit groups, for a thread that keeps two copies in flight and needs only the older one: commit after every
+// (possibly empty) request so that the group count is the same on every path, then wait until <= N groups are pending
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // three planes of a pixel group -> a thread's staging slots (`sstride` floats between the planes)
 template <int VEC>
 __device__ __forceinline__ void cp_async_px(float *stg, int sstride, const float *base, size_t plane, size_t off) {

@@ -104,7 +104,7 @@ static int launch_step_sp(StepArgs &a, cudaStream_t stream) {
     size_t smem;
     if (!rows) {
         if constexpr (SP == 0u || sp_sharp(SP) < 0) {
-            smem = (size_t)a.ch.n * 3 * NTH * VEC * sizeof(float);
+            smem = (size_t)(a.ch.n + 2) * 3 * NTH * VEC * sizeof(float);        // tape + two staging slot sets
             int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, false, SP>, smem);
             if (st) return st;
             geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, false, SP>, NTH, smem), NTH);
@@ -149,7 +149,7 @@ template <int VEC, bool HM, int NTH>
 static int launch_step_rows(StepArgs &a, int paths, cudaStream_t stream) {
     const int B = a.g.B, H = a.g.H, W = a.g.W, K = a.rows_K;
     if (paths & 1) {
-        const size_t smem = (size_t)K * 3 * NTH * VEC * sizeof(float);
+        const size_t smem = (size_t)(K + 2) * 3 * NTH * VEC * sizeof(float);        // tape + two staging slot sets
         int st = step_set_smem(step_flat_kernel<VEC, HM, NTH, true>, smem);
         if (st) return st;
         geom_step_flat(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_flat_kernel<VEC, HM, NTH, true>, NTH, smem), NTH);

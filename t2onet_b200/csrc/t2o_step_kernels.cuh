@@ -406,9 +406,13 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
     __syncthreads();
 
-    V *tape = reinterpret_cast<V *>(dyn_smem) + tid;       // input of operator k, plane c: tape[(k*3 + c) * SNT]
+    // dynamic shared memory: [staging slots: image 3 x SNT vectors, upstream 3 x SNT vectors][tape]
+    constexpr int STGF = SNT * VEC;
+    float *stg_i = dyn_smem + tid * VEC, *stg_u = stg_i + 3 * STGF;
+    V *tape = reinterpret_cast<V *>(dyn_smem + 6 * STGF) + tid;   // input of operator k, plane c: tape[(k*3 + c) * SNT]
     const unsigned int opsp = SP ? SP : ch.ops_packed;
     const int clamped = SP ? SPC : ch.clamped;
+    const float *up_b = go_b ? go_b : tgt_b;
     GradAcc A;
     acc_zero(A);
     float l1 = 0.0f;
@@ -416,19 +420,28 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     const long long g0 = (long long)chunk * a.g.chunk_groups;
     long long g1 = g0 + a.g.chunk_groups;
     if (g1 > a.g.ngroups) g1 = a.g.ngroups;
+    // the image group of the next iteration and the upstream group of this one are in flight (cp.async into the
+    // thread's own staging slots) while the forward sweep runs
+    if (g0 + tid < g1) cp_async_px<VEC>(stg_i, STGF, img_b, plane, (size_t)(g0 + tid) * VEC);
     for (long long gi = g0 + tid; gi < g1; gi += SNT) {
         const size_t off = (size_t)gi * VEC;
         float x[3][VEC], m[3][VEC], g[3][VEC];
-        ld_px<VEC>(img_b, plane, off, x);
+        cp_async_wait_all();
+        lds_px<VEC>(stg_i, STGF, x);
+        cp_async_px<VEC>(stg_u, STGF, up_b, plane, off);
+        if (gi + SNT < g1) cp_async_px<VEC>(stg_i, STGF, img_b, plane, off + (size_t)SNT * VEC);
         ldm<VEC, HM>(mask_b, a.mask_ch, plane, off, m);
-        prefetch_px(go_b ? go_b : tgt_b, plane, off);                       // needed after the forward sweep
-        if (gi + SNT < g1) prefetch_px(img_b, plane, off + (size_t)SNT * VEC);   // next iteration
 #pragma unroll UNR
         for (int k = 0; k < n; ++k) {
             tape_st<VEC>(tape + k * 3 * SNT, SNT, x);
             fwd_op_grp<VEC, HM>(packed_op(opsp, k), sh.tabs[k], L, x, m, (clamped >> k) & 1);
         }
-        upstream_grad<VEC>(go_b, tgt_b, plane, off, gl1, x, g, l1, true);
+        {
+            float u[3][VEC];
+            cp_async_wait_all();
+            lds_px<VEC>(stg_u, STGF, u);
+            upstream_grad_ld<VEC>(go_b != nullptr, u, tgt_b, plane, off, gl1, x, g, l1, true);
+        }
         if (out_b) st_px<VEC>(out_b, plane, off, x);
 #pragma unroll UNR
         for (int k = n - 1; k >= 0; --k) {
@@ -522,11 +535,16 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
         const bool in_b = lane_on && rB >= ya - 1 && rB <= yb;                       // phase B works on this lane's row
         const bool img_b_ok = in_b && col_ok && rB >= 0 && rB < H;                   // ... and the row is inside the image
         // ---------------- phase A: X = (operators before the stencil)(img) on row rA
+        const bool in_a = col_ok && rA >= 0 && rA < H && rA <= yb + 1;               // phase A has an image row to work on
+        float xa[3][VEC];
+        if (in_a) {
+            cp_async_wait_all();
+            lds_px<VEC>(stg, STGF, xa);
+        }
+        if (img_b_ok) cp_async_px<VEC>(stg, STGF, up_b, plane, (size_t)rB * W + coff);   // phase B's upstream row
         if (lane_on) {
-            float x[3][VEC];
-            if (col_ok && rA >= 0 && rA < H && rA <= yb + 1) {
-                cp_async_wait_all();
-                lds_px<VEC>(stg, STGF, x);
+            float (&x)[3][VEC] = xa;
+            if (in_a) {
                 if (sp > 0) {
                     float m[3][VEC];
                     ldm<VEC, HM>(mask_b, a.mask_ch, plane, (size_t)rA * W + coff, m);
@@ -543,7 +561,6 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll
             for (int c = 0; c < 3; ++c) st_vec<VEC>(dst + c * ROWF, x[c]);
         }
-        if (img_b_ok) cp_async_px<VEC>(stg, STGF, up_b, plane, (size_t)rB * W + coff);   // phase B's upstream row
         __syncthreads();
         // ---------------- phase B: stencil, operators after it, loss, their backward on row rA - 1 -> GY ring
         if (in_b) {
