@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define T2O_VERSION 101          /* major*100 + minor */
+#define T2O_VERSION 102          /* major*100 + minor */
 #define T2O_MAX_CHAIN 8          /* operators fused in one launch */
 #define T2O_MAX_CURVE_STEPS 8    /* cfg.curve_steps (options/fiveK_base_options.py:50) */
 #define T2O_MAX_OP_PARAMS 24     /* color: 3 * curve_steps */
@@ -41,6 +41,7 @@ extern "C" {
 /* Operator ids = reference Executor indices (executors/executor.py:30) + extension ids for the
  * operator classes that exist without an Executor slot (models/operators.py:186,527). */
 enum t2o_op {
+    T2O_OP_SKIP = -2,         /* t2o_score_candidates only: the candidate is not evaluated (a finished Nelder-Mead fit) */
     T2O_OP_IDENTITY = -1,     /* executors/executor.py:44-46 (op_ind < 0): passthrough, no clamp */
     T2O_OP_BRIGHTNESS = 0,    /* models/operators.py:277-283 */
     T2O_OP_CONTRAST = 1,      /* models/operators.py:240-245 */
@@ -165,6 +166,41 @@ int t2o_score_candidates(const float *states, int S, const float *targets, int T
                          const int32_t *cand_op, const float *cand_param, int C,
                          float *l1_sum, int H, int W, int curve_steps,
                          void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
+ * Device-resident Nelder-Mead: P independent fits argmin_param L1(op(state; param), target), one per (state, operator)
+ * pair of a planner step -- scipy.optimize.minimize(func, param0, method='Nelder-Mead') as utils/beam_search.py:88
+ * calls it (scipy defaults: xatol = fatol = 1e-4, maxiter = maxfev = 200 N, initial simplex step 5 % / 2.5e-4),
+ * with float64 simplex arithmetic in scipy's operation order.  A fit is a sequential chain of evaluations; an
+ * evaluation is candidate p of t2o_score_candidates (fits and candidates share the index, sorted by state):
+ *     t2o_nm_start(...)                                   builds the simplices, writes the first vertices
+ *     repeat: t2o_score_candidates(...cand_op, cand_param... -> l1_sum);  t2o_nm_advance(... l1_sum ...)
+ * Nothing synchronises with the host: vertices (cand_param, float32 rows of 24) and scores (l1_sum) stay in device
+ * memory, so rounds can be enqueued back to back or captured in a CUDA graph.  A finished fit sets its
+ * cand_op[p] = T2O_OP_SKIP (the scorer then ignores it), ctl[p][1] = 6 and leaves its result in xbest / fbest.
+ * All state is caller-allocated device memory; no initialisation is required before t2o_nm_start.
+ */
+typedef struct {
+    double *sim;      /* (P, 25, 24) simplex vertices */
+    double *fsim;     /* (P, 25)     function values by sorted position */
+    double *vec;      /* (P, 3, 24)  centroid, reflected point, pending point */
+    double *fxr;      /* (P,)        value of the reflected point */
+    double *xbest;    /* (P, 24)     result: best vertex (valid once the fit is done) */
+    double *fbest;    /* (P,)        result: its function value */
+    int32_t *perm;    /* (P, 25)     simplex row of each sorted position */
+    int32_t *ctl;     /* (P, 8)      n, phase (6 = done), k, function calls, iterations, scipy status (0 ok, 1 maxfev, 2 maxiter), op, 0 */
+} t2o_nm_state;
+
+/* n_dims (P,) int32: parameters of each fit (1..24); prob_op (P,) int32: its operator id; x0 (P, 24) float64 start
+ * points (utils/beam_search.py:150-153: zeros, ones for the curve operators). */
+int t2o_nm_start(const t2o_nm_state *state /*host struct of device pointers*/, int P,
+                 const int32_t *n_dims, const int32_t *prob_op, const double *x0,
+                 float *cand_param, int32_t *cand_op, t2o_stream_t stream);
+/* l1_sum (P,): the scorer's output for the pending vertices; numel = 3*H*W*batch of get_dist's mean
+ * (utils/beam_search.py:172): the function value is float32(l1_sum * float32(1 / numel)) -- torch's CUDA division by a
+ * host scalar -- widened to float64, as .item() gives. */
+int t2o_nm_advance(const t2o_nm_state *state /*host struct of device pointers*/, int P,
+                   const float *l1_sum, float numel, float *cand_param, int32_t *cand_op, t2o_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,11 @@ class T2OError(RuntimeError):
     pass
 
 
+class NMState(ctypes.Structure):
+    """t2o_nm_state of include/t2o.h: device pointers of the Nelder-Mead state arrays."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ('sim', 'fsim', 'vec', 'fxr', 'xbest', 'fbest', 'perm', 'ctl')]
+
+
 def _declare(lib):
     lib.t2o_version.restype = ctypes.c_int
     lib.t2o_status_string.restype = ctypes.c_char_p
@@ -57,13 +62,17 @@ def _declare(lib):
     lib.t2o_l1_sum.argtypes = [vp, vp, vp, ci, ctypes.c_int64, vp, ctypes.c_size_t, vp]
     lib.t2o_score_candidates.restype = ci
     lib.t2o_score_candidates.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, ci, vp, ctypes.c_size_t, vp]
+    lib.t2o_nm_start.restype = ci
+    lib.t2o_nm_start.argtypes = [ctypes.POINTER(NMState), ci, vp, vp, vp, vp, vp, vp]
+    lib.t2o_nm_advance.restype = ci
+    lib.t2o_nm_advance.argtypes = [ctypes.POINTER(NMState), ci, vp, ctypes.c_float, vp, vp, vp]
     return lib
 
 
 EXPORTS = ['t2o_version', 't2o_status_string', 't2o_last_cuda_error', 't2o_num_params', 't2o_workspace_bytes',
            't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_rows_forward',
            't2o_rows_backward', 't2o_l1_sum',
-           't2o_score_candidates']
+           't2o_score_candidates', 't2o_nm_start', 't2o_nm_advance']
 
 
 def lib():

@@ -27,6 +27,10 @@ size_t score_workspace_bytes(int S, int C, int H, int W);
 int score_candidates(const float *states, int S, const float *targets, int T, const int *state_target,
                      const int *cand_begin, const int *cand_op, const float *cand_param, int C, float *l1_sum,
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int nm_start(const t2o_nm_state *st, int P, const int *n_dims, const int *prob_op, const double *x0,
+             float *cand_param, int *cand_op, cudaStream_t stream);
+int nm_advance(const t2o_nm_state *st, int P, const float *l1_sum, float numel, float *cand_param, int *cand_op,
+               cudaStream_t stream);
 const char *last_cuda_error();
 }  // namespace t2o
 
@@ -108,6 +112,16 @@ int t2o_score_candidates(const float *states, int S, const float *targets, int T
                          int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
     return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, C, l1_sum, H, W,
                                  curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_nm_start(const t2o_nm_state *state, int P, const int32_t *n_dims, const int32_t *prob_op, const double *x0,
+                 float *cand_param, int32_t *cand_op, t2o_stream_t stream) {
+    return t2o::nm_start(state, P, n_dims, prob_op, x0, cand_param, cand_op, (cudaStream_t)stream);
+}
+
+int t2o_nm_advance(const t2o_nm_state *state, int P, const float *l1_sum, float numel, float *cand_param,
+                   int32_t *cand_op, t2o_stream_t stream) {
+    return t2o::nm_advance(state, P, l1_sum, numel, cand_param, cand_op, (cudaStream_t)stream);
 }
 
 }  // extern "C"

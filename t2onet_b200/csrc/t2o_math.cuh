@@ -35,7 +35,7 @@
 namespace t2o {
 
 enum : int {
-    OP_IDENTITY = -1, OP_BRIGHTNESS = 0, OP_CONTRAST = 1, OP_SATURATION = 2, OP_COLOR = 3, OP_INPAINT = 4,
+    OP_SKIP = -2, OP_IDENTITY = -1, OP_BRIGHTNESS = 0, OP_CONTRAST = 1, OP_SATURATION = 2, OP_COLOR = 3, OP_INPAINT = 4,
     OP_TONE = 5, OP_SHARPNESS = 6, OP_WHITE = 7, OP_EXPOSURE = 8, OP_WHITEBALANCE = 9, OP_COUNT = 10
 };
 

@@ -81,6 +81,15 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
     const int spitch = TW + 2 * HX, srows = TH + 2;
     const int t_idx = a.state_target ? a.state_target[s] : s % a.T;
 
+    // a state whose candidates are all T2O_OP_SKIP (finished fits) is not even staged; every CTA of the state takes
+    // the same decision, so the state's arrival counter stays untouched
+    const int cbeg = a.cand_begin[s], cend = a.cand_begin[s + 1];
+    {
+        bool any = false;
+        for (int ci = cbeg; ci < cend; ++ci) any |= a.cand_op[ci] != OP_SKIP;
+        if (!any) return;
+    }
+
     float *sS = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
     float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sS) + ((3 * srows * spitch * 4 + 127) & ~127));
     const size_t plane = (size_t)H * W;
@@ -117,12 +126,12 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         __syncthreads();
     }
 
-    const int cbeg = a.cand_begin[s], cend = a.cand_begin[s + 1];
     const int TWg = TW / VEC;
     const int ngroups = TH * TWg;
     float *tab = wtab[warp];
     for (int ci = cbeg + split * SCORE_NW + warp; ci < cend; ci += a.nsplit * SCORE_NW) {
         const int op = a.cand_op[ci];
+        if (op == OP_SKIP) continue;
         __syncwarp();
         if (lane == 0) build_table(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
         __syncwarp();

@@ -475,3 +475,95 @@ def score_candidates(states, targets, cand_state, cand_op, cand_param, state_tar
     states, targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
     cb = CandidateBatch(states.shape[0], cand_state, cand_op, cand_param, states.device, state_target)
     return score_prepared(states, targets, cb, curve_steps)
+
+
+class DeviceNelderMead:
+    """P Nelder-Mead fits that live on the GPU (t2o_nm_start / t2o_nm_advance), each scored as candidate p of
+    t2o_score_candidates: argmin_param L1(op(states[prob_state[p]]; param), its target) with scipy's defaults, as
+    get_param_naive runs them one by one through scipy (utils/beam_search.py:65-91).
+
+    prob_state must be ascending.  run() enqueues rounds of (score, advance) without host synchronisation -- after a
+    warm-up the rounds replay as a CUDA graph -- and looks at the fits' state only every `check_every` rounds.
+    Results: x (P, 24) float64 (columns >= n are 0), fun (P,) float64, nit / nfev / status (P,) int32."""
+
+    ROWS = _lib.MAX_OP_PARAMS + 1
+
+    def __init__(self, states, targets, prob_state, prob_op, x0, state_target=None, curve_steps=CURVE_STEPS, numel=None):
+        self.states, self.targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
+        dev = self.states.device
+        self.dev, self.L = dev, curve_steps
+        S, _, H, W = self.states.shape
+        self.S, self.H, self.W = S, H, W
+        P = len(prob_op)
+        self.P = P
+        self.numel = float(numel if numel is not None else 3 * H * W)
+        n_dims = [num_params(int(o), curve_steps) for o in prob_op]
+        if any(n < 1 or n > _lib.MAX_OP_PARAMS for n in n_dims):
+            raise _lib.T2OError('Nelder-Mead fits need operators with 1..24 parameters')
+        x0m = torch.zeros(P, _lib.MAX_OP_PARAMS, dtype=torch.float64)
+        for i, (v, n) in enumerate(zip(x0, n_dims)):
+            x0m[i, :n] = torch.as_tensor(v, dtype=torch.float64).flatten()[:n]
+        self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target)
+        self.n_dims = torch.tensor(n_dims, dtype=torch.int32, device=dev)
+        self.prob_op = torch.as_tensor(prob_op, dtype=torch.int32).to(dev)
+        self.x0 = x0m.to(dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.sim = torch.empty(P, self.ROWS, _lib.MAX_OP_PARAMS, **f64)
+        self.fsim = torch.empty(P, self.ROWS, **f64)
+        self.vec = torch.zeros(P, 3, _lib.MAX_OP_PARAMS, **f64)
+        self.fxr = torch.zeros(P, **f64)
+        self.xbest = torch.zeros(P, _lib.MAX_OP_PARAMS, **f64)
+        self.fbest = torch.zeros(P, **f64)
+        self.perm = torch.zeros(P, self.ROWS, dtype=torch.int32, device=dev)
+        self.ctl = torch.zeros(P, 8, dtype=torch.int32, device=dev)
+        self.l1 = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.state = _lib.NMState(*[t.data_ptr() for t in (self.sim, self.fsim, self.vec, self.fxr, self.xbest, self.fbest,
+                                                            self.perm, self.ctl)])
+        self.rounds = 0
+        lib = _lib.lib()
+        self.ws = _lib.workspace(dev, lib.t2o_score_workspace_bytes(S, P, H, W))
+        _lib.check(lib.t2o_nm_start(ctypes.byref(self.state), P, _lib.ptr(self.n_dims), _lib.ptr(self.prob_op), _lib.ptr(self.x0),
+                                    _lib.ptr(self.cb.prm), _lib.ptr(self.cb.ops), _lib.stream_ptr(dev)))
+
+    def _round(self):
+        lib, cb = _lib.lib(), self.cb
+        sp = _lib.stream_ptr(self.dev)
+        _lib.check(lib.t2o_score_candidates(_lib.ptr(self.states), self.S, _lib.ptr(self.targets), self.targets.shape[0],
+                                            _lib.ptr(cb.state_target), _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm),
+                                            self.P, _lib.ptr(self.l1), self.H, self.W, self.L, _lib.ptr(self.ws),
+                                            self.ws.numel(), sp))
+        _lib.check(lib.t2o_nm_advance(ctypes.byref(self.state), self.P, _lib.ptr(self.l1), self.numel, _lib.ptr(cb.prm),
+                                      _lib.ptr(cb.ops), sp))
+
+    def active(self):
+        """Number of unfinished fits (synchronises)."""
+        return int((self.ctl[:, 1] != 6).sum().item())
+
+    def run(self, check_every=64, use_graph=True, max_rounds=None):
+        limit = 200 * _lib.MAX_OP_PARAMS + 8 if max_rounds is None else max_rounds
+        for _ in range(check_every):                               # eager warm-up (also sets the kernels' attributes)
+            self._round()
+        self.rounds += check_every
+        graph = None
+        while self.rounds < limit and self.active() > 0:
+            if use_graph and graph is None:
+                # the rounds are identical launches over fixed buffers: record them once, replay from now on
+                side = torch.cuda.Stream(self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):         # _round() launches on the capturing stream
+                    for _ in range(check_every):
+                        self._round()
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+            if graph is not None:
+                graph.replay()
+            else:
+                for _ in range(check_every):
+                    self._round()
+            self.rounds += check_every
+        return self.result()
+
+    def result(self):
+        ctl = self.ctl.cpu()
+        return {'x': self.xbest.cpu(), 'fun': self.fbest.cpu(), 'nit': ctl[:, 4].clone(), 'nfev': ctl[:, 3].clone(),
+                'status': ctl[:, 5].clone(), 'done': (ctl[:, 1] == 6), 'n': ctl[:, 0].clone()}

@@ -23,8 +23,13 @@ class NMResult:
         self.success = status == 0
 
 
-def nelder_mead(x0, xatol=1e-4, fatol=1e-4):
-    """Generator: yields a float64 vertex to evaluate, expects f(vertex) via send(); returns NMResult."""
+def nelder_mead(x0, xatol=1e-4, fatol=1e-4, stable=False):
+    """Generator: yields a float64 vertex to evaluate, expects f(vertex) via send(); returns NMResult.
+
+    stable=True sorts the simplex with a stable argsort (ties keep their order) instead of scipy's np.argsort
+    default (an unstable quicksort whose tie order is an implementation detail): that is what the device version
+    (csrc/t2o_nm.cu) does, and the setting its cross-check uses."""
+    argsort = (lambda a: np.argsort(a, kind='stable')) if stable else np.argsort
     x0 = np.asarray(np.atleast_1d(x0).flatten(), dtype=np.float64)
     rho, chi, psi, sigma = 1, 2, 0.5, 0.5
     nonzdelt, zdelt = 0.05, 0.00025
@@ -55,10 +60,10 @@ def nelder_mead(x0, xatol=1e-4, fatol=1e-4):
             fsim[k] = yield from func(sim[k])
     except _MaxFun:
         pass
-    ind = np.argsort(fsim)
+    ind = argsort(fsim)
     sim = np.take(sim, ind, 0)
     fsim = np.take(fsim, ind, 0)
-    ind = np.argsort(fsim)
+    ind = argsort(fsim)
     fsim = np.take(fsim, ind, 0)
     sim = np.take(sim, ind, 0)
     iterations = 1
@@ -108,7 +113,7 @@ def nelder_mead(x0, xatol=1e-4, fatol=1e-4):
             iterations += 1
         except _MaxFun:
             pass
-        ind = np.argsort(fsim)
+        ind = argsort(fsim)
         sim = np.take(sim, ind, 0)
         fsim = np.take(fsim, ind, 0)
     x = sim[0]

@@ -5,13 +5,19 @@ candidate-scoring kernel.
 What changes underneath: the reference fits the parameters of every
 (beam state, operator) pair one after the other, each Nelder-Mead evaluation being an
 `executor.execute` + `get_dist` + `.item()` round trip (utils/beam_search.py:77-87).  Here all fits
-of a beam step advance in lock-step (t2onet_b200/nelder_mead.py) and every round scores the pending
-vertex of every fit with ONE `t2o_score_candidates` launch over the TMA-staged state tiles.  The
-selection logic (utils/beam_search.py:239-259) is unchanged.
+of a beam step -- of every image pair in flight (`beam_search_batch`) -- advance in lock-step as
+device-resident Nelder-Mead state machines (t2o_nm_start / t2o_nm_advance, csrc/t2o_nm.cu); a round
+scores the pending vertex of every fit with ONE `t2o_score_candidates` launch over the TMA-staged state
+tiles, and vertices / scores never leave device memory (rounds replay as a CUDA graph).  The fitted
+candidates of a step are applied and scored by one per-row launch (t2o_rows_forward).  The selection
+logic (utils/beam_search.py:239-259) is unchanged.  t2onet_b200/nelder_mead.py is the same
+Nelder-Mead as a host coroutine (`T2O_HOST_NM=1` or `fit_params_nelder_mead_host`), kept as the
+cross-check of the device version.
 
 Only the 'L1' distance is implemented: the discriminator branches of the reference call undefined
 names (utils/beam_search.py:42,55) and are dead code.
 """
+import os
 import random
 
 import numpy as np
@@ -62,14 +68,14 @@ def _param0(operation, executor):
     assert False, 'the operation is not global operation'
 
 
-def fit_params_nelder_mead(states, targets, problems, executor, state_target=None, counter=None):
-    """Fit many (state index, operator) problems at once.
+def fit_params_nelder_mead_host(states, targets, problems, executor, state_target=None, counter=None, stable=False):
+    """Fit many (state index, operator) problems at once with the host coroutine (one launch + one sync per round).
 
     states (S,3,H,W) / targets (T,3,H,W) CUDA tensors; problems: list of (state_idx, operation).
     Returns a list of NMResult in problem order (x is float64, as scipy returns it)."""
     numel = float(states[0].numel())
     L = getattr(executor.opt, 'curve_steps', 8)
-    gens = {i: nelder_mead(_param0(op, executor)) for i, (s, op) in enumerate(problems)}
+    gens = {i: nelder_mead(_param0(op, executor), stable=stable) for i, (s, op) in enumerate(problems)}
     order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))   # candidates sorted by state
     rank = {k: r for r, k in enumerate(order)}
 
@@ -94,20 +100,59 @@ def fit_params_nelder_mead(states, targets, problems, executor, state_target=Non
     return [res[i] for i in range(len(problems))]
 
 
+class _Fit:
+    __slots__ = ('x', 'fun', 'nit', 'nfev', 'status', 'success')
+
+    def __init__(self, x, fun, nit, nfev, status):
+        self.x, self.fun, self.nit, self.nfev, self.status = x, fun, nit, nfev, status
+        self.success = status == 0
+
+
+def fit_params_nelder_mead(states, targets, problems, executor, state_target=None, counter=None, numel=None):
+    """Fit many (state index, operator) problems at once on the device (TF.DeviceNelderMead).
+
+    states (S,3,H,W) / targets (T,3,H,W) CUDA tensors; problems: list of (state_idx, operation).
+    Returns a list of results (x float64 (n,), fun, nit, nfev, status, success) in problem order."""
+    if os.environ.get('T2O_HOST_NM') == '1':
+        return fit_params_nelder_mead_host(states, targets, problems, executor, state_target, counter)
+    if not problems:
+        return []
+    L = getattr(executor.opt, 'curve_steps', 8)
+    order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))       # the scorer wants candidates sorted by state
+    nm = TF.DeviceNelderMead(states, targets, [problems[i][0] for i in order], [problems[i][1] for i in order],
+                             [_param0(problems[i][1], executor) for i in order], state_target=state_target,
+                             curve_steps=L, numel=numel)
+    r = nm.run()
+    assert bool(r['done'].all()), 'Nelder-Mead fits did not finish'
+    if counter is not None:
+        counter[0] += int(r['nfev'].sum())
+    out = [None] * len(problems)
+    x, fun = r['x'].numpy(), r['fun'].numpy()
+    for pos, i in enumerate(order):
+        n = int(r['n'][pos])
+        out[i] = _Fit(x[pos, :n].copy(), float(fun[pos]), int(r['nit'][pos]), int(r['nfev'][pos]), int(r['status'][pos]))
+    return out
+
+
 def get_param_naive(img, out, txt, mask, param0, executor, discriminator, op_ind, dist_type, optimizer):
     """utils/beam_search.py:65-91 (L1 only): Nelder-Mead from param0 -> (param (1,n) tensor, success)."""
     assert dist_type == 'L1'
     L = getattr(executor.opt, 'curve_steps', 8)
     numel = float(img.numel())
-    gen = nelder_mead(np.asarray(param0, dtype=np.float64))
+    if os.environ.get('T2O_HOST_NM') == '1':
+        gen = nelder_mead(np.asarray(param0, dtype=np.float64))
 
-    def score(keys, points):
-        prm = np.zeros((1, 24), dtype=np.float32)
-        prm[0, :len(points[0])] = points[0]
-        l1 = TF.score_candidates(img, out, [0], [op_ind], torch.from_numpy(prm), curve_steps=L)
-        return (l1 / numel).tolist()
-    res = run_lockstep({0: gen}, score)[0]
-    return torch.tensor(np.array([list(res.x)])).to(img.device), res.success
+        def score(keys, points):
+            prm = np.zeros((1, 24), dtype=np.float32)
+            prm[0, :len(points[0])] = points[0]
+            l1 = TF.score_candidates(img, out, [0], [op_ind], torch.from_numpy(prm), curve_steps=L)
+            return (l1 / numel).tolist()
+        res = run_lockstep({0: gen}, score)[0]
+        return torch.tensor(np.array([list(res.x)])).to(img.device), res.success
+    nm = TF.DeviceNelderMead(img, out, [0], [op_ind], [np.asarray(param0, dtype=np.float64)], curve_steps=L, numel=numel)
+    r = nm.run()
+    n = int(r['n'][0])
+    return r['x'][:1, :n].clone().to(img.device), int(r['status'][0]) == 0
 
 
 def gd_minimize(func, param0, method='adam'):
@@ -161,78 +206,127 @@ def get_param(I0, I1, txt, operation, executor, discriminator, dist_type, optimi
     return get_param_gd(I0, I1, txt, None, param0, executor, discriminator, operation, dist_type, optimizer)
 
 
-def _score_outputs(I_list, ops, params, I_gt, executor):
-    """I_out and dist for every fitted candidate of a step (utils/beam_search.py:230,237)."""
-    outs, dists = [], []
-    numel = float(I_gt.numel())
+def _score_outputs(I_list, ops, params, I_gt_list, executor):
+    """I_out and dist for every fitted candidate of a step (utils/beam_search.py:230,237): one per-row launch
+    (every row its own state, operator, parameters and target), one device->host read of the distances."""
+    if not I_list:
+        return [], []
     L = getattr(executor.opt, 'curve_steps', 8)
-    for I, op, p in zip(I_list, ops, params):
-        p32 = p.to(I.device).float()
-        packed, offs, pstride = TF.pack_params([op], [p32], I.shape[0], I.device, L)
-        out, l1 = TF._forward_raw([op], offs, I, None, 0, packed, pstride, I_gt, True, True, L)
-        outs.append(out)
-        dists.append(l1.sum() / numel)
-    vals = torch.stack(dists).tolist() if dists else []
+    dev = I_list[0].device
+    numel = float(I_gt_list[0].numel())
+    outs, vals = [], []
+    CH = 1024                                                       # rows per launch (bounds the temporaries)
+    for c0 in range(0, len(I_list), CH):
+        Is, Gs = I_list[c0:c0 + CH], I_gt_list[c0:c0 + CH]
+        img = torch.cat(Is, 0).contiguous()
+        tgt = torch.cat(Gs, 0).contiguous()
+        prm = torch.zeros(len(Is), 24, dtype=torch.float32)
+        for r, p in enumerate(params[c0:c0 + CH]):
+            prm[r, :p.shape[1]] = p[0].float()                      # float64 -> float32, as torch.tensor([param], dtype=torch.float)
+        row_ops = [[int(o)] for o in ops[c0:c0 + CH]]
+        ops_dev, ops_host = TF._prep_row_ops(row_ops, len(Is), dev)
+        out, l1 = TF._rows_forward_raw(ops_dev, ops_host, img, None, 0, prm.to(dev), tgt, True, True, L)
+        vals += (l1 / numel).tolist()
+        outs += [out[r:r + 1] for r in range(len(Is))]
     return outs, vals
+
+
+def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type='L1',
+                      optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None):
+    """`beam_search` (utils/beam_search.py:196-264) for M image pairs at once: I_0, I_gt (M,3,H,W).
+
+    Every pair runs the reference's beam search unchanged; what is shared is the work: all (pair, beam state,
+    operator) fits of a step advance in lock-step on the device and are applied / scored by one launch.
+    Returns a list of M (actions, Is) tuples, each exactly what `beam_search` returns for that pair."""
+    assert dist_type == 'L1', 'only the L1 distance is implemented'
+    I_0 = I_0.to(device) if not I_0.is_cuda else I_0
+    I_gt = I_gt.to(I_0.device)
+    M = I_0.shape[0]
+    numel = float(I_gt[0:1].numel())
+    st = [{'min_dist': float('inf'), 'sequences': [[[], float('inf')]], 'I_buff': [I_0[m:m + 1]], 'alive': True}
+          for m in range(M)]
+    for i in range(max_step):
+        live = [m for m in range(M) if st[m]['alive']]
+        if not live:
+            break
+        # -- every (pair, beam state, operator) of this step (utils/beam_search.py:220-223)
+        problems, states, state_pair = [], [], []       # problem: (state index, operation, pair, beam index)
+        for m in live:
+            seqs, buff = st[m]['sequences'], st[m]['I_buff']
+            for j in range(len(buff)):
+                s_idx = len(states)
+                states.append(buff[j])
+                state_pair.append(m)
+                step_ops = [operations[i]] if _variant == 'fixed_order' else operations
+                for operation in step_ops:
+                    if not replace and operation in [operation_names.index(v[0]) for v in seqs[j][0]]:
+                        continue
+                    problems.append((s_idx, operation, m, j))
+        # -- fit all of them (utils/beam_search.py:229)
+        if optimizer == 'Nelder-Mead' and problems:
+            fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _ in problems],
+                                          executor, state_target=state_pair, counter=counter, numel=numel)
+            params = [torch.tensor(np.array([list(r.x)])) for r in fits]
+        else:
+            params = [get_param(states[s], I_gt[m:m + 1], txt, op, executor, None, dist_type, optimizer)[0]
+                      for s, op, m, _ in problems]
+        # -- apply + score (utils/beam_search.py:230-237)
+        outs, dists = _score_outputs([states[s] for s, _, _, _ in problems], [op for _, op, _, _ in problems], params,
+                                     [I_gt[m:m + 1] for _, _, m, _ in problems], executor)
+        # -- the reference's bookkeeping, pair by pair (utils/beam_search.py:239-259)
+        by_pair = {m: [] for m in live}
+        for k, (s, op, m, j) in enumerate(problems):
+            by_pair[m].append((j, op, params[k], outs[k], dists[k]))
+        for m in live:
+            S = st[m]
+            all_candidates, I_tmp_list, tmp_min_dists = [], [], []
+            no_update_flag, finish_flag = True, False
+            for j, operation, param, I_out, dist in by_pair[m]:
+                if _variant == 'eps_greedy' or dist < S['min_dist']:
+                    tmp_min_dists.append(dist)
+                    candidate = [S['sequences'][j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out)], dist]
+                    all_candidates.append(candidate)
+                    I_tmp_list.append(I_out)
+                    if _variant != 'eps_greedy':
+                        no_update_flag = False
+                    if dist < err:
+                        finish_flag = True
+            S['min_dist'] = min(tmp_min_dists) if len(tmp_min_dists) > 0 else S['min_dist']
+            if len(all_candidates) < beam_size:
+                all_candidates += S['sequences']
+                I_tmp_list += S['I_buff']
+            dists_arr = np.array([v[1] for v in all_candidates])
+            order = np.argsort(dists_arr)
+            if _variant == 'eps_greedy' and random.random() < _eps:
+                chosen = random.choices(range(len(all_candidates)), k=beam_size)
+            else:
+                chosen = list(order)[:beam_size]
+            # the kept images are rows of this step's output tensor: copy them out (once) so that it can be freed
+            S['sequences'], S['I_buff'] = [], []
+            for idx in chosen:
+                seq, img = all_candidates[idx], I_tmp_list[idx]
+                if img._base is not None:
+                    img = img.clone()
+                    seq = [seq[0][:-1] + [seq[0][-1][:-1] + (img,)], seq[1]]
+                S['sequences'].append(seq)
+                S['I_buff'].append(img)
+            if no_update_flag or finish_flag:
+                S['alive'] = False
+    results = []
+    for m in range(M):
+        seqs = st[m]['sequences']
+        actions = [[act[:-1] for act in seq[0]] for seq in seqs]
+        Is = [[act[-1].cpu() for act in seq[0]] for seq in seqs]      # the reference returns CPU images (:236)
+        results.append((actions, Is))
+    return results
 
 
 def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,
                 dist_type, optimizer, replace=False, _variant='default', _eps=0.05, counter=None):
     """utils/beam_search.py:196-264 -- same arguments and return value:
     actions: list(beam) of list(step) of (op_name, param list, dist); Is: same nesting of CPU images."""
-    assert dist_type == 'L1', 'only the L1 distance is implemented'
-    I_0 = I_0.to(device) if not I_0.is_cuda else I_0
-    I_gt = I_gt.to(I_0.device)
-    min_dist = float('inf')
-    sequences = [[[], float('inf')]]
-    I_buff = [I_0]
-    for i in range(max_step):
-        all_candidates, I_tmp_list, tmp_min_dists = [], [], []
-        no_update_flag, finish_flag = True, False
-        # -- every (beam state, operator) pair of this step (utils/beam_search.py:220-223)
-        problems = []
-        for j in range(len(I_buff)):
-            step_ops = [operations[i]] if _variant == 'fixed_order' else operations
-            for operation in step_ops:
-                if not replace and operation in [operation_names.index(v[0]) for v in sequences[j][0]]:
-                    continue
-                problems.append((j, operation))
-        # -- fit all of them (utils/beam_search.py:229)
-        if optimizer == 'Nelder-Mead' and problems:
-            states = torch.cat(I_buff, 0).contiguous()
-            fits = fit_params_nelder_mead(states, I_gt, problems, executor, state_target=[0] * len(I_buff),
-                                          counter=counter)
-            params = [torch.tensor(np.array([list(r.x)])) for r in fits]
-        else:
-            params = [get_param(I_buff[j], I_gt, txt, op, executor, None, dist_type, optimizer)[0] for j, op in problems]
-        # -- apply + score (utils/beam_search.py:230-237), then the reference's bookkeeping (:239-246)
-        outs, dists = _score_outputs([I_buff[j] for j, _ in problems], [op for _, op in problems], params, I_gt, executor)
-        for (j, operation), param, I_out, dist in zip(problems, params, outs, dists):
-            if _variant == 'eps_greedy' or dist < min_dist:
-                tmp_min_dists.append(dist)
-                candidate = [sequences[j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out.cpu())], dist]
-                all_candidates.append(candidate)
-                I_tmp_list.append(I_out)
-                if _variant != 'eps_greedy':
-                    no_update_flag = False
-                if dist < err:
-                    finish_flag = True
-        min_dist = min(tmp_min_dists) if len(tmp_min_dists) > 0 else min_dist
-        if len(all_candidates) < beam_size:
-            all_candidates += sequences
-            I_tmp_list += I_buff
-        dists_arr = np.array([v[1] for v in all_candidates])
-        order = np.argsort(dists_arr)
-        if _variant == 'eps_greedy' and random.random() < _eps:
-            sequences = random.choices(all_candidates, k=beam_size)
-        else:
-            sequences = [all_candidates[idx] for idx in order][:beam_size]
-        I_buff = [I_tmp_list[idx] for idx in order][:beam_size]
-        if no_update_flag or finish_flag:
-            break
-    actions = [[act[:-1] for act in seq[0]] for seq in sequences]
-    Is = [[act[-1] for act in seq[0]] for seq in sequences]
-    return actions, Is
+    return beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type,
+                             optimizer, replace, _variant, _eps, counter, txt)[0]
 
 
 def beam_search_fixed_order(I_0, I_gt, txt, executor, beam_size, operations, operation_names, max_step, err, dist_type,

@@ -1,0 +1,74 @@
+"""Device-resident Nelder-Mead (t2o_nm_start / t2o_nm_advance, csrc/t2o_nm.cu) against the host coroutine restating
+scipy's _minimize_neldermead (t2onet_b200/nelder_mead.py, itself checked against scipy in test_host_logic.py): both are
+driven by the same scorer (t2o_score_candidates), so equal function values must give the same vertex sequence --
+final vertices, function values, iteration and evaluation counts are compared EXACTLY.  (The coroutine runs with
+stable=True: exact ties between fp32 function values are common, and scipy's tie order is numpy's unstable-quicksort
+implementation detail, which the device's stable rank sort does not imitate.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from parity_util import sample_params
+
+pytestmark = pytest.mark.gpu
+GLOBAL_OPS = [0, 1, 2, 3, 5, 6]
+
+
+@pytest.fixture(scope='module')
+def T():
+    import t2onet_b200 as T
+    return T
+
+
+def _pairs(S, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(S, 3, H, W, generator=g)
+    tgt = img.clone()
+    for op in (0, 5, 6):                                   # a planted edit so that the fits have something to find
+        tgt = O.execute(op, tgt, sample_params(op, S, g))
+    return img.cuda(), tgt.cuda()
+
+
+def test_device_nm_equals_host_coroutine(T):
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    states, targets = _pairs(3, 32, 48, 77)
+    problems = [(0, 0), (0, 1), (0, 2), (0, 5), (0, 6), (1, 3), (1, 5), (1, 6), (2, 0), (2, 2)]
+    host = planner.fit_params_nelder_mead_host(states, targets, problems, ex, state_target=[0, 1, 2], stable=True)
+    dev = planner.fit_params_nelder_mead(states, targets, problems, ex, state_target=[0, 1, 2])
+    for (s, op), h, d in zip(problems, host, dev):
+        assert d.nfev == h.nfev and d.nit == h.nit and d.status == h.status, (s, op, d.nfev, h.nfev, d.nit, h.nit)
+        assert np.array_equal(np.asarray(d.x), np.asarray(h.x)), (s, op, d.x, h.x)
+        assert d.fun == h.fun, (s, op, d.fun, h.fun)
+
+
+def test_device_nm_scalar_fit_finds_planted_parameter(T):
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 3, 40, 64, generator=g)
+    p = torch.tensor([[0.23]])
+    tgt = O.execute(0, img, p)
+    param, ok = planner.get_param(img.cuda(), tgt.cuda(), None, 0, ex, None, 'L1', 'Nelder-Mead')
+    assert ok and param.dtype == torch.float64 and tuple(param.shape) == (1, 1)
+    assert abs(param.item() - 0.23) < 2e-3
+
+
+def test_beam_search_batch_equals_single_pairs(T):
+    """beam_search_batch over M pairs == beam_search on each pair alone (the lock-step only shares launches)."""
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    img, tgt = _pairs(3, 32, 32, 9)
+    batch = planner.beam_search_batch(img, tgt, ex, 2, [0, 1, 6], O.ACTION_NAMES, 2, 1e-3)
+    for m in range(3):
+        actions, Is = planner.beam_search(img[m:m + 1], tgt[m:m + 1], None, ex, None, 2, [0, 1, 6], O.ACTION_NAMES, 2, 1e-3,
+                                          'L1', 'Nelder-Mead')
+        b_actions, b_Is = batch[m]
+        assert [[a[0] for a in seq] for seq in actions] == [[a[0] for a in seq] for seq in b_actions]
+        for seq, bseq in zip(actions, b_actions):
+            for a, b in zip(seq, bseq):
+                assert a[1] == b[1] and a[2] == b[2]
+        for seq, bseq in zip(Is, b_Is):
+            for x, y in zip(seq, bseq):
+                assert not x.is_cuda and torch.equal(x, y)
