@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
     if (arrive_is_last(a.counters + s, (unsigned)per_state, &last_flag)) {
         for (int ci = cbeg + warp; ci < cend; ci += SCORE_NW) {
             float v = 0.0f;
-            for (int t = lane; t < a.ntiles; t += 32) v += __ldcg(a.part + (size_t)ci * a.ntiles + t);
+            for (int t = lane; t < a.ntiles; t += 32) {
+                float *pp = a.part + (size_t)ci * a.ntiles + t;
+                v += __ldcg(pp);
+                *pp = 0.0f;             // the workspace is left zeroed (it is shared with the chain entry points' counters)
+            }
             v = warp_sum(v);
             if (lane == 0) a.l1_sum[ci] = v;
         }

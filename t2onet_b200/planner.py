@@ -307,7 +307,8 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                 seq, img = all_candidates[idx], I_tmp_list[idx]
                 if img._base is not None:
                     img = img.clone()
-                    seq = [seq[0][:-1] + [seq[0][-1][:-1] + (img,)], seq[1]]
+                    if seq[0] and seq[0][-1][-1] is I_tmp_list[idx]:
+                        seq = [seq[0][:-1] + [seq[0][-1][:-1] + (img,)], seq[1]]
                 S['sequences'].append(seq)
                 S['I_buff'].append(img)
             if no_update_flag or finish_flag:

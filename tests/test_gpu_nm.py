@@ -72,3 +72,20 @@ def test_beam_search_batch_equals_single_pairs(T):
         for seq, bseq in zip(Is, b_Is):
             for x, y in zip(seq, bseq):
                 assert not x.is_cuda and torch.equal(x, y)
+
+
+def test_entry_points_leave_the_shared_workspace_zeroed(T):
+    """include/t2o.h: the workspace is zero again after every call -- the scorer's per-tile partials included (the
+    chain entry points keep their arrival counters where a scorer launch with fewer states keeps partials)."""
+    from t2onet_b200 import _lib, functional as TF
+    states, targets = _pairs(2, 32, 48, 3)
+    prm = torch.rand(20, 24) + 0.5
+    TF.score_candidates(states, targets, [0] * 10 + [1] * 10, [5] * 20, prm)
+    big, big_t = _pairs(40, 32, 48, 4)
+    out, l1 = TF._rows_forward_raw(*TF._prep_row_ops([[0]] * 40, 40, big.device), big, None, 0,
+                                   torch.full((40, 24), 0.1, device=big.device), big_t, True, True, 8)
+    torch.cuda.synchronize()
+    ws = _lib.workspace(states.device, 1)
+    assert not bool(ws.any())
+    ref = (out - big_t).abs().flatten(1).sum(1)
+    assert torch.allclose(l1, ref, rtol=1e-5)
