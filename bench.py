@@ -489,6 +489,34 @@ def extras(TF, dev, wl):
                                  'Gpixel_candidates_per_s': C * H * W / t_sc / 1e6}
     except Exception as exc:
         ex['planner_scoring'] = {'error': repr(exc)}
+    # ---- the planner end to end through its public API: beam_search_batch (= the reference's beam_search on every pair,
+    # utils/beam_search.py:196-264) over 64 synthetic pairs of 3x128x128, beam 8, the six global operators, max 6 steps,
+    # Nelder-Mead fits resident on the device (BASELINE config 3 shape; 1000 pairs = 16 such batches)
+    try:
+        import time
+        import t2onet_b200 as T
+        from t2onet_b200 import planner
+        names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+        exe = T.Executor(T.default_options()).to(dev)
+        M = 64
+        img, tgt, _ = make_batch(M, 128, 128, 3010, dev)
+        best = None
+        for rep in range(3):                                # the first repetition warms the kernels up
+            cnt = [0]
+            torch.cuda.synchronize()
+            t0 = time.time()
+            res = planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2, counter=cnt)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            if rep > 0 and (best is None or dt < best[0]):
+                best = (dt, cnt[0])
+        ex['planner_e2e'] = {'workload': '%d pairs of 3x128x128, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, Nelder-Mead' % M,
+                             'seconds': best[0], 'pairs_per_s': M / best[0], 'candidates': best[1],
+                             'candidates_per_s': best[1] / best[0],
+                             'mean_steps': sum(len(r[0][0]) for r in res) / M,
+                             'how': 'wall clock around beam_search_batch (host bookkeeping and result copies included), best of 2'}
+    except Exception as exc:
+        ex['planner_e2e'] = {'error': repr(exc)}
     return ex
 
 

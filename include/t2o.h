@@ -15,8 +15,10 @@
  *         params[b * param_stride + param_off[k] + i],  i < t2o_num_params(op_ids[k])
  *     with the reference's layouts (tone: (L,), color: (3, L) index c*L+i, models/operators.py:578,608)
  *   - all work is enqueued on `stream`; nothing synchronises the device
- *   - `workspace` is caller-owned device scratch of >= t2o_workspace_bytes(...) bytes that must
- *     be ZERO before its first use (the library leaves it zeroed again after every call)
+ *   - `workspace` is caller-owned device scratch of >= t2o_workspace_bytes(...) bytes whose first 256 KiB
+ *     (the per-image / per-state arrival counters) must be ZERO before its first use; every call leaves
+ *     them zeroed again, whatever the batch size, so one workspace can serve all entry points in turn
+ *     (never two launches that overlap in time); the bytes behind the counters are plain scratch
  *   - every function returns a t2o_status (0 = ok) and never throws; inputs are never modified
  */
 #ifndef T2O_H_
@@ -147,7 +149,8 @@ int t2o_rows_backward(int K, const int32_t *row_ops, const int32_t *row_ops_host
                       int B, int H, int W, int curve_steps,
                       void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 
-/* Per-image sum |a - b| over n floats per image: get_dist(x1, x2, 'L1') * numel, utils/beam_search.py:170-173. */
+/* Per-image sum |a - b| over n floats per image: get_dist(x1, x2, 'L1') * numel, utils/beam_search.py:170-173.
+ * workspace: >= 256 KiB + B * (n_per_image / 4096 + 2) * 4 bytes. */
 int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_per_image,
                void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 

@@ -19,7 +19,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 size_t max_tiles(int H, int W) { return ((size_t)W / 28 + 2) * ((size_t)H / 16 + 2); }
 size_t chain_workspace_bytes(int B, int H, int W, int pstride) {
     const size_t mt = max_tiles(H, W);
-    return align_up((size_t)B * 4, 256) + align_up((size_t)B * mt * 4, 256) + align_up((size_t)B * mt * (size_t)(pstride > 0 ? pstride : 1) * 4, 256);
+    return COUNTER_REGION + align_up((size_t)B * mt * 4, 256) + align_up((size_t)B * mt * (size_t)(pstride > 0 ? pstride : 1) * 4, 256);
 }
 struct Workspace {
     unsigned int *counters;
@@ -29,7 +29,7 @@ Workspace carve_workspace(void *ws, int B, int H, int W) {
     const size_t mt = max_tiles(H, W);
     char *p = (char *)ws;
     Workspace w;
-    w.counters = (unsigned int *)p; p += align_up((size_t)B * 4, 256);
+    w.counters = (unsigned int *)p; p += COUNTER_REGION;             // B <= 65535 counters
     w.part_l1 = (float *)p; p += align_up((size_t)B * mt * 4, 256);
     w.part_gp = (float *)p;
     return w;
@@ -244,11 +244,11 @@ int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long l
     if (tile < 4096) tile = 4096;
     if (tile > 65536) tile = 65536;
     a.ntiles = (int)((n + tile - 1) / tile);
-    const size_t need = align_up((size_t)B * 4, 256) + (size_t)B * a.ntiles * 4;
+    const size_t need = COUNTER_REGION + (size_t)B * a.ntiles * 4;
     if (!ws || ws_bytes < need) return T2O_ERR_WORKSPACE;
     a.a = pa; a.b = pb; a.l1_sum = l1_sum; a.n = n; a.tile_elems = tile;
     a.counters = (unsigned int *)ws;
-    a.part = (float *)((char *)ws + align_up((size_t)B * 4, 256));
+    a.part = (float *)((char *)ws + COUNTER_REGION);
     dim3 grid(a.ntiles, B);
     if (vec == 4) l1_sum_kernel<4><<<grid, NT, 0, stream>>>(a);
     else if (vec == 2) l1_sum_kernel<2><<<grid, NT, 0, stream>>>(a);

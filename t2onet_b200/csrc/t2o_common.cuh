@@ -11,6 +11,10 @@ constexpr int NT = 256;           // threads per CTA of the chain kernels
 constexpr int NUM_SMS = 148;      // B200
 constexpr int MIN_TILE_PX = 1024; // smallest tile any launcher picks (bounds the workspace)
 constexpr int MAX_PSTRIDE = 256;  // floats per parameter row
+// Every entry point keeps its arrival counters (one per image / state, left at 0 again by the last CTA) in the first
+// COUNTER_REGION bytes of the workspace and its partial sums behind them: whatever batch sizes share one workspace,
+// one call's partials never land on another call's counters.
+constexpr size_t COUNTER_REGION = 65536 * sizeof(unsigned int);
 
 // One fused chain, uniform over the batch.
 struct ChainDesc {

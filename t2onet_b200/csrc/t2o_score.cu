@@ -189,11 +189,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
     if (arrive_is_last(a.counters + s, (unsigned)per_state, &last_flag)) {
         for (int ci = cbeg + warp; ci < cend; ci += SCORE_NW) {
             float v = 0.0f;
-            for (int t = lane; t < a.ntiles; t += 32) {
-                float *pp = a.part + (size_t)ci * a.ntiles + t;
-                v += __ldcg(pp);
-                *pp = 0.0f;             // the workspace is left zeroed (it is shared with the chain entry points' counters)
-            }
+            for (int t = lane; t < a.ntiles; t += 32) v += __ldcg(a.part + (size_t)ci * a.ntiles + t);
             v = warp_sum(v);
             if (lane == 0) a.l1_sum[ci] = v;
         }
@@ -237,7 +233,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline size_t score_max_tiles(int H, int W) { return ((size_t)W / 32 + 2) * ((size_t)H / 8 + 2); }
 
 size_t score_workspace_bytes(int S, int C, int H, int W) {
-    return align_up((size_t)(S > 0 ? S : 1) * 4, 256) + (size_t)(C > 0 ? C : 1) * score_max_tiles(H, W) * 4;
+    return COUNTER_REGION + (size_t)(C > 0 ? C : 1) * score_max_tiles(H, W) * 4;
 }
 
 int score_candidates(const float *states, int S, const float *targets, int T, const int *state_target,
@@ -245,6 +241,7 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
     if (!states || !targets || !cand_begin || !cand_op || !cand_param || !l1_sum) return T2O_ERR_INVALID_ARG;
     if (S < 1 || T < 1 || C < 0 || H < 1 || W < 1) return T2O_ERR_INVALID_ARG;
+    if ((size_t)S * sizeof(unsigned int) > COUNTER_REGION) return T2O_ERR_UNSUPPORTED;
     if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
     if (C == 0) return T2O_OK;
     if (!ws || ws_bytes < score_workspace_bytes(S, C, H, W)) return T2O_ERR_WORKSPACE;
@@ -252,7 +249,7 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
     a.states = states; a.targets = targets; a.cand_param = cand_param; a.state_target = state_target;
     a.cand_begin = cand_begin; a.cand_op = cand_op; a.l1_sum = l1_sum;
     a.counters = (unsigned int *)ws;
-    a.part = (float *)((char *)ws + align_up((size_t)S * 4, 256));
+    a.part = (float *)((char *)ws + COUNTER_REGION);
     a.S = S; a.T = T; a.C = C; a.H = H; a.W = W; a.L = L;
     const bool aligned = ((uintptr_t)states % 16 == 0) && ((uintptr_t)targets % 16 == 0);
     const int vec = (W % 4 == 0) ? 4 : 1;

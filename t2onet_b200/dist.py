@@ -79,3 +79,19 @@ def plan_dataset(pairs, executor, plan_fn, group=None):
         I_0, I_gt = pairs[i]
         local[i] = plan_fn(I_0, I_gt, executor)
     return gather_records(local, len(pairs), group)
+
+
+def plan_dataset_batched(pairs, executor, batch_fn, batch=64, group=None):
+    """Image-sharded planning in lock-step batches: rank r takes items r, r+R, ... and hands them to
+    batch_fn(indices, [pairs[i] for i in indices], executor) -> list of JSON-able records `batch` at a time
+    (e.g. stacking the pairs for planner.beam_search_batch, whose device-resident fits want many pairs in flight).
+    No communication during the search; every rank returns the full, ordered list."""
+    rank, world = rank_world(group)
+    mine = list(shard_indices(len(pairs), rank, world))
+    local = {}
+    for c0 in range(0, len(mine), batch):
+        idx = mine[c0:c0 + batch]
+        recs = batch_fn(idx, [pairs[i] for i in idx], executor)
+        assert len(recs) == len(idx)
+        local.update(zip(idx, recs))
+    return gather_records(local, len(pairs), group)

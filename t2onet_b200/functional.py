@@ -420,7 +420,7 @@ def l1_sum(a, b):
     n = a.numel() // B
     lib = _lib.lib()
     out = torch.empty(B, device=a.device, dtype=torch.float32)
-    ws = _lib.workspace(a.device, 1 << 20)
+    ws = _lib.workspace(a.device, (1 << 18) + B * (n // 4096 + 2) * 4)     # counters + one partial per >= 4096-float tile
     st = lib.t2o_l1_sum(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), B, n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device))
     _lib.check(st)
     return out

@@ -74,18 +74,25 @@ def test_beam_search_batch_equals_single_pairs(T):
                 assert not x.is_cuda and torch.equal(x, y)
 
 
-def test_entry_points_leave_the_shared_workspace_zeroed(T):
-    """include/t2o.h: the workspace is zero again after every call -- the scorer's per-tile partials included (the
-    chain entry points keep their arrival counters where a scorer launch with fewer states keeps partials)."""
+def test_entry_points_share_one_workspace_across_batch_sizes(T):
+    """include/t2o.h: one workspace serves all entry points in turn, whatever the batch sizes -- the arrival counters
+    live in a fixed region that no call's partial sums can reach (a scorer launch with few states followed by a
+    chain launch over many rows, and the other way round, used to overlap them)."""
     from t2onet_b200 import _lib, functional as TF
     states, targets = _pairs(2, 32, 48, 3)
     prm = torch.rand(20, 24) + 0.5
-    TF.score_candidates(states, targets, [0] * 10 + [1] * 10, [5] * 20, prm)
+    sc0 = TF.score_candidates(states, targets, [0] * 10 + [1] * 10, [5] * 20, prm).clone()
     big, big_t = _pairs(40, 32, 48, 4)
-    out, l1 = TF._rows_forward_raw(*TF._prep_row_ops([[0]] * 40, 40, big.device), big, None, 0,
-                                   torch.full((40, 24), 0.1, device=big.device), big_t, True, True, 8)
+    for _ in range(2):
+        out, l1 = TF._rows_forward_raw(*TF._prep_row_ops([[0]] * 40, 40, big.device), big, None, 0,
+                                       torch.full((40, 24), 0.1, device=big.device), big_t, True, True, 8)
+        ref = (out - big_t).abs().flatten(1).sum(1)
+        assert torch.allclose(l1, ref, rtol=1e-5)
+        many, many_t = _pairs(30, 32, 48, 6)
+        sc = TF.score_candidates(many, many_t, list(range(30)), [0] * 30, torch.full((30, 24), 0.1))
+        ref = (TF.execute_rows(many, [[0]] * 30, torch.full((30, 24), 0.1, device=many.device)) - many_t).abs().flatten(1).sum(1)
+        assert torch.allclose(sc, ref, rtol=1e-5)
+        assert torch.equal(TF.score_candidates(states, targets, [0] * 10 + [1] * 10, [5] * 20, prm), sc0)
     torch.cuda.synchronize()
     ws = _lib.workspace(states.device, 1)
-    assert not bool(ws.any())
-    ref = (out - big_t).abs().flatten(1).sum(1)
-    assert torch.allclose(l1, ref, rtol=1e-5)
+    assert not bool(ws[:65536 * 4].any())

@@ -234,6 +234,16 @@ def _dist_worker(rank, world, port, q):
         recs = D.plan_dataset(pairs, None, lambda a, b, ex: {'item': a, 'val': a + b, 'rank': dist.get_rank()})
         assert [r['item'] for r in recs] == list(range(7))
         assert [r['rank'] for r in recs] == [i % world for i in range(7)]
+        # the same in lock-step batches (planner.beam_search_batch wants many pairs in flight per rank)
+        calls = []
+
+        def batch_fn(idx, items, ex):
+            calls.append(list(idx))
+            return [{'item': a, 'val': a + b, 'rank': dist.get_rank()} for a, b in items]
+        recs = D.plan_dataset_batched(pairs, None, batch_fn, batch=3)
+        assert [r['item'] for r in recs] == list(range(7)) and [r['val'] for r in recs] == [11 * i for i in range(7)]
+        assert [r['rank'] for r in recs] == [i % world for i in range(7)]
+        assert all(len(c) <= 3 for c in calls) and sorted(sum(calls, [])) == list(range(rank, 7, world))
         # candidate-sharded selection: packed-key all_reduce(MIN)
         g = torch.Generator().manual_seed(5)
         scores = torch.rand(4, 10, generator=g)                 # the same global table on both ranks
