@@ -339,7 +339,7 @@ def run_ours(args, wl):
                      'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram read + write)', 'traffic_source': traffic_src,
                      'algorithmic_bytes': BYTES_PER_PX_FUSED * px_step, 'peak_source': peak_src,
                      'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0,
-                     'note': 'FP32-issue-bound in practice (DESIGN.md section 4): ~730 thread-instructions per pixel'},
+                     'note': 'FP32-issue-bound in practice (DESIGN.md section 4): ~610 thread-instructions per pixel, issue-active 71 % (profiles/r01f_step_c4_summary.txt)'},
     }
     if world == 1 and not args.no_extras:
         line['cpu_baseline'] = cpu_baseline(wl)
