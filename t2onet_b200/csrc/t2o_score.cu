@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
                                                          const __grid_constant__ ScoreArgs a) {
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     __shared__ __align__(16) float wtab[SCORE_NW][TAB];
+    __shared__ float wsum[SCORE_NW][SCORE_NW];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int last_flag;
 
@@ -128,16 +129,11 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
 
     const int TWg = TW / VEC;
     const int ngroups = TH * TWg;
-    float *tab = wtab[warp];
-    for (int ci = cbeg + split * SCORE_NW + warp; ci < cend; ci += a.nsplit * SCORE_NW) {
-        const int op = a.cand_op[ci];
-        if (op == OP_SKIP) continue;
-        __syncwarp();
-        if (lane == 0) build_table(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
-        __syncwarp();
+    // one lane's share of a candidate's |op(state) - target| over the tile: groups first, first + stride, ...
+    auto tile_sum = [&](int op, const float *tab, int first, int stride) -> float {
         float sum = 0.0f;
         const float p = tab[0];
-        for (int gi = lane; gi < ngroups; gi += 32) {
+        for (int gi = first; gi < ngroups; gi += stride) {
             const int ly = gi / TWg, lx = (gi - ly * TWg) * VEC;
             if (y0 + ly >= H || x0 + lx >= W) continue;       // ragged edge (W % VEC == 0)
             float x[3][VEC], t[3][VEC];
@@ -181,8 +177,43 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
                 for (int v = 0; v < VEC; ++v) sum += fabsf(x[c][v] - t[c][v]);
             }
         }
-        sum = warp_sum(sum);
-        if (lane == 0) a.part[(size_t)ci * a.ntiles + tile] = sum;
+        return sum;
+    };
+
+    if (a.nsplit == 1 && cend - cbeg <= SCORE_NW) {
+        // Few candidates (the Nelder-Mead rounds: at most one per operator and state): warp w builds the table of
+        // candidate w, then ALL warps share every candidate's tile (warp w takes groups w*32 + lane, + 256, ...) and
+        // the per-warp sums are added in warp order -- instead of one warp per candidate and the others idle.
+        const int ncand = cend - cbeg;
+        if (warp < ncand && lane == 0) {
+            const int op = a.cand_op[cbeg + warp];
+            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
+        }
+        __syncthreads();
+        for (int c = 0; c < ncand; ++c) {
+            const int op = a.cand_op[cbeg + c];
+            if (op == OP_SKIP) continue;
+            const float sum = warp_sum(tile_sum(op, wtab[c], warp * 32 + lane, SCORE_NT));
+            if (lane == 0) wsum[c][warp] = sum;
+        }
+        __syncthreads();
+        if (tid < ncand && a.cand_op[cbeg + tid] != OP_SKIP) {
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SCORE_NW; ++w) v += wsum[tid][w];
+            a.part[(size_t)(cbeg + tid) * a.ntiles + tile] = v;
+        }
+    } else {
+        float *tab = wtab[warp];
+        for (int ci = cbeg + split * SCORE_NW + warp; ci < cend; ci += a.nsplit * SCORE_NW) {
+            const int op = a.cand_op[ci];
+            if (op == OP_SKIP) continue;
+            __syncwarp();
+            if (lane == 0) build_table(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
+            __syncwarp();
+            const float sum = warp_sum(tile_sum(op, tab, lane, 32));
+            if (lane == 0) a.part[(size_t)ci * a.ntiles + tile] = sum;
+        }
     }
 
     // last CTA of this state sums the per-tile partials of all its candidates (fixed order)
