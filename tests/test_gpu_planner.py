@@ -152,3 +152,40 @@ def test_executor_api_and_fc_head_gradients(T):
         h = torch.nn.functional.leaky_relu(f @ w['fc1.weight'].t() + w['fc1.bias'])
         po = O.regress(op, h @ w['fc2.weight'].t() + w['fc2.bias'], opt)
         assert max_abs(out.detach().cpu(), O.execute(op, img, po)) <= TOL_PIX
+
+
+def test_beam_search_batch_matches_reference_on_recorded_pairs(T, golden_dir):
+    """The reference's own driver settings (preprocess/gen_greedy_seqs_FiveK.py:37-43: beam 3, six operators, err 1e-2,
+    max_step 6) on the pairs recorded by oracle/make_planner_golden.py from the unmodified reference: the chosen
+    operator sequences must be identical unless the competing candidates were tied within the fit tolerance.
+    The 8- and 24-parameter curve fits stop unconverged at maxfev = 200 N, so their final distance depends on the
+    simplex path, i.e. on the L1's low bits; where tone and colour candidates end within ~5e-4 of each other the beam
+    order can flip (5 of the 16 recorded pairs, |final distance - reference's| <= 6e-4 on each).  A different top
+    sequence is therefore accepted only if its final distance is within 1e-3 of the reference's, and on a minority."""
+    path = os.path.join(golden_dir, 'planner_pairs.json')
+    if not os.path.exists(path):
+        pytest.skip('planner_pairs golden not recorded')
+    rec = json.load(open(path))
+    d = np.load(os.path.join(golden_dir, 'planner_pairs.npz'))
+    I0, Igt = torch.from_numpy(d['I0']).cuda(), torch.from_numpy(d['Igt']).cuda()
+    st = rec['settings']
+    ex = T.Executor(T.default_options()).cuda()
+    res = T.planner.beam_search_batch(I0, Igt, ex, st['beam'], st['operations'], O.ACTION_NAMES, st['max_step'], st['err'])
+    exact = 0
+    for m, (pair, (actions, Is)) in enumerate(zip(rec['pairs'], res)):
+        ref_top, top = pair['actions'][0], actions[0]
+        ref_ops, ops = [a[0] for a in ref_top], [a[0] for a in top]
+        ref_dist = ref_top[-1][2] if ref_top else pair['init_dist']
+        dist = top[-1][2] if top else pair['init_dist']
+        assert abs(dist - ref_dist) <= 1e-3, (m, ops, ref_ops, dist, ref_dist)
+        if ops == ref_ops:
+            exact += 1
+            for a, r in zip(top, ref_top):
+                assert abs(a[2] - r[2]) <= 2e-3, (m, a[0], a[2], r[2])
+        # replaying the returned sequence reproduces the returned images and distances
+        img = I0[m:m + 1]
+        for a, I_k in zip(top, Is[0]):
+            img = T.planner.execute(img, O.ACTION_NAMES.index(a[0]), torch.tensor([a[1]], device='cuda'), ex)
+            assert max_abs(img.cpu(), I_k) <= TOL_PIX
+            assert abs(T.planner.get_dist(img, Igt[m:m + 1]).item() - a[2]) <= 1e-6
+    assert exact * 8 >= 5 * len(rec['pairs']), 'only %d of %d top sequences identical to the reference' % (exact, len(rec['pairs']))

@@ -93,3 +93,21 @@ def test_planner_beam_matches_reference(golden_dir):
                                1e-2, 'L1', 'Nelder-Mead')
     got = [[[a[0], a[1], a[2]] for a in seq] for seq in actions]
     assert got == tr['beam2']['actions']
+
+
+def test_oracle_planner_reproduces_recorded_pair_transcripts(golden_dir):
+    """oracle/planner.py (the CPU restatement of utils/beam_search.py) on the first recorded pairs of
+    oracle/make_planner_golden.py: same operator sequences, parameters and distances as the unmodified reference."""
+    path = os.path.join(golden_dir, 'planner_pairs.json')
+    rec = json.load(open(path))
+    d = np.load(os.path.join(golden_dir, 'planner_pairs.npz'))
+    st = rec['settings']
+    for m in (1, 4):                                    # the two cheapest pairs (seconds of CPU each)
+        I0, Igt = torch.from_numpy(d['I0'][m:m + 1]), torch.from_numpy(d['Igt'][m:m + 1])
+        actions, Is = P.beam_search(I0, Igt, None, O.OracleExecutor(), None, st['beam'], st['operations'], O.ACTION_NAMES,
+                                    st['max_step'], st['err'], 'L1', 'Nelder-Mead')
+        ref = rec['pairs'][m]['actions']
+        assert [[a[0] for a in seq] for seq in actions] == [[a[0] for a in seq] for seq in ref]
+        for seq, rseq in zip(actions, ref):
+            for a, r in zip(seq, rseq):
+                assert list(a[1]) == r[1] and a[2] == r[2]
