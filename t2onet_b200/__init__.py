@@ -6,6 +6,7 @@ Public surface (mirrors the reference's Python API):
     t2onet_b200.operators   Operator subclasses            (models/operators.py)
     t2onet_b200.executor    Executor                       (executors/executor.py)
     t2onet_b200.planner     beam_search, get_dist, ...     (utils/beam_search*.py)
+    t2onet_b200.plans       planner records on disk + reader (preprocess/gen_greedy_seqs_FiveK.py, datasets/FiveKdataset.py)
     t2onet_b200.functional  chain / chain_l1 / score_candidates over the C-ABI (include/t2o.h)
 """
 from . import functional  # noqa: F401
@@ -14,6 +15,7 @@ from .operators import (Operator, ExposureOperator, ContrastOperator, Brightness
                         SaturationOperator, WhiteOperator, ImprovedWhiteBalanceOperator, ToneOperator, ColorOperator,
                         InpaintOperator)
 from . import planner  # noqa: F401
+from . import plans  # noqa: F401
 from ._lib import T2OError, lib  # noqa: F401
 
 __version__ = '0.1.0'

@@ -189,3 +189,25 @@ def test_beam_search_batch_matches_reference_on_recorded_pairs(T, golden_dir):
             assert max_abs(img.cpu(), I_k) <= TOL_PIX
             assert abs(T.planner.get_dist(img, Igt[m:m + 1]).item() - a[2]) <= 1e-6
     assert exact * 8 >= 5 * len(rec['pairs']), 'only %d of %d top sequences identical to the reference' % (exact, len(rec['pairs']))
+
+
+def test_plan_record_roundtrip_and_lossless_replay(T, pair, tmp_path):
+    """plans.write_plan / read_plan around a planner result, and plans.replay: the intermediate images re-executed from
+    the stored sequence equal the planner's own (the reference re-reads them JPEG-quantised, FiveKdataset.py:114-118)."""
+    from t2onet_b200 import plans
+    I0, Igt, _ = pair
+    ex = T.Executor(T.default_options()).cuda()
+    actions, Is = T.planner.beam_search(I0.cuda(), Igt.cuda(), None, ex, None, 2, GLOBAL_OPS, O.ACTION_NAMES, 3, 1e-2,
+                                        'L1', 'Nelder-Mead')
+    init = T.planner.get_dist(I0.cuda(), Igt.cuda(), 'L1').item()
+    plans.write_plan(str(tmp_path), 'train', 0, 'make it brighter', I0, Igt, actions, Is, init)
+    for f in ('00000.json', 'input.jpg', 'target.jpg', 'edit0.jpg'):
+        assert os.path.exists(os.path.join(str(tmp_path), 'train0', f)), f
+    op_seq, params, trunc, seq = plans.read_plan(str(tmp_path), 'train', 0)
+    assert op_seq[0] == 1 and op_seq[trunc + 1] == 2 and 1 <= trunc <= len(actions[0])
+    assert [int(v) - 3 for v in op_seq[1:trunc + 1]] == [O.ACTION_NAMES.index(a[0]) for a in actions[0][:trunc]]
+    outs = plans.replay(I0.cuda(), actions[0], ex)
+    for o, ref in zip(outs, Is[0]):
+        assert max_abs(o.cpu(), ref) <= TOL_PIX
+    jpg = plans.load_train_img(os.path.join(str(tmp_path), 'train0', 'edit0.jpg'), I0.shape[-1])
+    assert max_abs(jpg, Is[0][0][0]) > max_abs(outs[0].cpu(), Is[0][0])          # what the lossless replay saves

@@ -284,3 +284,37 @@ def test_score_key_packing_orders_like_floats():
     sc, ids = D.unpack_score_keys(D.pack_score_keys(s, torch.arange(6)))
     assert torch.equal(sc, s) and torch.equal(ids, torch.arange(6))
     assert D.shard_indices(7, 1, 3) == [1, 4] and D.shard_indices(2, 3, 4) == []
+
+
+# ------------------------------------------------------------------ planner records on disk (t2onet_b200/plans.py)
+def test_plan_records_encode_like_the_reference_reader(tmp_path):
+    """encode_plan / read_plan == FiveKAct.get_act of the unmodified reference (datasets/FiveKdataset.py:86-113) on the
+    records of tests/golden/plans.json (oracle/make_plans_golden.py): operator ids, truncation, parameter normalisation."""
+    import json
+    from t2onet_b200 import plans
+    cases = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'plans.json')))
+    assert len({c['trunc_len'] for c in cases}) >= 3
+    for i, c in enumerate(cases):
+        op_seq, params, trunc, seq = plans.encode_plan(json.loads(json.dumps(c['record'])))
+        assert [int(v) for v in op_seq] == c['op_seq'] and trunc == c['trunc_len'] and len(seq) == trunc
+        assert np.array_equal(params, np.array(c['params'], dtype=np.float32))
+        # the writer's layout is the reader's: <save_dir>/<phase><i>/<i:05d>.json
+        rec = c['record']
+        plans.write_plan(str(tmp_path), 'train', i, rec['request'], None, None, rec['operation sequence'], [],
+                         rec['init distance'], write_images=False)
+        op_seq2, params2, trunc2, _ = plans.read_plan(str(tmp_path), 'train', i)
+        assert np.array_equal(op_seq2, op_seq) and np.array_equal(params2, params) and trunc2 == trunc
+        with open(os.path.join(str(tmp_path), 'train%d' % i, '%05d.json' % i)) as f:
+            assert json.load(f) == rec
+
+
+def test_analyze_traj_rule():
+    from t2onet_b200 import plans
+    assert plans.analyze_traj([1.0, 0.5, 0.2, 0.199, 0.1]) == 2       # third step improves by < 1 % of the initial distance
+    assert plans.analyze_traj([1.0, 0.999]) == 1                       # never 0
+    assert plans.analyze_traj([1.0, 0.5, 0.2]) == 2                    # every step counts
+    img = torch.rand(1, 3, 5, 7)
+    bgr = plans.tensor2img(img)
+    assert bgr.shape == (5, 7, 3) and bgr.dtype == np.uint8
+    assert np.array_equal(bgr[:, :, ::-1], (img[0].permute(1, 2, 0) * 255).numpy().astype(np.uint8))
+    assert torch.equal(plans.img2tensor(bgr)[0], torch.from_numpy(bgr[:, :, ::-1].transpose(2, 0, 1).copy()) / 255)
