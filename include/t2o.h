@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define T2O_VERSION 102          /* major*100 + minor */
+#define T2O_VERSION 103          /* major*100 + minor */
 #define T2O_MAX_CHAIN 8          /* operators fused in one launch */
 #define T2O_MAX_CURVE_STEPS 8    /* cfg.curve_steps (options/fiveK_base_options.py:50) */
 #define T2O_MAX_OP_PARAMS 24     /* color: 3 * curve_steps */
@@ -41,7 +41,7 @@ extern "C" {
                                     (models/operators.py:128), without the mask blend and clamp */
 
 /* Operator ids = reference Executor indices (executors/executor.py:30) + extension ids for the
- * operator classes that exist without an Executor slot (models/operators.py:186,527). */
+ * operator classes that exist without an Executor slot (models/operators.py:186,527 and :298,373,414). */
 enum t2o_op {
     T2O_OP_SKIP = -2,         /* t2o_score_candidates only: the candidate is not evaluated (a finished Nelder-Mead fit) */
     T2O_OP_IDENTITY = -1,     /* executors/executor.py:44-46 (op_ind < 0): passthrough, no clamp */
@@ -54,7 +54,11 @@ enum t2o_op {
     T2O_OP_SHARPNESS = 6,     /* models/operators.py:351-358 */
     T2O_OP_WHITE = 7,         /* models/operators.py:510-512 */
     T2O_OP_EXPOSURE = 8,      /* models/operators.py:209-210 */
-    T2O_OP_WHITEBALANCE = 9   /* models/operators.py:548-549 */
+    T2O_OP_WHITEBALANCE = 9,  /* models/operators.py:548-549 */
+    T2O_OP_BNW = 10,          /* models/operators.py:314-316   lerp(img, luminance, p) */
+    T2O_OP_BLUR = 11,         /* models/operators.py:397-404   lerp(img, 3x3 Gaussian (sigma 2, zero padding) * img, p): a stencil
+                                 operator like sharpness -- a launch holds at most one of the two */
+    T2O_OP_HUE = 12           /* models/operators.py:432-438   hsv_to_rgb(p, s, v): every pixel's hue replaced by p (radians) */
 };
 
 enum t2o_status {

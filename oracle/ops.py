@@ -23,6 +23,8 @@ from . import hsv as _hsv
 OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_INPAINT, OP_TONE, OP_SHARPNESS, OP_WHITE = range(8)
 # not registered in the Executor, but named by the north star (models/operators.py:186,527)
 OP_EXPOSURE, OP_WHITEBALANCE = 8, 9
+# further classes without an Executor slot (models/operators.py:298, 373, 414)
+OP_BNW, OP_BLUR, OP_HUE = 10, 11, 12
 OP_IDENTITY = -1  # executors/executor.py:44-46
 
 # planner / dataset action names (preprocess/gen_greedy_seqs_FiveK.py:40)
@@ -45,7 +47,8 @@ def num_params(op_id, cfg=None):
     """models/operators.py: num_op_param of each class (:190,:228,:263,:336,:458,:498,:532,:563,:599,:629)."""
     L = 8 if cfg is None else cfg.curve_steps
     return {OP_BRIGHTNESS: 1, OP_CONTRAST: 1, OP_SATURATION: 1, OP_COLOR: 3 * L, OP_INPAINT: 1,
-            OP_TONE: L, OP_SHARPNESS: 1, OP_WHITE: 1, OP_EXPOSURE: 1, OP_WHITEBALANCE: 3}[op_id]
+            OP_TONE: L, OP_SHARPNESS: 1, OP_WHITE: 1, OP_EXPOSURE: 1, OP_WHITEBALANCE: 3,
+            OP_BNW: 1, OP_BLUR: 1, OP_HUE: 1}[op_id]
 
 
 # ---------------------------------------------------------------- pixel helpers
@@ -148,7 +151,41 @@ def process_color(img, param, cfg):
     return _curve(img, param.view(-1, 3, L, 1, 1), L, True)
 
 
+def process_bnw(img, param, cfg):
+    """models/operators.py:314-316"""
+    return lerp(img, rgb2lum(img), _bc(param))
+
+
+def _gaussian_kernel():
+    """models/operators.py:685-709 (kernel_size 3, sigma 2): the 3x3 weights of get_gaussian_kernel."""
+    x_coord = torch.arange(3)
+    x_grid = x_coord.repeat(3).view(3, 3)
+    xy_grid = torch.stack([x_grid, x_grid.t()], dim=-1).float()
+    mean, variance = (3 - 1) / 2., 2 ** 2.
+    k = (1. / (2. * np.pi * variance)) * torch.exp(-torch.sum((xy_grid - mean) ** 2., dim=-1) / (2 * variance))
+    return (k / torch.sum(k)).view(1, 1, 3, 3)
+
+
+_GAUSS = _gaussian_kernel()
+
+
+def process_blur(img, param, cfg):
+    """models/operators.py:397-404 (per-channel 3x3 Gaussian, zero padding 1, then lerp)."""
+    planes = [F.conv2d(c, _GAUSS, padding=1) for c in img.split([1, 1, 1], 1)]
+    return lerp(img, torch.cat(planes, 1), _bc(param))
+
+
+def process_hue(img, param, cfg):
+    """models/operators.py:432-438, with the parameter broadcast per batch row (the reference's
+    `param.expand_as(value)` of a (B, 1) parameter only works for B == 1)."""
+    hsv = _hsv.rgb_to_hsv(img)
+    hue, sat, value = hsv.split([1, 1, 1], 1)
+    out_hsv = torch.cat((_bc(param).expand_as(value), sat, value), 1)
+    return _hsv.hsv_to_rgb(out_hsv)
+
+
 _PROCESS = {
+    OP_BNW: process_bnw, OP_BLUR: process_blur, OP_HUE: process_hue,
     OP_BRIGHTNESS: process_brightness, OP_CONTRAST: process_contrast, OP_SATURATION: process_saturation,
     OP_COLOR: process_color, OP_TONE: process_tone, OP_SHARPNESS: process_sharpness, OP_WHITE: process_white,
     OP_EXPOSURE: process_exposure, OP_WHITEBALANCE: process_whitebalance,

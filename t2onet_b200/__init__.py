@@ -13,7 +13,7 @@ from . import functional  # noqa: F401
 from .executor import Executor  # noqa: F401
 from .operators import (Operator, ExposureOperator, ContrastOperator, BrightnessOperator, SharpnessOperator,  # noqa: F401
                         SaturationOperator, WhiteOperator, ImprovedWhiteBalanceOperator, ToneOperator, ColorOperator,
-                        InpaintOperator)
+                        InpaintOperator, BNWOperator, BlurOperator, HueOperator)
 from . import planner  # noqa: F401
 from . import plans  # noqa: F401
 from ._lib import T2OError, lib  # noqa: F401

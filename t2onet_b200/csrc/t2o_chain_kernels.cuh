@@ -36,6 +36,7 @@ __device__ __forceinline__ void apply_op_grp(int op, const float *tab, int L, fl
     switch (op) {
         T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
         T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+        T2O_CASE(OP_BNW) T2O_CASE(OP_HUE)
         default: break;
     }
 #undef T2O_CASE
@@ -76,7 +77,7 @@ T2O_HD int build_chain_desc(int n_ops, const int *op_ids, const int *param_off, 
         if (op < OP_IDENTITY || op >= OP_COUNT) return T2O_ERR_INVALID_ARG;
         const int po = param_off ? param_off[k] : k * slot;
         if (po < 0 || po + op_num_params(op, L) > pstride) return T2O_ERR_INVALID_ARG;
-        if (op == OP_SHARPNESS) {
+        if (op_is_stencil(op)) {                               // one stencil operator (sharpness or blur) per launch
             if (d.sharp >= 0) return T2O_ERR_UNSUPPORTED;
             d.sharp = k;
         }
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
     if (col_ok && rA >= 0 && rA < H && rA <= yb) prefetch_px(img_b, plane, (size_t)rA * W + coff);
     __syncthreads();
     const float p = tabs[sp][0];
+    const bool blur = SP ? false : ch.op[sp] == OP_BLUR;        // which stencil (the specialised chains hold a sharpness)
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
         const int rB = rA - 1;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float ctr[VEC], lap[VEC];
-                    stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr, lap);
+                    stencil_any<VEC>(blur, xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr, lap);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         const float yv = fmaf(p, lap[v], ctr[v]);

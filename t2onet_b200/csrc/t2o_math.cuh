@@ -36,7 +36,8 @@ namespace t2o {
 
 enum : int {
     OP_SKIP = -2, OP_IDENTITY = -1, OP_BRIGHTNESS = 0, OP_CONTRAST = 1, OP_SATURATION = 2, OP_COLOR = 3, OP_INPAINT = 4,
-    OP_TONE = 5, OP_SHARPNESS = 6, OP_WHITE = 7, OP_EXPOSURE = 8, OP_WHITEBALANCE = 9, OP_COUNT = 10
+    OP_TONE = 5, OP_SHARPNESS = 6, OP_WHITE = 7, OP_EXPOSURE = 8, OP_WHITEBALANCE = 9,
+    OP_BNW = 10, OP_BLUR = 11, OP_HUE = 12, OP_COUNT = 13
 };
 
 constexpr int MAX_CHAIN = 8;
@@ -61,6 +62,12 @@ T2O_HD int op_num_params(int op, int L) {
     }
 }
 T2O_HD bool op_is_curve(int op) { return op == OP_TONE || op == OP_COLOR; }
+// operators that read the pixel's 3x3 neighbourhood: y = x + p * S(x) with a symmetric stencil S
+T2O_HD bool op_is_stencil(int op) { return op == OP_SHARPNESS || op == OP_BLUR; }
+// BlurOperator (models/operators.py:373-411): lerp(img, G * img, p) = img + p * (G - delta) * img with G the 3x3 Gaussian of
+// get_gaussian_kernel(3, 2) (:685-717), zero padding 1; the fp32 weights below are the reference's own (centre, edge, corner)
+constexpr float BLUR_WC = 0.13080118596553802f, BLUR_WE = 0.11543164402246475f, BLUR_WK = 0.10186807066202164f;
+constexpr float TWO_PI_F = 6.283185307179586f;
 
 struct F2 { float a, b; };   // == float2 without needing vector_types.h on the host
 
@@ -188,6 +195,30 @@ T2O_HD void build_table(int op, const float *p, int L, float *tab) {
         case OP_BRIGHTNESS: case OP_SATURATION: tab[0] = p[0]; tab[1] = 1.0f + p[0]; break;
         case OP_CONTRAST: tab[0] = p[0]; tab[1] = 1.0f - p[0]; break;
         case OP_SHARPNESS: case OP_WHITE: tab[0] = p[0]; break;
+        case OP_BLUR: tab[0] = p[0]; break;
+        case OP_BNW: tab[0] = p[0]; tab[1] = 1.0f - p[0]; break;
+        case OP_HUE: {
+            // hsv_to_rgb with a constant hue (models/operators.py:432-438): the sector hi and the fraction f are
+            // per-image constants; channel c is v * (1 - a_c * s) with a_c in {0, 1, f, 1 - f} by sector
+            const float h6 = (p[0] / TWO_PI_F) * 6.0f;
+            float m6 = fmodf(h6, 6.0f);
+            if (m6 < 0.0f) m6 += 6.0f;                        // torch's % takes the sign of the divisor
+            float hi = fmodf(floorf(h6), 6.0f);
+            if (hi < 0.0f) hi += 6.0f;
+            const float f = m6 - hi, df = 6.0f / TWO_PI_F;
+            const int sec = (int)hi;
+            // rows of the gather table (v, q, p, p, t, v | t, v, v, q, p, p | p, p, t, v, v, q): v -> 0, p -> 1, q -> f, t -> 1 - f
+            // (two bits per sector, packed: no local array, so the kernels keep no stack frame for it)
+            const unsigned int code[3] = {856u, 1411u, 2101u};     // {0,2,1,1,3,0}, {3,0,0,2,1,1}, {1,1,3,0,0,2}
+            const int sc = sec < 0 ? 0 : (sec > 5 ? 5 : sec);
+            tab[0] = p[0];
+            for (int c = 0; c < 3; ++c) {
+                const int k = (int)((code[c] >> (2 * sc)) & 3u);
+                tab[1 + c] = k == 0 ? 0.0f : (k == 1 ? 1.0f : (k == 2 ? f : 1.0f - f));
+                tab[4 + c] = k == 2 ? df : (k == 3 ? -df : 0.0f);
+            }
+            break;
+        }
         case OP_EXPOSURE: tab[0] = p[0]; tab[1] = expf(p[0] * LN2_F); break;
         case OP_WHITEBALANCE: tab[0] = p[0]; tab[1] = p[1]; tab[2] = p[2]; break;
         case OP_TONE: build_curve(p, L, tab); break;
@@ -228,6 +259,19 @@ T2O_HD void contrast_y(const float *tab, float r, float g, float b, float &yr, f
     yr = r * F; yg = g * F; yb = b * F;
 }
 
+// BNWOperator.process (models/operators.py:314-316): lerp(img, rgb2lum(img), p)
+T2O_HD void bnw_y(const float *tab, float r, float g, float b, float &yr, float &yg, float &yb) {
+    const float pl = tab[0] * lum_rn(r, g, b);
+    yr = fmaf(tab[1], r, pl); yg = fmaf(tab[1], g, pl); yb = fmaf(tab[1], b, pl);
+}
+
+// HueOperator.process (models/operators.py:432-438): hsv_to_rgb(param, s, v) -- see build_table
+T2O_HD void hue_y(const float *tab, float r, float g, float b, float &yr, float &yg, float &yb) {
+    const float v = max3(r, g, b), mn = min3(r, g, b);
+    const float vs = v * ((v - mn) * rcp(v + HSV_EPS));
+    yr = fmaf(-tab[1], vs, v); yg = fmaf(-tab[2], vs, v); yb = fmaf(-tab[3], vs, v);
+}
+
 // bin of a clamped input xs in [0, 1]: j = floor(L xs) in 0..L, t = L xs, tf = float(j); returns the segment
 // record of bin j.  On the device the record's address comes straight from the bit pattern of 2^23 + floor(t)
 // (0x4B000000 + j): one shift-add, no mask (xs is clamped, so j <= L always).
@@ -255,6 +299,8 @@ T2O_HD float curve_y(const float *ct, int L, float x) {
 
 // y = x + p * laplace(x), zero padding handled by the caller (neighbours outside the image are 0)
 T2O_HD float laplace(float c, float up, float dn, float lf, float rt) { return fmaf(4.0f, c, -((up + dn) + (lf + rt))); }
+// y = x + p * blur_delta(x): (G - delta) * x of the 3x3 Gaussian; `edge` = up + dn + lf + rt, `corner` = the four diagonals
+T2O_HD float blur_delta(float c, float edge, float corner) { return fmaf(BLUR_WC - 1.0f, c, fmaf(BLUR_WE, edge, BLUR_WK * corner)); }
 
 // pointwise operators only (sharpness needs neighbours and is applied by the kernels)
 template <bool CL = false>
@@ -268,6 +314,8 @@ T2O_HD void op_y(int op, const float *tab, int L, float r, float g, float b, flo
         case OP_WHITE: yr = 1.0f; yg = 1.0f; yb = 1.0f; break;
         case OP_EXPOSURE: yr = r * tab[1]; yg = g * tab[1]; yb = b * tab[1]; break;
         case OP_WHITEBALANCE: yr = r * tab[0]; yg = g * tab[1]; yb = b * tab[2]; break;
+        case OP_BNW: bnw_y(tab, r, g, b, yr, yg, yb); break;
+        case OP_HUE: hue_y(tab, r, g, b, yr, yg, yb); break;
         default: yr = r; yg = g; yb = b; break;
     }
 }
@@ -302,9 +350,10 @@ T2O_HD void blend_bwd(float y, float x, float m, float g, float &gy, float &gd) 
 // The curve slots are kept as pairs so that the device accumulates two bins per packed FFMA2 (sm_100 fp32x2).
 struct GradAcc {
     F2 color[3][MAX_L / 2];
-    float bright, contrast, satur, expo, sharp;
+    float bright, contrast, satur, expo, sharp;     // `sharp` serves the launch's one stencil operator (sharpness or blur)
     F2 tone[MAX_L / 2];
     float wb[3];
+    float bnw, hue;
 };
 // c + a * b on both halves: one FFMA2 issue slot on the device
 T2O_HD F2 fma2(F2 a, F2 b, F2 c) {
@@ -317,11 +366,11 @@ T2O_HD F2 fma2(F2 a, F2 b, F2 c) {
 }
 constexpr int ACC_SLOTS = 48;     // slot layout used by the kernels' reduction (see acc_slot_* below)
 constexpr int ACC_COLOR = 0, ACC_BRIGHT = 27, ACC_CONTRAST = 28, ACC_SATUR = 29, ACC_EXPO = 30,
-              ACC_SHARP = 31, ACC_TONE = 32, ACC_WB = 41;
+              ACC_SHARP = 31, ACC_TONE = 32, ACC_WB = 41, ACC_BNW = 24, ACC_HUE = 25;
 T2O_HD void acc_zero(GradAcc &a) {
     for (int c = 0; c < 3; ++c) { for (int i = 0; i < MAX_L / 2; ++i) a.color[c][i] = F2{0.0f, 0.0f}; a.wb[c] = 0.0f; }
     for (int i = 0; i < MAX_L / 2; ++i) a.tone[i] = F2{0.0f, 0.0f};
-    a.bright = 0.0f; a.contrast = 0.0f; a.satur = 0.0f; a.expo = 0.0f; a.sharp = 0.0f;
+    a.bright = 0.0f; a.contrast = 0.0f; a.satur = 0.0f; a.expo = 0.0f; a.sharp = 0.0f; a.bnw = 0.0f; a.hue = 0.0f;
 }
 T2O_HD void acc_to_slots(const GradAcc &a, float *v) {     // v[ACC_SLOTS]
     for (int i = 0; i < ACC_SLOTS; ++i) v[i] = 0.0f;
@@ -331,7 +380,7 @@ T2O_HD void acc_to_slots(const GradAcc &a, float *v) {     // v[ACC_SLOTS]
     }
     for (int i = 0; i < MAX_L / 2; ++i) { v[ACC_TONE + 2 * i] = a.tone[i].a; v[ACC_TONE + 2 * i + 1] = a.tone[i].b; }
     v[ACC_BRIGHT] = a.bright; v[ACC_CONTRAST] = a.contrast; v[ACC_SATUR] = a.satur;
-    v[ACC_EXPO] = a.expo; v[ACC_SHARP] = a.sharp;
+    v[ACC_EXPO] = a.expo; v[ACC_SHARP] = a.sharp; v[ACC_BNW] = a.bnw; v[ACC_HUE] = a.hue;
 }
 
 // Each *_bwd takes the operator input x = (r,g,b), the mask, the upstream gradient
@@ -434,6 +483,48 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     gb = fmaf(gyb, F, gdb) + 0.06f * k;
 }
 
+template <bool HM>
+T2O_HD void bnw_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
+                    float &gr, float &gg, float &gb, float &acc, bool own) {
+    const float p = tab[0], q = tab[1];
+    const float lum = lum_rn(r, g, b);
+    const float pl = p * lum;
+    float gyr, gyg, gyb, gdr, gdg, gdb;
+    blend_bwd<HM>(fmaf(q, r, pl), r, mr, gr, gyr, gdr);
+    blend_bwd<HM>(fmaf(q, g, pl), g, mg, gg, gyg, gdg);
+    blend_bwd<HM>(fmaf(q, b, pl), b, mb, gb, gyb, gdb);
+    const float Sg = gyr + gyg + gyb;
+    if (own) acc += gyr * (lum - r) + gyg * (lum - g) + gyb * (lum - b);
+    const float k = p * Sg;
+    gr = fmaf(gyr, q, gdr) + 0.27f * k;
+    gg = fmaf(gyg, q, gdg) + 0.67f * k;
+    gb = fmaf(gyb, q, gdb) + 0.06f * k;
+}
+
+template <bool HM>
+T2O_HD void hue_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
+                    float &gr, float &gg, float &gb, float &acc, bool own) {
+    const float v = max3(r, g, b), mn = min3(r, g, b);
+    const float inv = rcp(v + HSV_EPS);
+    const float s = (v - mn) * inv, kap = v * inv;
+    const float vs = v * s;
+    float gyr, gyg, gyb, gdr, gdg, gdb;
+    blend_bwd<HM>(fmaf(-tab[1], vs, v), r, mr, gr, gyr, gdr);
+    blend_bwd<HM>(fmaf(-tab[2], vs, v), g, mg, gg, gyg, gdg);
+    blend_bwd<HM>(fmaf(-tab[3], vs, v), b, mb, gb, gyb, gdb);
+    const float Sg = gyr + gyg + gyb;
+    const float Sa = tab[1] * gyr + tab[2] * gyg + tab[3] * gyb;
+    if (own) acc -= vs * (tab[4] * gyr + tab[5] * gyg + tab[6] * gyb);
+    // y_c = v - a_c v (v - mn) / (v + eps): d/dv = 1 - a_c (s + kap (1 - s)), d/dmn = a_c kap; max / min route to the
+    // first tied channel (gray pixels: both to channel 0, which then receives exactly Sg)
+    const float Gv = Sg - Sa * fmaf(kap, 1.0f - s, s);
+    const float Gmn = Sa * kap;
+    const int im = argmax3(r, g, b), in = argmin3(r, g, b);
+    gr = gdr + (im == 0 ? Gv : 0.0f) + (in == 0 ? Gmn : 0.0f);
+    gg = gdg + (im == 1 ? Gv : 0.0f) + (in == 1 ? Gmn : 0.0f);
+    gb = gdb + (im == 2 ? Gv : 0.0f) + (in == 2 ? Gmn : 0.0f);
+}
+
 // one channel of a curve operator: G[i] += g * clamp(L x - i, 0, 1)
 template <bool HM, bool CL>
 T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, F2 *G, bool own) {
@@ -480,6 +571,8 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
             gg = curve_bwd<HM, CL>(tab + CT, L, g, mg, gg, A.color[1], own);
             gb = curve_bwd<HM, CL>(tab + 2 * CT, L, b, mb, gb, A.color[2], own);
             break;
+        case OP_BNW: bnw_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.bnw, own); break;
+        case OP_HUE: hue_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.hue, own); break;
         case OP_WHITE: {
             float gy, gd;
             blend_bwd<HM>(1.0f, r, mr, gr, gy, gd); gr = gd;

@@ -154,6 +154,23 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
                         x[c][v] = sat01(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]));
                     }
                 }
+            } else if (op == OP_BLUR) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float *row = src + c * srows * spitch, *ru = row - spitch, *rd = row + spitch;
+                    float ctr[VEC], up[VEC], dn[VEC];
+                    lds_vec<VEC>(row, ctr);
+                    lds_vec<VEC>(ru, up);
+                    lds_vec<VEC>(rd, dn);
+                    const float lf = row[-1], rt = row[VEC], ul = ru[-1], ur = ru[VEC], dl = rd[-1], dr = rd[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
+                        const float e = v > 0 ? up[v - 1] : ul, f = v < VEC - 1 ? up[v + 1] : ur;
+                        const float g = v > 0 ? dn[v - 1] : dl, h = v < VEC - 1 ? dn[v + 1] : dr;
+                        x[c][v] = sat01(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]));
+                    }
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) lds_vec<VEC>(src + c * srows * spitch, x[c]);
@@ -165,6 +182,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         break;
                     T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
                     T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+                    T2O_CASE(OP_BNW) T2O_CASE(OP_HUE)
 #undef T2O_CASE
                     default: break;
                 }

@@ -95,7 +95,12 @@ T2O_HD int build_step_desc(int n_ops, const int *op_ids, const int *param_off, i
         if ((seen >> op) & 1u) return T2O_ERR_UNSUPPORTED;
         seen |= 1u << op;
         switch (op) {
-            case OP_SHARPNESS: d.sharp = k; d.slot_col[ACC_SHARP] = po; break;
+            case OP_SHARPNESS: case OP_BLUR:                    // one stencil operator per launch; both feed the `sharp` slot
+                if (d.sharp >= 0) return T2O_ERR_UNSUPPORTED;
+                d.sharp = k; d.slot_col[ACC_SHARP] = po;
+                break;
+            case OP_BNW: d.slot_col[ACC_BNW] = po; break;
+            case OP_HUE: d.slot_col[ACC_HUE] = po; break;
             case OP_BRIGHTNESS: d.slot_col[ACC_BRIGHT] = po; break;
             case OP_CONTRAST: d.slot_col[ACC_CONTRAST] = po; break;
             case OP_SATURATION: d.slot_col[ACC_SATUR] = po; break;
@@ -129,7 +134,7 @@ __host__ __device__ constexpr unsigned int pack_ops(int o0 = -1, int o1 = -1, in
            (unsigned)(o4 + 1) << 16 | (unsigned)(o5 + 1) << 20 | (unsigned)(o6 + 1) << 24 | (unsigned)(o7 + 1) << 28;
 }
 __host__ __device__ constexpr int sp_count(unsigned int sp) { int n = 0; for (int k = 0; k < MAX_CHAIN; ++k) if ((sp >> (4 * k)) & 15u) n = k + 1; return n; }
-__host__ __device__ constexpr int sp_sharp(unsigned int sp) { for (int k = 0; k < MAX_CHAIN; ++k) if (packed_op(sp, k) == OP_SHARPNESS) return k; return -1; }
+__host__ __device__ constexpr int sp_sharp(unsigned int sp) { for (int k = 0; k < MAX_CHAIN; ++k) if (packed_op(sp, k) == OP_SHARPNESS) return k; return -1; }   // (no blur chain is specialised)
 __host__ __device__ constexpr int sp_clamped(unsigned int sp) {
     int c = 0;
     for (int k = 1; k < MAX_CHAIN; ++k) if (packed_op(sp, k - 1) >= 0 || ((c >> (k - 1)) & 1)) c |= 1 << k;
@@ -154,6 +159,8 @@ __device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, floa
         case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
         case OP_EXPOSURE: T2O_CASE(OP_EXPOSURE, false) break;
         case OP_WHITEBALANCE: T2O_CASE(OP_WHITEBALANCE, false) break;
+        case OP_BNW: T2O_CASE(OP_BNW, false) break;
+        case OP_HUE: T2O_CASE(OP_HUE, false) break;
         default: break;
     }
 #undef T2O_CASE
@@ -175,6 +182,8 @@ __device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, cons
         case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
         case OP_EXPOSURE: T2O_CASE(OP_EXPOSURE, false) break;
         case OP_WHITEBALANCE: T2O_CASE(OP_WHITEBALANCE, false) break;
+        case OP_BNW: T2O_CASE(OP_BNW, false) break;
+        case OP_HUE: T2O_CASE(OP_HUE, false) break;
         default: break;
     }
 #undef T2O_CASE
@@ -271,6 +280,31 @@ __device__ __forceinline__ void stencil_ring(const float *row, const float *up, 
         const float r = v < VEC - 1 ? ctr[v + 1] : rt;
         lap[v] = laplace(ctr[v], u[v], d[v], l, r);
     }
+}
+
+// The blur's 9-point variant: the same plus the four diagonal neighbours (up[-1], up[VEC], dn[-1], dn[VEC] are addressable too).
+template <int VEC>
+__device__ __forceinline__ void stencil_ring9(const float *row, const float *up, const float *dn,
+                                              float (&ctr)[VEC], float (&lap)[VEC]) {
+    float u[VEC], d[VEC];
+    lds_vec<VEC>(row, ctr);
+    lds_vec<VEC>(up, u);
+    lds_vec<VEC>(dn, d);
+    const float lf = row[-1], rt = row[VEC], ul = up[-1], ur = up[VEC], dl = dn[-1], dr = dn[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
+        const float a = v > 0 ? u[v - 1] : ul, b = v < VEC - 1 ? u[v + 1] : ur;
+        const float e = v > 0 ? d[v - 1] : dl, f = v < VEC - 1 ? d[v + 1] : dr;
+        lap[v] = blur_delta(ctr[v], (u[v] + d[v]) + (l + r), (a + b) + (e + f));
+    }
+}
+// S(x) of the launch's stencil operator (warp-uniform choice): y = x + p * S(x)
+template <int VEC>
+__device__ __forceinline__ void stencil_any(bool blur, const float *row, const float *up, const float *dn,
+                                            float (&ctr)[VEC], float (&lap)[VEC]) {
+    if (blur) stencil_ring9<VEC>(row, up, dn, ctr, lap);
+    else stencil_ring<VEC>(row, up, dn, ctr, lap);
 }
 
 // ---------------------------------------------------------------- warp transpose-reductions
@@ -515,6 +549,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
+    const bool blur = SP ? false : ch.op[sp] == OP_BLUR;           // which stencil (the specialised chains hold a sharpness)
     const bool need_c = gi_b != nullptr || sp > 0;
     const int clamped = SP ? SPC : ch.clamped;
     const unsigned int opsp = SP ? SP : ch.ops_packed;
@@ -575,7 +610,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
                 const float *xb = Xc + sB * SLOTF, *xu = Xc + sU * SLOTF, *xd = Xc + sD * SLOTF;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    stencil_ring<VEC>(xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr[c], lap[c]);
+                    stencil_any<VEC>(blur, xb + c * ROWF, xu + c * ROWF, xd + c * ROWF, ctr[c], lap[c]);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v)
                         x[c][v] = sat01(blend<HM>(fmaf(p, lap[c][v], ctr[c][v]), ctr[c][v], m[c][v]));
@@ -641,7 +676,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float ctr[VEC], lap[VEC];
-                    stencil_ring<VEC>(yc + c * ROWF, yu + c * ROWF, yd + c * ROWF, ctr, lap);
+                    stencil_any<VEC>(blur, yc + c * ROWF, yu + c * ROWF, yd + c * ROWF, ctr, lap);
                     float gdv[VEC];
                     if constexpr (HM) lds_vec<VEC>(GDc + sC * SLOTF + c * ROWF, gdv);
 #pragma unroll

@@ -16,6 +16,8 @@ from . import _lib
 
 OP_IDENTITY, OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_INPAINT = -1, 0, 1, 2, 3, 4
 OP_TONE, OP_SHARPNESS, OP_WHITE, OP_EXPOSURE, OP_WHITEBALANCE = 5, 6, 7, 8, 9
+OP_BNW, OP_BLUR, OP_HUE = 10, 11, 12          # classes without an Executor slot (models/operators.py:298, 373, 414)
+STENCIL_OPS = (OP_SHARPNESS, OP_BLUR)
 CURVE_STEPS = 8
 
 
@@ -72,12 +74,13 @@ def split_segments(op_ids):
     keeps one register accumulator slot per operator type; the stencil of a second sharpness needs a new pass)."""
     segs, cur, seen = [], [], set()
     for i, op in enumerate(op_ids):
-        if len(cur) == _lib.MAX_CHAIN or op in seen:
+        key = 'stencil' if op in STENCIL_OPS else op          # sharpness and blur share the launch's one stencil
+        if len(cur) == _lib.MAX_CHAIN or key in seen:
             segs.append(cur)
             cur, seen = [], set()
         cur.append(i)
         if op >= 0:
-            seen.add(op)
+            seen.add(key)
     if cur:
         segs.append(cur)
     return segs

@@ -301,6 +301,59 @@ class ColorOperator(Operator):
         return ub, lb, (ub + lb) / 2
 
 
+class BNWOperator(Operator):
+    """models/operators.py:298-329 (no Executor slot): lerp(img, luminance, p)"""
+    op_id = TF.OP_BNW
+
+    def __init__(self, cfg):
+        super(BNWOperator, self).__init__(cfg)
+        self.short_name = 'black&white'
+        self.num_op_param = 1
+        self.setup()
+
+    def op_param_regressor(self, features):
+        return torch.sigmoid(features)
+
+    def get_param_range(self):
+        return 1, 0, 0.5
+
+
+class BlurOperator(Operator):
+    """models/operators.py:373-411 (no Executor slot): lerp(img, 3x3 Gaussian(sigma 2, zero padding) * img, p)"""
+    op_id = TF.OP_BLUR
+
+    def __init__(self, cfg):
+        super(BlurOperator, self).__init__(cfg)
+        self.short_name = 'blur'
+        self.num_op_param = 1
+        self.setup()
+
+    def op_param_regressor(self, features):
+        return torch.sigmoid(features)
+
+    def get_param_range(self):
+        return 1, 0, 0.5
+
+
+class HueOperator(Operator):
+    """models/operators.py:414-451 (no Executor slot): hsv_to_rgb(param, s, v) -- the hue of every pixel replaced by the
+    parameter (radians, kornia's [0, 2 pi) scale).  The reference's `param.expand_as(value)` only broadcasts for a
+    batch of one; here every batch row takes its own parameter."""
+    op_id = TF.OP_HUE
+
+    def __init__(self, cfg):
+        super(HueOperator, self).__init__(cfg)
+        self.short_name = 'hue_'
+        self.num_op_param = 1
+        self.setup()
+
+    def op_param_regressor(self, features):
+        return features
+
+    def get_param_range(self):
+        return 1, 0, 0.5
+
+
 class InpaintOperator(Operator):
     """models/operators.py:625-682.  The EdgeConnect inpainting network is OUT OF SCOPE (a local,
     deep-CNN operator).  The stub keeps the module and checkpoint names."""

@@ -144,6 +144,8 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                     case OP_CONTRAST: gp[0] = (float)accd[ACC_CONTRAST]; break;
                     case OP_SATURATION: gp[0] = (float)accd[ACC_SATUR]; break;
                     case OP_EXPOSURE: gp[0] = (float)accd[ACC_EXPO]; break;
+                    case OP_BNW: gp[0] = (float)accd[ACC_BNW]; break;
+                    case OP_HUE: gp[0] = (float)accd[ACC_HUE]; break;
                     case OP_WHITEBALANCE: for (int t = 0; t < 3; ++t) gp[t] = (float)accd[ACC_WB + t]; break;
                     default: break;
                 }

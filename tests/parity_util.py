@@ -27,6 +27,10 @@ def sample_params(op, B, g, wide=False):
         return u * 2 - 1
     if op == O.OP_WHITEBALANCE:
         return 0.4 + 1.4 * u
+    if op == O.OP_HUE:
+        return (u * 6.2831853) if not wide else (u * 21 - 7)
+    if op in (O.OP_BNW, O.OP_BLUR):
+        return u if not wide else (u * 2 - 0.5)
     return u
 
 

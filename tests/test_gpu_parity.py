@@ -12,7 +12,7 @@ from parity_util import TOL_GRAD, TOL_PIX, kink_slack, max_abs, oracle_chain_wit
 
 pytestmark = pytest.mark.gpu
 
-ALL_OPS = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+ALL_OPS = [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12]       # 10-12: BNW, Blur, Hue (single_ops_ext.npz)
 
 
 @pytest.fixture(scope='module')
@@ -23,7 +23,9 @@ def TF():
 
 @pytest.fixture(scope='module')
 def single(golden_dir):
-    return np.load(os.path.join(golden_dir, 'single_ops.npz'))
+    d = dict(np.load(os.path.join(golden_dir, 'single_ops.npz')))
+    d.update(np.load(os.path.join(golden_dir, 'single_ops_ext.npz')))
+    return d
 
 
 @pytest.fixture(scope='module')
@@ -112,7 +114,8 @@ def test_single_op_oracle(TF, op, shape):
 
 
 CHAINS = [[0, 1, 2, 3, 5, 6], [6, 0, 1, 2, 3, 5], [1, 6, 5], [3, 5], [6], [2, 6, 0], [8, 9, 7, 0], [0, 1, 2, 3, 5, 8, 9, 6],
-          [6, 1, 6, 5], [5, 5, 3, 3, 1, 1, 0, 0, 2, 2], [0, -1, 5]]
+          [6, 1, 6, 5], [5, 5, 3, 3, 1, 1, 0, 0, 2, 2], [0, -1, 5],
+          [10, 11, 12], [11], [0, 11, 5, 10], [12, 6, 11, 1], [2, 12, 3, 11]]        # BNW 10, Blur 11, Hue 12
 
 
 @pytest.mark.parametrize('shape', [(2, 40, 64), (1, 67, 131), (2, 128, 128), (1, 35, 66)])

@@ -49,7 +49,7 @@ def oracle_rows(img, row_ops, params, mask, loss_fn):
     return out.detach(), p.grad, x.grad
 
 
-MIXED = [[0], [1], [2], [3], [5], [6], [7], [-1], [6], [0], [8], [9], [5], [3]]
+MIXED = [[0], [1], [2], [3], [5], [6], [7], [-1], [6], [0], [8], [9], [5], [3], [10], [11], [12], [11]]
 
 
 @pytest.mark.parametrize('shape', [(32, 48), (37, 53), (128, 128), (9, 6)])

@@ -23,7 +23,7 @@ def test_library_exports_every_symbol_declared_in_the_header():
     lib = _lib.lib()                               # builds if stale; loads without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.t2o_version() == 102
+    assert lib.t2o_version() == 103
     assert lib.t2o_status_string(2) == b'unsupported configuration'
     assert [lib.t2o_num_params(op, 8) for op in (-1, 0, 1, 2, 3, 5, 6, 7, 8, 9)] == [0, 1, 1, 1, 24, 8, 1, 1, 1, 3]
     assert lib.t2o_num_params(42, 8) == -1
@@ -190,9 +190,10 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
 
 
-@pytest.mark.parametrize('op', [0, 1, 2, 3, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize('op', [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 12])
 def test_kernel_math_single_ops_vs_reference_golden(hostcheck, golden_dir, op):
-    G = np.load(os.path.join(golden_dir, 'single_ops.npz'))
+    G = dict(np.load(os.path.join(golden_dir, 'single_ops.npz')))
+    G.update(np.load(os.path.join(golden_dir, 'single_ops_ext.npz')))
     for variant in ('n_none', 'n_m1', 'n_m3', 'w_none'):
         key = 'op%d_%s' % (op, variant)
         mk = variant.split('_')[1]

@@ -11,12 +11,14 @@ import torch
 from oracle import ops as O
 from oracle import planner as P
 
-OPS = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+OPS = [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12]       # 10-12: BNW, Blur, Hue (single_ops_ext.npz)
 
 
 @pytest.fixture(scope='module')
 def single(golden_dir):
-    return np.load(os.path.join(golden_dir, 'single_ops.npz'))
+    d = dict(np.load(os.path.join(golden_dir, 'single_ops.npz')))
+    d.update(np.load(os.path.join(golden_dir, 'single_ops_ext.npz')))
+    return d
 
 
 @pytest.fixture(scope='module')
