@@ -416,10 +416,14 @@ def extras(TF, dev, wl):
         img = torch.rand(B, 3, H, W, generator=dgen, device=dev)
         gout = torch.randn(B, 3, H, W, generator=dgen, device=dev)
         ops_tab = {}
-        names = {0: 'brightness', 1: 'contrast', 2: 'saturation', 3: 'color', 5: 'tone', 6: 'sharpness', 8: 'exposure', 9: 'whitebalance'}
+        names = {0: 'brightness', 1: 'contrast', 2: 'saturation', 3: 'color', 5: 'tone', 6: 'sharpness', 8: 'exposure', 9: 'whitebalance',
+                 10: 'black&white', 11: 'blur', 12: 'hue'}
         prm = dict(zip(CHAIN, make_params(B, gen, dev)))
         prm[8] = torch.rand(B, 1, generator=gen).to(dev) * 2 - 1
         prm[9] = 0.4 + 1.4 * torch.rand(B, 3, generator=gen).to(dev)
+        prm[10] = torch.rand(B, 1, generator=gen).to(dev)
+        prm[11] = torch.rand(B, 1, generator=gen).to(dev)
+        prm[12] = torch.rand(B, 1, generator=gen).to(dev) * 6.28
         for op, name in names.items():
             p = prm[op].contiguous()
             n = p.shape[1]
@@ -428,6 +432,12 @@ def extras(TF, dev, wl):
             ops_tab[name] = {'fwd_ms': t_f, 'fwd_GBps_at_24B_px': 24 * px / t_f / 1e6, 'fwd_frac_of_measured_peak': 24 * px / t_f / 1e6 / peak,
                              'bwd_ms': t_b, 'bwd_GBps_at_36B_px': 36 * px / t_b / 1e6, 'bwd_frac_of_measured_peak': 36 * px / t_b / 1e6 / peak}
         ex['c4_single_ops'] = ops_tab
+        # evaluation metrics at the same shape: SSIM (utils/ssim) and L1, 24 B/px each (two images read, one scalar out)
+        from t2onet_b200 import metrics as MT
+        t_s = bench(lambda: MT.ssim_sum(img, gout), 5)
+        t_l = bench(lambda: TF.l1_sum(img, gout), 5)
+        ex['c4_metrics'] = {'ssim_ms': t_s, 'ssim_GBps_at_24B_px': 24 * px / t_s / 1e6, 'ssim_frac_of_measured_peak': 24 * px / t_s / 1e6 / peak,
+                            'l1_ms': t_l, 'l1_GBps_at_24B_px': 24 * px / t_l / 1e6, 'l1_frac_of_measured_peak': 24 * px / t_l / 1e6 / peak}
         del img, gout
         torch.cuda.empty_cache()
     except Exception as exc:

@@ -159,6 +159,16 @@ int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_p
                void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 
 /*
+ * SSIM of image pairs (evaluation metric, utils/ssim/__init__.py:19-41 as utils/eval.py:57-60 uses it: 11x11 Gaussian
+ * window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2): ssim_sum[b] = sum over channels and pixels of the SSIM map
+ * of (img1[b], img2[b]); the reference's value is ssim_sum / (C*H*W) (its mean over the batch: the sums' total / numel).
+ * img1, img2 (B, C, H, W) float32 contiguous.  One pass over HBM, nothing stored but the sums.
+ */
+size_t t2o_ssim_workspace_bytes(int B, int C, int H, int W);
+int t2o_ssim_sum(const float *img1, const float *img2, float *ssim_sum, int B, int C, int H, int W,
+                 void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
  * Planner candidate scoring (the inner loop of get_param_naive / beam_search,
  * utils/beam_search.py:77-87,229-237): candidate c applies operator cand_op[c] with parameters
  * cand_param[c*24 ..] to state image cand_state[c] and is scored against that state's target,

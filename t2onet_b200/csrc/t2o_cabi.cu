@@ -31,6 +31,9 @@ int nm_start(const t2o_nm_state *st, int P, const int *n_dims, const int *prob_o
              float *cand_param, int *cand_op, cudaStream_t stream);
 int nm_advance(const t2o_nm_state *st, int P, const float *l1_sum, float numel, float *cand_param, int *cand_op,
                cudaStream_t stream);
+size_t ssim_workspace_bytes(int B, int C, int H, int W);
+int ssim_sum(const float *img1, const float *img2, float *out, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+             cudaStream_t stream);
 const char *last_cuda_error();
 }  // namespace t2o
 
@@ -122,6 +125,16 @@ int t2o_nm_start(const t2o_nm_state *state, int P, const int32_t *n_dims, const 
 int t2o_nm_advance(const t2o_nm_state *state, int P, const float *l1_sum, float numel, float *cand_param,
                    int32_t *cand_op, t2o_stream_t stream) {
     return t2o::nm_advance(state, P, l1_sum, numel, cand_param, cand_op, (cudaStream_t)stream);
+}
+
+size_t t2o_ssim_workspace_bytes(int B, int C, int H, int W) {
+    if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
+    return t2o::ssim_workspace_bytes(B, C, H, W);
+}
+
+int t2o_ssim_sum(const float *img1, const float *img2, float *ssim_sum, int B, int C, int H, int W, void *workspace,
+                 size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::ssim_sum(img1, img2, ssim_sum, B, C, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -113,3 +113,13 @@ def test_oracle_planner_reproduces_recorded_pair_transcripts(golden_dir):
         for seq, rseq in zip(actions, ref):
             for a, r in zip(seq, rseq):
                 assert list(a[1]) == r[1] and a[2] == r[2]
+
+
+@pytest.mark.parametrize('name', ['a', 'b', 'c'])
+def test_oracle_ssim_matches_reference(golden_dir, name):
+    """oracle/metrics.py == utils/ssim/__init__.py of the reference on the recorded pairs (bit for bit)."""
+    from oracle import metrics as OM
+    d = np.load(os.path.join(golden_dir, 'ssim.npz'))
+    x, y = torch.from_numpy(d[name + '_x']), torch.from_numpy(d[name + '_y'])
+    assert np.float32(OM.ssim(x, y).item()) == d[name + '_mean']
+    assert np.array_equal(OM.ssim(x, y, size_average=False).numpy(), d[name + '_per'])
