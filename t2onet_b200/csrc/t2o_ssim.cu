@@ -176,11 +176,7 @@ int ssim_sum(const float *img1, const float *img2, float *out, int B, int C, int
     for (int x = 0; x < SS_K; ++x) gs += g[x];
     for (int x = 0; x < SS_K; ++x) a.w[x] = g[x] / gs;
     const size_t smem = (size_t)(2 * SS_PH * SS_PITCH + 5 * SS_PH * SS_TW) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        T2O_CUDA_OK(cudaFuncSetAttribute(ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    T2O_CUDA_OK(cudaFuncSetAttribute(ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set at every launch
     dim3 grid(a.ntiles, C, B);
     ssim_kernel<<<grid, SS_NT, smem, stream>>>(a);
     T2O_CUDA_OK(cudaGetLastError());

@@ -220,9 +220,12 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor):
         Is, Gs = I_list[c0:c0 + CH], I_gt_list[c0:c0 + CH]
         img = torch.cat(Is, 0).contiguous()
         tgt = torch.cat(Gs, 0).contiguous()
-        prm = torch.zeros(len(Is), 24, dtype=torch.float32)
+        prm = np.zeros((len(Is), 24), dtype=np.float32)
         for r, p in enumerate(params[c0:c0 + CH]):
-            prm[r, :p.shape[1]] = p[0].float()                      # float64 -> float32, as torch.tensor([param], dtype=torch.float)
+            if isinstance(p, torch.Tensor):
+                p = p.detach().cpu().numpy()
+            prm[r, :p.shape[1]] = p[0]                              # float64 -> float32, as torch.tensor([param], dtype=torch.float)
+        prm = torch.from_numpy(prm)
         row_ops = [[int(o)] for o in ops[c0:c0 + CH]]
         ops_dev, ops_host = TF._prep_row_ops(row_ops, len(Is), dev)
         out, l1 = TF._rows_forward_raw(ops_dev, ops_host, img, None, 0, prm.to(dev), tgt, True, True, L)
@@ -266,7 +269,7 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
         if optimizer == 'Nelder-Mead' and problems:
             fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _ in problems],
                                           executor, state_target=state_pair, counter=counter, numel=numel)
-            params = [torch.tensor(np.array([list(r.x)])) for r in fits]
+            params = [np.asarray(r.x, dtype=np.float64)[None, :] for r in fits]     # (1, n) float64, as the reference's tensors
         else:
             params = [get_param(states[s], I_gt[m:m + 1], txt, op, executor, None, dist_type, optimizer)[0]
                       for s, op, m, _ in problems]
