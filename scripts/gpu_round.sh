@@ -13,6 +13,7 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 echo "== ncu launch list (c2 bench)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2_$TAG.csv python bench.py --steps 5 --warmup 3 --no-extras --no-graph > $OUT/ncu_c2_$TAG.log 2>&1
 echo "== ncu full captures"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ssim_kernel -s 1 -c 1 -f -o $OUT/prof_ssim_$TAG python scripts/dev/time_ssim.py > $OUT/ncu_ssim_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 2 -c 1 -f -o $OUT/prof_step_c2_$TAG python scripts/run_once.py c2 > $OUT/ncu_step_c2_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 2 -c 1 -f -o $OUT/prof_step_c4_$TAG python scripts/run_once.py bwd_c4 > $OUT/ncu_step_c4_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chain_fwd -s 1 -c 1 -f -o $OUT/prof_fwd_c4_$TAG python scripts/run_once.py fwd_c4 > $OUT/ncu_fwd_c4_$TAG.log 2>&1
