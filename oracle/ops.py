@@ -114,7 +114,7 @@ _LAPLACE = torch.tensor([[[[0, -1, 0], [-1, 4, -1], [0, -1, 0]]]], dtype=torch.f
 
 def process_sharpness(img, param, cfg):
     """models/operators.py:351-358 (per-channel 3x3 Laplacian, zero padding 1)."""
-    planes = [F.conv2d(c, _LAPLACE, padding=1) for c in img.split([1, 1, 1], 1)]
+    planes = [F.conv2d(c, _LAPLACE.to(img.device), padding=1) for c in img.split([1, 1, 1], 1)]
     return img + _bc(param) * torch.cat(planes, 1)
 
 
@@ -171,7 +171,7 @@ _GAUSS = _gaussian_kernel()
 
 def process_blur(img, param, cfg):
     """models/operators.py:397-404 (per-channel 3x3 Gaussian, zero padding 1, then lerp)."""
-    planes = [F.conv2d(c, _GAUSS, padding=1) for c in img.split([1, 1, 1], 1)]
+    planes = [F.conv2d(c, _GAUSS.to(img.device), padding=1) for c in img.split([1, 1, 1], 1)]
     return lerp(img, torch.cat(planes, 1), _bc(param))
 
 

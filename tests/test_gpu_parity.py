@@ -296,6 +296,31 @@ def test_identity_chain_and_large_image_properties(TF):
         assert np.allclose((2 * a).cpu().numpy(), b.cpu().numpy(), rtol=1e-6, atol=1e-12)
 
 
+def test_full_resolution_chain_against_the_oracle_on_the_gpu(TF):
+    """BASELINE config 4's image size (3 x 2048 x 3072, one image): the fused forward + L1 + backward launch against the
+    oracle's torch ops run on the same GPU in fp32 (autograd through all six operators, ~20 GB of saved planes) --
+    pixels max-abs 1e-5, L1 1e-5, parameter gradients relative 1e-4, at the size the benchmark runs."""
+    B, H, W = 1, 2048, 3072
+    g = torch.Generator(device='cuda').manual_seed(11)
+    img = torch.rand(B, 3, H, W, generator=g, device='cuda')
+    ops = [0, 1, 2, 3, 5, 6]
+    cg = torch.Generator().manual_seed(12)
+    params = [sample_params(op, B, cg).cuda() for op in ops]
+    with torch.no_grad():
+        tgt = O.chain(img, ops, [sample_params(op, B, cg).cuda() for op in ops])
+    ps = [p.clone().requires_grad_() for p in params]
+    out_o = O.chain(img, ops, ps)
+    loss_o = (out_o - tgt).abs().mean()
+    loss_o.backward()
+    out, l1, grads, _ = TF.chain_forward_backward(img, ops, params, tgt)
+    assert (out - out_o.detach()).abs().max().item() <= TOL_PIX
+    assert abs(l1.sum().item() / img.numel() - loss_o.item()) <= 1e-5
+    for k, (gk, p) in enumerate(zip(grads, ps)):
+        assert rel_err(gk.cpu(), p.grad.cpu()) <= TOL_GRAD, (ops[k], gk, p.grad)
+    del out_o, loss_o, ps
+    torch.cuda.empty_cache()
+
+
 def test_errors_are_loud(TF):
     from t2onet_b200 import T2OError
     img = torch.rand(1, 3, 8, 8).cuda()
