@@ -311,6 +311,23 @@ def run_ours(args, wl):
     h2d = 2 * px_step * 12 + hpar[0].numel() * 4
     d2h = B * 4 + B * 36 * 4
 
+    planner_line = None
+    if world > 1 and not args.no_extras:
+        # planner throughput scaling: every rank plans its own 64 pairs (image sharding, no data-path communication)
+        barrier()
+        err = None
+        try:
+            sec, cand, steps = planner_e2e_run(dev, 3010 + 17 * rank)
+        except Exception as exc:   # report, never hide -- and still take part in the collectives below
+            sec, cand, steps, err = 0.0, 0, 0.0, repr(exc)
+        t = torch.tensor([sec, float(cand), steps, 0.0 if err is None else 1.0], device=dev, dtype=torch.float64)
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        if tsum[3].item() > 0:
+            planner_line = {'error': err or 'a rank failed'}
+        else:
+            planner_line = planner_e2e_line(tmax[0].item(), int(tsum[1].item()), tsum[2].item() / world, n_gpus=world)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -344,6 +361,8 @@ def run_ours(args, wl):
     if world == 1 and not args.no_extras:
         line['cpu_baseline'] = cpu_baseline(wl)
         line['extras'] = extras(TF, dev, wl)
+    if planner_line is not None:
+        line['extras'] = {'planner_e2e': planner_line}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -367,6 +386,41 @@ def cpu_baseline(wl):
 
 def fused_scale(B, H, W, dev):
     return torch.full((B,), 1.0 / (B * 3 * H * W), device=dev, dtype=torch.float32)
+
+
+PLANNER_M = 64
+
+
+def planner_e2e_run(dev, seed, reps=3):
+    """beam_search_batch (= the reference's beam_search on every pair, utils/beam_search.py:196-264) over 64 synthetic pairs
+    of 3x128x128, beam 8, the six global operators, max 6 steps, Nelder-Mead fits resident on the device (BASELINE
+    config 3's shape; 1000 pairs = 16 such batches).  -> (best wall-clock seconds of reps - 1 timed repetitions,
+    candidates scored, mean steps of the top sequences); the first repetition warms the kernels up."""
+    import t2onet_b200 as T
+    from t2onet_b200 import planner
+    names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+    exe = T.Executor(T.default_options()).to(dev)
+    img, tgt, _ = make_batch(PLANNER_M, 128, 128, seed, dev)
+    best = None
+    for rep in range(reps):
+        cnt = [0]
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2, counter=cnt)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        if rep > 0 and (best is None or dt < best[0]):
+            best = (dt, cnt[0])
+    return best[0], best[1], sum(len(r[0][0]) for r in res) / PLANNER_M
+
+
+def planner_e2e_line(seconds, candidates, mean_steps, n_gpus):
+    pairs = PLANNER_M * n_gpus
+    return {'workload': '%d pairs of 3x128x128 per GPU, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, Nelder-Mead' % PLANNER_M,
+            'n_gpus': n_gpus, 'seconds': seconds, 'pairs_per_s': pairs / seconds, 'candidates': candidates,
+            'candidates_per_s': candidates / seconds, 'mean_steps': mean_steps,
+            'how': 'wall clock around beam_search_batch (host bookkeeping and result copies included), best of 2; N > 1: pairs sharded '
+                   'by image, no communication during the search, slowest rank\'s time, candidates summed over ranks'}
 
 
 def extras(TF, dev, wl):
@@ -499,32 +553,9 @@ def extras(TF, dev, wl):
                                  'Gpixel_candidates_per_s': C * H * W / t_sc / 1e6}
     except Exception as exc:
         ex['planner_scoring'] = {'error': repr(exc)}
-    # ---- the planner end to end through its public API: beam_search_batch (= the reference's beam_search on every pair,
-    # utils/beam_search.py:196-264) over 64 synthetic pairs of 3x128x128, beam 8, the six global operators, max 6 steps,
-    # Nelder-Mead fits resident on the device (BASELINE config 3 shape; 1000 pairs = 16 such batches)
+    # ---- the planner end to end through its public API (see planner_e2e_run)
     try:
-        import time
-        import t2onet_b200 as T
-        from t2onet_b200 import planner
-        names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
-        exe = T.Executor(T.default_options()).to(dev)
-        M = 64
-        img, tgt, _ = make_batch(M, 128, 128, 3010, dev)
-        best = None
-        for rep in range(3):                                # the first repetition warms the kernels up
-            cnt = [0]
-            torch.cuda.synchronize()
-            t0 = time.time()
-            res = planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2, counter=cnt)
-            torch.cuda.synchronize()
-            dt = time.time() - t0
-            if rep > 0 and (best is None or dt < best[0]):
-                best = (dt, cnt[0])
-        ex['planner_e2e'] = {'workload': '%d pairs of 3x128x128, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, Nelder-Mead' % M,
-                             'seconds': best[0], 'pairs_per_s': M / best[0], 'candidates': best[1],
-                             'candidates_per_s': best[1] / best[0],
-                             'mean_steps': sum(len(r[0][0]) for r in res) / M,
-                             'how': 'wall clock around beam_search_batch (host bookkeeping and result copies included), best of 2'}
+        ex['planner_e2e'] = planner_e2e_line(*planner_e2e_run(dev, 3010), n_gpus=1)
     except Exception as exc:
         ex['planner_e2e'] = {'error': repr(exc)}
     return ex
