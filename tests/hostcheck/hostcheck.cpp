@@ -11,6 +11,15 @@
 
 using namespace t2o;
 
+// S(x) of the stencil operators at one pixel of a plane (zero padding): laplace for sharpness, (G - delta) for blur
+static inline float stencil_at(int op, const float *pc, int H, int W, int yy, int xx) {
+    auto at = [&](int y, int x) { return (y >= 0 && y < H && x >= 0 && x < W) ? pc[(size_t)y * W + x] : 0.f; };
+    const float ctr = at(yy, xx), up = at(yy - 1, xx), dn = at(yy + 1, xx), lf = at(yy, xx - 1), rt = at(yy, xx + 1);
+    if (op == t2o::OP_BLUR)
+        return t2o::blur_delta(ctr, (up + dn) + (lf + rt), (at(yy - 1, xx - 1) + at(yy - 1, xx + 1)) + (at(yy + 1, xx - 1) + at(yy + 1, xx + 1)));
+    return t2o::laplace(ctr, up, dn, lf, rt);
+}
+
 extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float *img, const float *mask, int mask_ch,
                         const float *params, int pstride, const float *grad_out, const float *target,
                         const float *grad_l1, float *out, float *l1_sum, float *grad_params, float *grad_img,
@@ -31,16 +40,14 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             const float *x = xs[k].data();
             float *y = xs[k + 1].data();
             const float *tab = &tabs[k * TAB];
-            if (ops[k] == OP_SHARPNESS) {
+            if (op_is_stencil(ops[k])) {
                 for (int c = 0; c < 3; ++c)
                     for (int yy = 0; yy < H; ++yy)
                         for (int xx = 0; xx < W; ++xx) {
                             const size_t i = (size_t)yy * W + xx;
                             const float *pc = x + c * plane;
                             const float ctr = pc[i];
-                            const float up = yy > 0 ? pc[i - W] : 0.f, dn = yy < H - 1 ? pc[i + W] : 0.f;
-                            const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
-                            const float v = fmaf(tab[0], laplace(ctr, up, dn, lf, rt), ctr);
+                            const float v = fmaf(tab[0], stencil_at(ops[k], pc, H, W, yy, xx), ctr);
                             y[c * plane + i] = sat01(has_mask ? blend<true>(v, ctr, M(c, i)) : v);
                         }
             } else {
@@ -74,7 +81,7 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
             const float *x = xs[k].data();
             const float *tab = &tabs[k * TAB];
             std::vector<double> accd(ACC_SLOTS, 0.0);
-            if (ops[k] == OP_SHARPNESS) {
+            if (op_is_stencil(ops[k])) {
                 const float p = tab[0];
                 double accp = 0;
                 for (int c = 0; c < 3; ++c)
@@ -83,9 +90,7 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                             const size_t i = (size_t)yy * W + xx;
                             const float *pc = x + c * plane;
                             const float ctr = pc[i];
-                            const float up = yy > 0 ? pc[i - W] : 0.f, dn = yy < H - 1 ? pc[i + W] : 0.f;
-                            const float lf = xx > 0 ? pc[i - 1] : 0.f, rt = xx < W - 1 ? pc[i + 1] : 0.f;
-                            const float lap = laplace(ctr, up, dn, lf, rt);
+                            const float lap = stencil_at(ops[k], pc, H, W, yy, xx);
                             float gy, gd;
                             if (has_mask) blend_bwd<true>(fmaf(p, lap, ctr), ctr, M(c, i), g[c * plane + i], gy, gd);
                             else blend_bwd<false>(fmaf(p, lap, ctr), ctr, 1.f, g[c * plane + i], gy, gd);
@@ -98,9 +103,7 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                         for (int xx = 0; xx < W; ++xx) {
                             const size_t i = (size_t)yy * W + xx;
                             const float *pg = gyv.data() + c * plane;
-                            const float up = yy > 0 ? pg[i - W] : 0.f, dn = yy < H - 1 ? pg[i + W] : 0.f;
-                            const float lf = xx > 0 ? pg[i - 1] : 0.f, rt = xx < W - 1 ? pg[i + 1] : 0.f;
-                            gn[c * plane + i] += pg[i] + p * laplace(pg[i], up, dn, lf, rt);
+                            gn[c * plane + i] += pg[i] + p * stencil_at(ops[k], pg, H, W, yy, xx);   // symmetric stencil: S^T = S
                         }
                 if (grad_params) grad_params[(size_t)b * pstride + poff[k]] = (float)accp;
                 g.swap(gn);

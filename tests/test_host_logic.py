@@ -190,7 +190,7 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
 
 
-@pytest.mark.parametrize('op', [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 12])
+@pytest.mark.parametrize('op', [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12])
 def test_kernel_math_single_ops_vs_reference_golden(hostcheck, golden_dir, op):
     G = dict(np.load(os.path.join(golden_dir, 'single_ops.npz')))
     G.update(np.load(os.path.join(golden_dir, 'single_ops_ext.npz')))
