@@ -332,3 +332,47 @@ def test_errors_are_loud(TF):
         TF.chain(img, [3], [torch.zeros(1, 3).cuda()])                        # too few parameters
     with pytest.raises(T2OError):
         TF.chain(img.double(), [0], [torch.zeros(1, 1).cuda()])
+
+
+def test_random_chains_shapes_and_masks_sweep(TF):
+    """A seeded sweep over random shapes (ragged widths -> 4-, 2- and 1-pixel groups, images shorter than a pipeline
+    band, single rows / columns), random operator chains over all twelve operators (repeats and identities included:
+    the binding splits them into launches) and random masks: pixels, L1 and gradients against the oracle."""
+    import random
+    rnd = random.Random(2024)
+    pool = [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, -1]
+    for trial in range(40):
+        B = rnd.choice([1, 2, 3])
+        H = rnd.choice([1, 2, 5, 9, 17, 33, 64, 100])
+        W = rnd.choice([1, 3, 4, 6, 10, 30, 64, 65, 128, 130, 200])
+        n = rnd.randint(1, 7)
+        ops = [rnd.choice(pool) for _ in range(n)]
+        if all(o < 0 for o in ops):
+            ops[0] = 1
+        mask_ch = rnd.choice([0, 0, 1, 3])
+        g = torch.Generator().manual_seed(1000 + trial)
+        img = torch.rand(B, 3, H, W, generator=g)
+        params = [sample_params(op, B, g) if op >= 0 else torch.zeros(B, 1) for op in ops]
+        mask = None if mask_ch == 0 else (torch.rand(B, mask_ch, H, W, generator=g) > 0.3).float()
+        target = torch.rand(B, 3, H, W, generator=g)
+        xo = img.clone().requires_grad_()
+        po = [p.clone().requires_grad_() for p in params]
+        out_o = O.chain(xo, ops, po, mask)
+        loss_o = (out_o - target).abs().mean()
+        loss_o.backward()
+        x = img.cuda().requires_grad_()
+        ps = [p.cuda().requires_grad_() for p in params]
+        out = TF.chain(x, ops, ps, None if mask is None else mask.cuda())
+        tag = (trial, B, H, W, ops, mask_ch)
+        assert max_abs(out.detach().cpu(), out_o.detach()) <= TOL_PIX, tag
+        loss = (out - target.cuda()).abs().mean()
+        loss.backward()
+        assert abs(loss.item() - loss_o.item()) <= 1e-5, tag
+        # kink pixels (a forward value within an ulp of a clamp edge / curve knot / the target) may take the other
+        # one-sided derivative: counted exactly from the image gradient, and the parameter gradients get their slack
+        slack = kink_slack(x.grad.cpu(), xo.grad, img.numel(), max_kinks=3)
+        for k, (p, q) in enumerate(zip(ps, po)):
+            if ops[k] < 0 or ops[k] == 7 or q.grad is None:
+                continue
+            d = (p.grad.cpu() - q.grad).abs().max().item()
+            assert d <= max(TOL_GRAD * q.grad.abs().max().item(), slack), (tag, k, p.grad, q.grad)
