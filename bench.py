@@ -438,6 +438,79 @@ def extras(TF, dev, wl):
         e.record(); sync()
         return s.elapsed_time(e) / iters
 
+    # ---- the Actor's call site end to end (BASELINE config 2 as the reference runs it, models/actor.py:156-170): 5 decoding
+    # steps, every row its own operator, parameters from the operators' FC heads (512 -> 512 -> n), L1 to a target, backward
+    # down to the FC weights -- (a) the reference's divide_op_group loop over Executor.execute, (b) Executor.execute_rows
+    try:
+        import t2onet_b200 as T
+        torch.manual_seed(10)
+        exe = T.Executor(T.default_options()).to(dev)
+        B, H, W, STEPS = 64, 128, 128, 5
+        gen = torch.Generator().manual_seed(10 + 7000)
+        img = torch.rand(B, 3, H, W, generator=gen).to(dev)
+        tgt = torch.rand(B, 3, H, W, generator=gen).to(dev)
+        feats = [torch.randn(B, 512, generator=gen).to(dev) for _ in range(STEPS)]
+        ops_cpu = [torch.tensor([CHAIN[int(v)] for v in torch.randint(0, len(CHAIN), (B,), generator=gen)]) for _ in range(STEPS)]
+        ops_dev = [o.to(dev) for o in ops_cpu]
+
+        def grouped_step(x, ops, ctx):
+            unqs = torch.unique(ops)
+            group_inds = [torch.nonzero(ops == u).squeeze(1) for u in unqs]
+            rev = torch.argsort(torch.cat(group_inds)).to(dev)
+            outs = []
+            for j, inds in enumerate(group_inds):
+                inds = inds.to(dev)
+                out_g, _ = exe.execute(x.index_select(0, inds), int(unqs[j]), None, ctx.index_select(0, inds), has_noise=False)
+                outs.append(out_g)
+            return torch.cat(outs).index_select(0, rev)
+
+        def episode(rows, batched=False):
+            exe.zero_grad(set_to_none=True)
+            x = img
+            for k in range(STEPS):
+                x = exe.execute_rows(x, ops_dev[k], None, feats[k], batched_heads=batched)[0] if rows else grouped_step(x, ops_cpu[k], feats[k])
+            loss = (x - tgt).abs().mean()
+            loss.backward()
+            return loss
+        t_grp = bench(lambda: episode(False), 10)
+        t_row = bench(lambda: episode(True), 10)
+        t_bat = bench(lambda: episode(True, True), 10)
+        # the same execute_rows episode (device-resident operator ids: no host sync anywhere) captured as ONE CUDA graph
+        t_graph, graph_err = None, None
+        try:
+            # Operator.execute keeps its last parameters (self.param, as the reference does): they hold the eager episodes'
+            # autograd graphs -- and their AccumulateGrad nodes, bound to the default stream -- alive; drop them first
+            import gc
+            for Op in exe.ops:
+                Op.param, Op.mask = None, None
+            gc.collect()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    episode(True, True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            exe.zero_grad(set_to_none=True)
+            with torch.cuda.graph(gr, capture_error_mode='thread_local'):
+                loss_g = episode(True, True)
+            t_graph = bench(lambda: gr.replay(), 10)
+            ref_loss = episode(True, True).item()
+            gr.replay()
+            torch.cuda.synchronize()
+            assert abs(loss_g.item() - ref_loss) <= 1e-5, (loss_g.item(), ref_loss)
+        except Exception as exc:
+            graph_err = repr(exc)
+        px = B * H * W
+        ex['actor_call_site'] = {'workload': '%dx3x%dx%d, %d decoding steps, a random global operator per row and step, FC heads included, '
+                                             'L1 + backward to the FC weights' % (B, H, W, STEPS),
+                                 'grouped_loop_ms': t_grp, 'execute_rows_ms': t_row, 'speedup': t_grp / t_row,
+                                 'execute_rows_batched_heads_ms': t_bat,
+                                 'execute_rows_batched_heads_cuda_graph_ms': t_graph, 'cuda_graph_error': graph_err,
+                                 'execute_rows_Mpixel_steps_per_s': px * STEPS / t_row / 1e3,
+                                 'how': 'eager PyTorch autograd around the kernels, CUDA events, 10 repetitions'}
+    except Exception as exc:
+        ex['actor_call_site'] = {'error': repr(exc)}
     # ---- C4: the roofline configuration (inputs >> L2)
     try:
         B, H, W = 16, 2048, 3072

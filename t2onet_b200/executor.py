@@ -57,7 +57,27 @@ class Executor(nn.Module):
         param = param.float().to(device)
         return torch.nn.functional.pad(param, (0, TF.PARAM_SLOT - param.shape[1]))
 
-    def execute_rows(self, img, op_inds, mask, features=None, specified_param=None, has_noise=False):
+    def _batched_head_params(self, features, ops_t):
+        """All operators' FC heads (fc1 -> LeakyReLU -> fc2 -> regressor, models/operators.py:73-88) as TWO batched GEMMs
+        over the stacked weights instead of two small GEMMs + an activation per operator; every row then keeps the
+        parameters of its own operator.  Same arithmetic per head up to the GEMM's summation order (~1e-6)."""
+        heads = [(ind, Op) for ind, Op in enumerate(self.ops) if not isinstance(Op, InpaintOperator)]
+        G, bs = len(heads), features.shape[0]
+        slot = TF.PARAM_SLOT
+        W1 = torch.stack([Op.fc1.weight for _, Op in heads])                                   # (G, fc, 2*hidden)
+        b1 = torch.stack([Op.fc1.bias for _, Op in heads])
+        h = torch.baddbmm(b1.unsqueeze(1), features.unsqueeze(0).expand(G, bs, features.shape[1]), W1.transpose(1, 2))
+        h = torch.nn.functional.leaky_relu(h, heads[0][1].lrelu.negative_slope)
+        W2 = torch.stack([torch.nn.functional.pad(Op.fc2.weight, (0, 0, 0, slot - Op.num_op_param)) for _, Op in heads])
+        b2 = torch.stack([torch.nn.functional.pad(Op.fc2.bias, (0, slot - Op.num_op_param)) for _, Op in heads])
+        y = torch.baddbmm(b2.unsqueeze(1), h, W2.transpose(1, 2))                              # (G, bs, 24)
+        params = torch.zeros(bs, slot, device=features.device)
+        for g, (ind, Op) in enumerate(heads):
+            p = torch.nn.functional.pad(Op.op_param_regressor(y[g, :, :Op.num_op_param]), (0, slot - Op.num_op_param))
+            params = torch.where((ops_t == ind).view(bs, 1), p, params)
+        return params
+
+    def execute_rows(self, img, op_inds, mask, features=None, specified_param=None, has_noise=False, batched_heads=False):
         """Extension: ONE operator step for a batch whose rows use DIFFERENT operators
         -- the Actor's divide_op_group loop (models/actor.py:100-114, 156-170, 245-259) as a single call:
             out, param = executor.execute_rows(img_x, pred_op.view(-1) - 3, mask, context)
@@ -66,13 +86,17 @@ class Executor(nn.Module):
                         heads exactly like the reference; a CUDA tensor keeps the whole step free of host syncs
                         (every operator head runs on the full batch and the rows select theirs).
         :param features: (bs, 2*hidden) or None   :param specified_param: (bs, >= n) zero-padded rows or None
+        :param batched_heads: with device-resident op_inds and features: run all FC heads as two batched GEMMs
+                        (_batched_head_params) instead of one pair of small GEMMs per operator
         :return out (bs, 3, h, w), param (bs, 24) zero-padded -- both differentiable."""
         assert (features is None) ^ (specified_param is None)
         bs, dev = img.shape[0], img.device
         on_device = isinstance(op_inds, torch.Tensor) and op_inds.is_cuda
         ops_t = op_inds.view(-1) if isinstance(op_inds, torch.Tensor) else torch.as_tensor(op_inds).view(-1)
         assert ops_t.numel() == bs
-        if on_device:
+        if on_device and batched_heads and features is not None and not has_noise:
+            params = self._batched_head_params(features, ops_t)
+        elif on_device:
             params = torch.zeros(bs, TF.PARAM_SLOT, device=dev)
             for ind, Op in enumerate(self.ops):
                 if isinstance(Op, InpaintOperator):

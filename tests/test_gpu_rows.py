@@ -197,3 +197,31 @@ def test_executor_execute_rows_vs_grouped_loop(where, use_mask):
     for n, p in ex.named_parameters():
         if n in ref_grads:
             assert rel_err(p.grad.cpu(), ref_grads[n].cpu(), atol=1e-6) <= TOL_GRAD, n
+
+
+def test_executor_batched_heads_match_per_operator_heads():
+    """execute_rows(batched_heads=True): all FC heads as two batched GEMMs == one pair of small GEMMs per operator, up to the
+    GEMM's summation order (values 1e-5, gradients down to the FC weights relative 1e-4)."""
+    import t2onet_b200 as T
+    torch.manual_seed(10)
+    ex = T.Executor(T.default_options()).cuda()
+    bs, H, W = 16, 32, 32
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(bs, 3, H, W, generator=g).cuda()
+    feat = torch.randn(bs, 512, generator=g).cuda()
+    wgt = torch.randn(bs, 3, H, W, generator=g).cuda()
+    ops = (torch.tensor([3, 4, 5, 6, 8, 9, 10, 2] * 2) - 3).cuda()
+    res = []
+    for batched in (False, True):
+        x, f = img.clone().requires_grad_(), feat.clone().requires_grad_()
+        ex.zero_grad()
+        out, par = ex.execute_rows(x, ops, None, f, batched_heads=batched)
+        ((out * wgt).sum() + par.sum()).backward()
+        res.append((out.detach().cpu(), par.detach().cpu(), x.grad.cpu(), f.grad.cpu(),
+                    {n: p.grad.clone().cpu() for n, p in ex.named_parameters() if p.grad is not None}))
+    a, b = res
+    assert max_abs(a[0], b[0]) <= TOL_PIX and max_abs(a[1], b[1]) <= 1e-5
+    assert rel_err(b[2], a[2]) <= TOL_GRAD and rel_err(b[3], a[3]) <= TOL_GRAD
+    assert set(a[4]) == set(b[4])
+    for n in a[4]:
+        assert rel_err(b[4][n], a[4][n], atol=1e-6) <= TOL_GRAD, n
