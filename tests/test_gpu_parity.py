@@ -249,7 +249,7 @@ def test_score_candidates_oracle(TF):
         targets = torch.rand(T, 3, H, W, generator=g)
         cs, co, cp = [], [], []
         for s in range(S):
-            for op in [0, 1, 2, 3, 5, 6, 8, 9, 7]:
+            for op in [0, 1, 2, 3, 5, 6, 8, 9, 7, 10, 11, 12]:
                 for rep in range(2 if s != 1 else 1):
                     cs.append(s); co.append(op)
                     row = torch.zeros(24); p = sample_params(op, 1, g)[0]; row[:p.numel()] = p
