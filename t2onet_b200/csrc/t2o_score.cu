@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "t2o_common.cuh"
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         if (!any) return;
     }
 
+    const bool coop = a.nsplit == 1 && cend - cbeg <= SCORE_NW;      // few candidates: all warps share each candidate's tile
+
     float *sS = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
     float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sS) + ((3 * srows * spitch * 4 + 127) & ~127));
     const size_t plane = (size_t)H * W;
@@ -106,6 +109,11 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
             mbar_expect_tx(&bar, bytes);
             tma_load_4d(sS, &tm_state, &bar, x0 - HX, y0 - 1, 0, s);
             tma_load_4d(sT, &tm_target, &bar, x0, y0, 0, t_idx);
+        }
+        // few candidates: their tables are built while the tiles are in flight
+        if (coop && warp < cend - cbeg && lane == 0) {
+            const int op = a.cand_op[cbeg + warp];
+            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
         }
         // bounded wait: a broken descriptor must fail loudly, not hang the GPU
         bool done = false;
@@ -123,6 +131,10 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
             const int c = i / (TH * TW), r = (i / TW) % TH, col = i % TW;
             const int y = y0 + r, x = x0 + col;
             sT[i] = (y < H && x < W) ? __ldg(tb + c * plane + (size_t)y * W + x) : 0.0f;
+        }
+        if (coop && warp < cend - cbeg && lane == 0) {
+            const int op = a.cand_op[cbeg + warp];
+            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
         }
         __syncthreads();
     }
@@ -198,16 +210,12 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         return sum;
     };
 
-    if (a.nsplit == 1 && cend - cbeg <= SCORE_NW) {
+    if (coop) {
         // Few candidates (the Nelder-Mead rounds: at most one per operator and state): warp w builds the table of
         // candidate w, then ALL warps share every candidate's tile (warp w takes groups w*32 + lane, + 256, ...) and
         // the per-warp sums are added in warp order -- instead of one warp per candidate and the others idle.
         const int ncand = cend - cbeg;
-        if (warp < ncand && lane == 0) {
-            const int op = a.cand_op[cbeg + warp];
-            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
-        }
-        __syncthreads();
+        __syncthreads();                 // the tables (built above, while the tiles were in flight)
         for (int c = 0; c < ncand; ++c) {
             const int op = a.cand_op[cbeg + c];
             if (op == OP_SKIP) continue;
@@ -304,7 +312,7 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
     const int vec = (W % 4 == 0) ? 4 : 1;
     // tile: up to 128 px wide, 32 rows (state 3x34x136 + target 3x32x128 floats = 105 KB -> 2 CTAs / SM)
     int TW = W < 128 ? (W + vec - 1) / vec * vec : 128;
-    int TH = H < 32 ? H : 32;
+    int TH = H < 32 ? H : 32;          // (16- and 8-row tiles measured slower in every regime: the cost is per CTA)
     a.TH = TH; a.TW = TW;
     a.tiles_x = (W + TW - 1) / TW;
     a.ntiles = a.tiles_x * ((H + TH - 1) / TH);
