@@ -227,6 +227,13 @@ T2O_HD void build_table(int op, const float *p, int L, float *tab) {
     }
 }
 
+// The same split in three: part c builds the c-th curve of a color operator, part 0 everything else -- so that three
+// threads per operator share the one table whose construction is long (3 x 9 segments, each with a division).
+T2O_HD void build_table_part(int op, int part, const float *p, int L, float *tab) {
+    if (op == OP_COLOR) build_curve(p + part * L, L, tab + part * CT);
+    else if (part == 0) build_table(op, p, L, tab);
+}
+
 // ---------------------------------------------------------------- blend + clamp (models/operators.py:129-130)
 template <bool HM>
 T2O_HD float blend(float y, float x, float m) { return HM ? fmaf(y, m, x * (1.0f - m)) : y; }

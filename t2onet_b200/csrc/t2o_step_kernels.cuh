@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
 
-    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
+    if (tid < 3 * n) build_table_part(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, sh.tabs[tid / 3]);
     __syncthreads();
 
     // dynamic shared memory: [staging slots: image 3 x SNT vectors, upstream 3 x SNT vectors][tape]
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constan
     const int ntp = sp > 1 ? sp - 1 : 0;
     V *tapeQ = reinterpret_cast<V *>(rings + NRING * RINGF) + ntp * RING * TSLOT + tid;      // [(k-sp-1)][c][SNT]
     for (int i = tid; i < NRING * RINGF; i += SNT) rings[i] = 0.0f;
-    if (tid < n) build_table(ch.op[tid], a.params + (size_t)b * a.pstride + ch.poff[tid], L, sh.tabs[tid]);
+    if (tid < 3 * n) build_table_part(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, sh.tabs[tid / 3]);
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
