@@ -634,16 +634,68 @@ def extras(TF, dev, wl):
     return ex
 
 
+def run_planner_c3(args):
+    """BASELINE config 3 in full: greedy/beam operation planning (the loop of preprocess/gen_greedy_seqs_FiveK.py) over 1000
+    synthetic 3x128x128 image pairs, beam width 8, the six global operators, Nelder-Mead -- image-sharded over the ranks,
+    64 pairs in lock-step per beam_search_batch call.  `python bench.py --workload c3 [--gpus N]`; one JSON line."""
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    import t2onet_b200 as T
+    from t2onet_b200 import planner
+    names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+    exe = T.Executor(T.default_options()).to(dev)
+    NPAIRS, BATCH = 1000, 64
+    mine = list(range(rank, NPAIRS, world))
+    img, tgt, _ = make_batch(8, 128, 128, 3010, dev)
+    planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2)           # warm-up (kernels, graphs)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.time()
+    cnt, steps, per_batch = [0], 0, []
+    for c0 in range(0, len(mine), BATCH):
+        idx = mine[c0:c0 + BATCH]
+        tb = time.time()
+        img, tgt, _ = make_batch(len(idx), 128, 128, 3010 + 7 * idx[0], dev)
+        res = planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2, counter=cnt)
+        steps += sum(len(r[0][0]) for r in res)
+        per_batch.append(round(time.time() - tb, 2))
+    torch.cuda.synchronize()
+    t = torch.tensor([time.time() - t0, float(cnt[0]), float(steps)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t = torch.stack([tmax[0], tsum[1], tsum[2]])
+    if rank == 0:
+        sec, cand = t[0].item(), int(t[1].item())
+        print(json.dumps({'metric': 'planner candidates/s', 'value': cand / sec, 'unit': 'candidates/s', 'n_gpus': world,
+                          'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'seconds': sec, 'pairs_per_s': NPAIRS / sec, 'rank0_seconds_per_batch': per_batch, 'candidates': cand, 'mean_steps': t[2].item() / NPAIRS,
+                          'config': {'workload': 'C3: 1000 pairs of 3x128x128, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, '
+                                                 'Nelder-Mead; image-sharded, %d pairs in lock-step per call' % BATCH}}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS) + ['c3'])
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
+    if args.workload == 'c3':
+        return run_planner_c3(args)
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
         run_reference(args, wl)
