@@ -1,35 +1,46 @@
-"""SSIM oracle -- TEST INFRASTRUCTURE ONLY: the pytorch_ssim recipe of the reference's utils/ssim/__init__.py:8-41
-restated op for op (torch CPU fp32)."""
-from math import exp
+"""SSIM oracle -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+CPU restatement (torch fp32) of the SSIM the reference's evaluation uses: utils/ssim/__init__.py:8-41, called as
+`ssim(img1, img2)` from utils/eval.py:57-60.  Same arithmetic in the same order, so the values are bit-identical to the
+reference's (asserted when tests/golden/ssim.npz is recorded, oracle/make_ssim_golden.py):
+
+  * window: w1[x] = exp(-(x - 5)^2 / (2 * 1.5^2)) for x = 0..10 evaluated in Python floats, stored as float32 and
+    normalised by its float32 sum (:8-10); the 2-D window is the float32 outer product w1 w1^T, one copy per channel
+    (:13-17);
+  * five depthwise convolutions with zero padding 5 -- of a, b, a*a, b*b, a*b (:20-29);
+  * map = (2 mu_a mu_b + C1)(2 cov + C2) / ((mu_a^2 + mu_b^2 + C1)(var_a + var_b + C2)), C1 = 0.01^2, C2 = 0.03^2 (:31-34);
+  * mean over everything, or per image (:36-39).
+"""
+import math
 
 import torch
 import torch.nn.functional as F
 
-
-def gaussian(window_size, sigma):
-    """utils/ssim/__init__.py:8-10"""
-    gauss = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
-    return gauss / gauss.sum()
+WINDOW, SIGMA = 11, 1.5
+C1, C2 = 0.01 ** 2, 0.03 ** 2
 
 
-def create_window(window_size, channel):
-    """utils/ssim/__init__.py:13-17"""
-    _1D_window = gaussian(window_size, 1.5).unsqueeze(1)
-    _2D_window = _1D_window.mm(_1D_window.t()).float().unsqueeze(0).unsqueeze(0)
-    return _2D_window.expand(channel, 1, window_size, window_size).contiguous()
+def window_2d(channels, like):
+    taps = [math.exp(-(x - WINDOW // 2) ** 2 / float(2 * SIGMA ** 2)) for x in range(WINDOW)]
+    w1 = torch.Tensor(taps)
+    w1 = w1 / w1.sum()
+    w2 = torch.outer(w1, w1).float()                      # == w1[:, None].mm(w1[None, :]): one product per element
+    return w2.expand(channels, 1, WINDOW, WINDOW).contiguous().type_as(like)
 
 
-def ssim(img1, img2, window_size=11, size_average=True):
-    """utils/ssim/__init__.py:19-41 via :63-73"""
-    channel = img1.size(1)
-    window = create_window(window_size, channel).type_as(img1)
-    pad = window_size // 2
-    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
-    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
-    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
-    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
-    C1, C2 = 0.01 ** 2, 0.03 ** 2
-    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
-    return ssim_map.mean() if size_average else ssim_map.mean(1).mean(1).mean(1)
+def _blur(x, w):
+    return F.conv2d(x, w, padding=WINDOW // 2, groups=x.size(1))
+
+
+def ssim(a, b, window_size=WINDOW, size_average=True):
+    assert window_size == WINDOW
+    w = window_2d(a.size(1), a)
+    mu_a, mu_b = _blur(a, w), _blur(b, w)
+    mu_aa, mu_bb, mu_ab = mu_a.pow(2), mu_b.pow(2), mu_a * mu_b
+    var_a = _blur(a * a, w) - mu_aa
+    var_b = _blur(b * b, w) - mu_bb
+    cov = _blur(a * b, w) - mu_ab
+    ssim_map = ((2 * mu_ab + C1) * (2 * cov + C2)) / ((mu_aa + mu_bb + C1) * (var_a + var_b + C2))
+    if size_average:
+        return ssim_map.mean()
+    return ssim_map.mean(1).mean(1).mean(1)
