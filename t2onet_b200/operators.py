@@ -45,6 +45,7 @@ class Operator(nn.Module):
     """models/operators.py:26-183.  img passed in must be RGB in [0, 1], (bs, 3, h, w), float32, CUDA."""
 
     op_id = None   # kernel operator id (= Executor index where one exists)
+    SHORT_NAME, N_PARAMS = None, None
 
     def __init__(self, cfg):
         super(Operator, self).__init__()
@@ -54,11 +55,14 @@ class Operator(nn.Module):
             raise NotImplementedError('discrete operator parameters (cfg.discrete_param) are out of scope; '
                                       'the reference default is 0 (options/fiveK_base_options.py:41)')
         self.channels = 2 * cfg.hidden_size
-        self.num_op_param = None
-        self.short_name = None
         self.op_param = None
         self.param_sample_flag = False
         self.curve_steps = getattr(cfg, 'curve_steps', 8)
+        # subclasses declare SHORT_NAME and N_PARAMS (an int, or a function of cfg); the FC head is built right away
+        self.short_name = self.SHORT_NAME
+        self.num_op_param = self.N_PARAMS(cfg) if callable(self.N_PARAMS) else self.N_PARAMS
+        if self.num_op_param is not None:
+            self.setup()
 
     def setup(self):
         """must be called by child class (models/operators.py:43-55)"""
@@ -137,11 +141,7 @@ class ExposureOperator(Operator):
     """models/operators.py:186-222"""
     op_id = TF.OP_EXPOSURE
 
-    def __init__(self, cfg):
-        super(ExposureOperator, self).__init__(cfg)
-        self.short_name = 'exposure'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'exposure', 1
 
     def op_param_regressor(self, features):
         bnd = self.cfg.exposure_range
@@ -155,11 +155,7 @@ class ContrastOperator(Operator):
     """models/operators.py:224-257"""
     op_id = TF.OP_CONTRAST
 
-    def __init__(self, cfg):
-        super(ContrastOperator, self).__init__(cfg)
-        self.short_name = 'contrast'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'contrast', 1
 
     def op_param_regressor(self, features):
         return torch.tanh(features)
@@ -172,11 +168,7 @@ class BrightnessOperator(Operator):
     """models/operators.py:259-295"""
     op_id = TF.OP_BRIGHTNESS
 
-    def __init__(self, cfg):
-        super(BrightnessOperator, self).__init__(cfg)
-        self.short_name = 'brightness'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'brightness', 1
 
     def op_param_regressor(self, features):
         bnd = self.cfg.brightness_range
@@ -190,12 +182,8 @@ class SharpnessOperator(Operator):
     """models/operators.py:332-370"""
     op_id = TF.OP_SHARPNESS
 
-    def __init__(self, cfg):
-        super(SharpnessOperator, self).__init__(cfg)
-        self.short_name = 'sharpness'
-        self.num_op_param = 1
-        self.setup()
-        self.kernel = torch.tensor([[[[0, -1, 0], [-1, 4, -1], [0, -1, 0]]]], dtype=torch.float)
+    SHORT_NAME, N_PARAMS = 'sharpness', 1
+    kernel = torch.tensor([[[[0, -1, 0], [-1, 4, -1], [0, -1, 0]]]], dtype=torch.float)      # (models/operators.py:338; the kernels' stencil)
 
     def op_param_regressor(self, features):
         return torch.sigmoid(features) * self.cfg.sharpness_range
@@ -209,11 +197,7 @@ class SaturationOperator(Operator):
     """models/operators.py:454-491"""
     op_id = TF.OP_SATURATION
 
-    def __init__(self, cfg):
-        super(SaturationOperator, self).__init__(cfg)
-        self.short_name = 'saturation'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'saturation', 1
 
     def op_param_regressor(self, features):
         return torch.tanh(F.relu(features)) * self.cfg.saturation_range[1] + \
@@ -227,11 +211,7 @@ class WhiteOperator(Operator):
     """models/operators.py:494-524"""
     op_id = TF.OP_WHITE
 
-    def __init__(self, cfg):
-        super(WhiteOperator, self).__init__(cfg)
-        self.short_name = 'color_bg'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'color_bg', 1
 
     def op_param_regressor(self, features):
         return torch.sigmoid(features)
@@ -244,11 +224,7 @@ class ImprovedWhiteBalanceOperator(Operator):
     """models/operators.py:527-555"""
     op_id = TF.OP_WHITEBALANCE
 
-    def __init__(self, cfg):
-        super(ImprovedWhiteBalanceOperator, self).__init__(cfg)
-        self.short_name = 'whitebalance'
-        self.num_op_param = 3
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'whitebalance', 3
 
     def op_param_regressor(self, features):
         log_wb_range = 0.5
@@ -267,12 +243,11 @@ class ToneOperator(Operator):
     """models/operators.py:557-591"""
     op_id = TF.OP_TONE
 
-    def __init__(self, cfg):
-        super(ToneOperator, self).__init__(cfg)
-        self.curve_steps = cfg.curve_steps
-        self.short_name = 'tone'
-        self.num_op_param = cfg.curve_steps
-        self.setup()
+    SHORT_NAME = 'tone'
+
+    @staticmethod
+    def N_PARAMS(cfg):
+        return cfg.curve_steps
 
     def op_param_regressor(self, features):
         return features
@@ -286,12 +261,11 @@ class ColorOperator(Operator):
     """models/operators.py:593-622"""
     op_id = TF.OP_COLOR
 
-    def __init__(self, cfg):
-        super(ColorOperator, self).__init__(cfg)
-        self.curve_steps = cfg.curve_steps
-        self.short_name = 'hue'
-        self.num_op_param = 3 * cfg.curve_steps
-        self.setup()
+    SHORT_NAME = 'hue'
+
+    @staticmethod
+    def N_PARAMS(cfg):
+        return 3 * cfg.curve_steps
 
     def op_param_regressor(self, features):
         return features
@@ -305,11 +279,7 @@ class BNWOperator(Operator):
     """models/operators.py:298-329 (no Executor slot): lerp(img, luminance, p)"""
     op_id = TF.OP_BNW
 
-    def __init__(self, cfg):
-        super(BNWOperator, self).__init__(cfg)
-        self.short_name = 'black&white'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'black&white', 1
 
     def op_param_regressor(self, features):
         return torch.sigmoid(features)
@@ -322,11 +292,7 @@ class BlurOperator(Operator):
     """models/operators.py:373-411 (no Executor slot): lerp(img, 3x3 Gaussian(sigma 2, zero padding) * img, p)"""
     op_id = TF.OP_BLUR
 
-    def __init__(self, cfg):
-        super(BlurOperator, self).__init__(cfg)
-        self.short_name = 'blur'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'blur', 1
 
     def op_param_regressor(self, features):
         return torch.sigmoid(features)
@@ -341,11 +307,7 @@ class HueOperator(Operator):
     batch of one; here every batch row takes its own parameter."""
     op_id = TF.OP_HUE
 
-    def __init__(self, cfg):
-        super(HueOperator, self).__init__(cfg)
-        self.short_name = 'hue_'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'hue_', 1
 
     def op_param_regressor(self, features):
         return features
@@ -359,11 +321,7 @@ class InpaintOperator(Operator):
     deep-CNN operator).  The stub keeps the module and checkpoint names."""
     op_id = TF.OP_INPAINT
 
-    def __init__(self, cfg):
-        super(InpaintOperator, self).__init__(cfg)
-        self.short_name = 'inpaint_obj'
-        self.num_op_param = 1
-        self.setup()
+    SHORT_NAME, N_PARAMS = 'inpaint_obj', 1
 
     def op_param_regressor(self, features):
         return torch.zeros((features.shape[0], self.num_op_param), requires_grad=True, device=features.device)
