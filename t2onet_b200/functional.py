@@ -551,12 +551,18 @@ class DeviceNelderMead:
         while self.rounds < limit and self.active() > 0:
             if use_graph and graph is None:
                 # the rounds are identical launches over fixed buffers: record them once, replay from now on
+                # (capture_begin / capture_end directly: torch.cuda.graph() would also run gc.collect() and empty the
+                # allocator cache at every capture -- tens of milliseconds per planner step; nothing is allocated here)
                 side = torch.cuda.Stream(self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):         # _round() launches on the capturing stream
-                    for _ in range(check_every):
-                        self._round()
+                with torch.cuda.stream(side):                      # _round() launches on the capturing stream
+                    graph.capture_begin()
+                    try:
+                        for _ in range(check_every):
+                            self._round()
+                    finally:
+                        graph.capture_end()
                 torch.cuda.current_stream(self.dev).wait_stream(side)
             if graph is not None:
                 graph.replay()
