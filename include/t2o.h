@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define T2O_VERSION 103          /* major*100 + minor */
+#define T2O_VERSION 104          /* major*100 + minor */
 #define T2O_MAX_CHAIN 8          /* operators fused in one launch */
 #define T2O_MAX_CURVE_STEPS 8    /* cfg.curve_steps (options/fiveK_base_options.py:50) */
 #define T2O_MAX_OP_PARAMS 24     /* color: 3 * curve_steps */
@@ -167,6 +167,20 @@ int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_p
 size_t t2o_ssim_workspace_bytes(int B, int C, int H, int W);
 int t2o_ssim_sum(const float *img1, const float *img2, float *ssim_sum, int B, int C, int H, int W,
                  void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
+ * 8-bit image <-> float32 tensor conversions (utils/visual_utils.py of the reference), so that images cross PCIe as the
+ * uint8 arrays they are and the x / 255 happens in HBM.  Bit-identical to the reference's host arithmetic:
+ *   t2o_u8_to_f32      dst[i] = float(src[i]) / 255  (IEEE division, utils/visual_utils.py:46,67)       any layout, n values
+ *   t2o_f32_to_u8      dst[i] = uint8(src[i] * 255)  (truncation, utils/visual_utils.py:55-57; clamped to [0, 255])
+ *   t2o_img2tensor     img2tensor (utils/visual_utils.py:61-70): (N, H, W, 3) BGR uint8 -> (N, 3, H, W) RGB float32 / 255
+ *   t2o_tensor2img     tensor2img (utils/visual_utils.py:50-58): (N, 3, H, W) RGB float32 -> (N, H, W, 3) BGR uint8
+ * The flat pair needs 16-byte aligned pointers; the float side of the layout pair too.
+ */
+int t2o_u8_to_f32(const uint8_t *src, float *dst, int64_t n, t2o_stream_t stream);
+int t2o_f32_to_u8(const float *src, uint8_t *dst, int64_t n, t2o_stream_t stream);
+int t2o_img2tensor(const uint8_t *hwc_bgr, float *chw_rgb, int N, int H, int W, t2o_stream_t stream);
+int t2o_tensor2img(const float *chw_rgb, uint8_t *hwc_bgr, int N, int H, int W, t2o_stream_t stream);
 
 /*
  * Planner candidate scoring (the inner loop of get_param_naive / beam_search,

@@ -93,13 +93,14 @@ def get_param(I0, I1, operation, executor, optimizer='Nelder-Mead', counter=None
 
 
 def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step,
-                err, dist_type, optimizer, replace=False, variant='default', eps=0.05, counter=None):
+                err, dist_type, optimizer, replace=False, variant='default', eps=0.05, counter=None, trace=None):
     """utils/beam_search.py:196-264.
 
     variant='fixed_order'  -> utils/beam_search_fixed_order.py:225-293 (one operator per step)
     variant='eps_greedy'   -> utils/beam_search_eps_greedy.py:238-309 (keeps every candidate,
                               random beams with probability eps, never clears no_update_flag)
-    Returns (actions, Is) with the reference's nesting.
+    Returns (actions, Is) with the reference's nesting.  `trace`: a list that receives one record per step (every
+    candidate evaluated + the argsort input / output), in the format of oracle/make_planner_golden_full.py.
     """
     assert dist_type == 'L1'
     min_dist = float('inf')
@@ -108,6 +109,7 @@ def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, 
     for i in range(max_step):
         all_candidates, I_tmp_list, tmp_min_dists = [], [], []
         no_update_flag, finish_flag = True, False
+        step_cands = []
         for j, I in enumerate(I_buff):
             step_ops = [operations[i]] if variant == 'fixed_order' else operations
             for operation in step_ops:
@@ -116,6 +118,8 @@ def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, 
                 param, _ = get_param(I, I_gt, operation, executor, optimizer, counter)
                 I_out = execute(I, operation, param, executor)
                 dist = get_dist(I_out, I_gt, dist_type).item()
+                step_cands.append({'parent': j, 'op': int(operation), 'param': [float(v) for v in param[0].tolist()],
+                                   'dist': float(dist)})
                 if variant == 'eps_greedy' or dist < min_dist:
                     tmp_min_dists.append(dist)
                     cand = [sequences[j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out.cpu())], dist]
@@ -131,6 +135,9 @@ def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, 
             I_tmp_list += I_buff
         dists = np.array([v[1] for v in all_candidates])
         order = np.argsort(dists)
+        if trace is not None:
+            trace.append({'candidates': step_cands, 'sort_dists': [float(v) for v in dists],
+                          'sort_order': [int(v) for v in order]})
         if variant == 'eps_greedy' and random.random() < eps:
             sequences = random.choices(all_candidates, k=beam_size)
         else:

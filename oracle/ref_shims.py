@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference from /root/reference -- TEST INFRASTRUCTURE ONLY.
+"""Import the UNMODIFIED reference -- TEST INFRASTRUCTURE ONLY.
 
-Only usable in the authoring container (the GPU box has no /root/reference); used
-by ``oracle/make_golden.py`` to record golden vectors and by the optional
-``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
-Nothing in the product, ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this.
+Two places hold it: the source tree /root/reference (authoring container only; ``oracle/make_*golden*.py`` record
+the golden vectors from it) and the sourceless byte-compiled tree ``oracle/_ref/t2onet`` that ``oracle/build_ref.py``
+makes from it (git-ignored; it travels to the GPU box, where ``tests/test_gpu_actor.py`` runs the reference's own
+Actor on the new Executor and ``bench.py --impl reference`` times the reference itself).  ``T2O_REFERENCE_ROOT``
+overrides both.  The product never imports this module.
 
 The reference needs three import shims and one class stub:
 
@@ -19,10 +20,27 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('T2O_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    cands = [os.environ.get('T2O_REFERENCE_ROOT'), '/root/reference', os.path.join(_HERE, '_ref', 't2onet')]
+    for c in cands:
+        if c and (os.path.isfile(os.path.join(c, 'models', 'operators.py')) or
+                  os.path.isfile(os.path.join(c, 'models', 'operators.pyc'))):
+            return c
+    return cands[0] or '/root/reference'
+
+
+REF_ROOT = _find_root()
 
 
 def available():
+    return os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.py')) or \
+        os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.pyc'))
+
+
+def is_source_tree():
     return os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.py'))
 
 
@@ -86,3 +104,42 @@ def load():
         beam_search_eps_greedy=beam_search_eps_greedy,
         options=lambda: BaseOptions().parser.parse_args([]))
     return _loaded
+
+
+def actor_options(**over):
+    """The option namespace experiments/t2onet/train_seq2seqL1.py builds (options/seq2seqGAN_train_options.py defaults),
+    with the vocabulary directory pointing into the reference tree."""
+    load()
+    from options.seq2seqGAN_train_options import TrainOptions
+    opt = TrainOptions().parser.parse_args([])
+    opt.vocab_dir = os.path.join(REF_ROOT, 'data', 'language')
+    for k, v in over.items():
+        setattr(opt, k, v)
+    return opt
+
+
+def build_actor(opt, executor_cls=None, seed=10):
+    """models/actor.py:Actor of the reference, unmodified.  `executor_cls` stands in for the name `Executor` the module
+    imported from executors.executor (models/actor.py:11,49) -- this is the whole switch a user of the reference makes
+    (INTEGRATION.md).  The GloVe table (an .h5 file the loader needs h5py for, utils/text_utils.py:70-73) is replaced
+    by a seeded random table of the same shape; everything else is the reference's own code and initialisation."""
+    import torch
+    load()
+    import models.actor as actor_mod
+    from utils.text_utils import load_vocab
+    n_vocab = len(load_vocab(opt.vocab_dir, opt.dataset, opt.session)[0])
+
+    def load_embedding(path):
+        g = torch.Generator().manual_seed(1234)
+        return torch.randn(n_vocab - 4, opt.word_vec_dim, generator=g) * 0.3
+
+    actor_mod.load_embedding = load_embedding
+    saved = actor_mod.Executor
+    if executor_cls is not None:
+        actor_mod.Executor = executor_cls
+    try:
+        torch.manual_seed(seed)
+        actor = actor_mod.Actor(opt)
+    finally:
+        actor_mod.Executor = saved
+    return actor

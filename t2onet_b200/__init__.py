@@ -7,6 +7,7 @@ Public surface (mirrors the reference's Python API):
     t2onet_b200.executor    Executor                       (executors/executor.py)
     t2onet_b200.planner     beam_search, get_dist, ...     (utils/beam_search*.py)
     t2onet_b200.plans       planner records on disk + reader (preprocess/gen_greedy_seqs_FiveK.py, datasets/FiveKdataset.py)
+    t2onet_b200.visual_utils  img2tensor / tensor2img on the device (utils/visual_utils.py)
     t2onet_b200.functional  chain / chain_l1 / score_candidates over the C-ABI (include/t2o.h)
 """
 from . import functional  # noqa: F401
@@ -16,6 +17,7 @@ from .operators import (Operator, ExposureOperator, ContrastOperator, Brightness
                         InpaintOperator, BNWOperator, BlurOperator, HueOperator)
 from . import planner  # noqa: F401
 from . import plans  # noqa: F401
+from . import visual_utils  # noqa: F401
 from ._lib import T2OError, lib  # noqa: F401
 
 __version__ = '0.1.0'

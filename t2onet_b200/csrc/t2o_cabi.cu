@@ -34,6 +34,10 @@ int nm_advance(const t2o_nm_state *st, int P, const float *l1_sum, float numel, 
 size_t ssim_workspace_bytes(int B, int C, int H, int W);
 int ssim_sum(const float *img1, const float *img2, float *out, int B, int C, int H, int W, void *ws, size_t ws_bytes,
              cudaStream_t stream);
+int convert_u8_to_f32(const uint8_t *src, float *dst, long long n, cudaStream_t stream);
+int convert_f32_to_u8(const float *src, uint8_t *dst, long long n, cudaStream_t stream);
+int convert_img2tensor(const uint8_t *hwc_bgr, float *chw_rgb, int N, int H, int W, cudaStream_t stream);
+int convert_tensor2img(const float *chw_rgb, uint8_t *hwc_bgr, int N, int H, int W, cudaStream_t stream);
 const char *last_cuda_error();
 }  // namespace t2o
 
@@ -135,6 +139,22 @@ size_t t2o_ssim_workspace_bytes(int B, int C, int H, int W) {
 int t2o_ssim_sum(const float *img1, const float *img2, float *ssim_sum, int B, int C, int H, int W, void *workspace,
                  size_t workspace_bytes, t2o_stream_t stream) {
     return t2o::ssim_sum(img1, img2, ssim_sum, B, C, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_u8_to_f32(const uint8_t *src, float *dst, int64_t n, t2o_stream_t stream) {
+    return t2o::convert_u8_to_f32(src, dst, (long long)n, (cudaStream_t)stream);
+}
+
+int t2o_f32_to_u8(const float *src, uint8_t *dst, int64_t n, t2o_stream_t stream) {
+    return t2o::convert_f32_to_u8(src, dst, (long long)n, (cudaStream_t)stream);
+}
+
+int t2o_img2tensor(const uint8_t *hwc_bgr, float *chw_rgb, int N, int H, int W, t2o_stream_t stream) {
+    return t2o::convert_img2tensor(hwc_bgr, chw_rgb, N, H, W, (cudaStream_t)stream);
+}
+
+int t2o_tensor2img(const float *chw_rgb, uint8_t *hwc_bgr, int N, int H, int W, t2o_stream_t stream) {
+    return t2o::convert_tensor2img(chw_rgb, hwc_bgr, N, H, W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

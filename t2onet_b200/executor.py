@@ -104,7 +104,7 @@ class Executor(nn.Module):
                 p = self._row_param(Op, features, specified_param, has_noise, bs, dev)
                 params = torch.where((ops_t == ind).view(bs, 1), p, params)
         else:
-            ops_l = [int(v) for v in ops_t.tolist()]
+            ops_l = [max(int(v), -1) for v in ops_t.tolist()]      # op_ind < 0: identity (executors/executor.py:44)
             params = torch.zeros(bs, TF.PARAM_SLOT, device=dev)
             for ind in sorted(set(ops_l)):
                 if ind < 0:

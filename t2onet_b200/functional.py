@@ -294,10 +294,12 @@ PARAM_SLOT = _lib.MAX_OP_PARAMS      # the Actor's zero-padded parameter rows (m
 def _prep_row_ops(row_ops, B, device):
     """-> (device int32 (B, K) tensor, ctypes host copy or None).  A list / CPU tensor is known on the host (validated
     up front, any K); a CUDA tensor stays on the device (K == 1, no host sync)."""
+    # every negative id is the identity, as Executor.execute treats op_ind < 0 (executors/executor.py:44): the Actor
+    # passes vocabulary id - 3, i.e. -3 / -2 / -1 for <NONE> / <START> / <END> (models/actor.py:146,165)
     if isinstance(row_ops, torch.Tensor) and row_ops.is_cuda:
-        t = row_ops.reshape(B, -1).to(torch.int32).contiguous()
+        t = row_ops.reshape(B, -1).to(torch.int32).clamp_min(OP_IDENTITY).contiguous()
         return t, None
-    t = torch.as_tensor(row_ops, dtype=torch.int32).reshape(B, -1).contiguous()
+    t = torch.as_tensor(row_ops, dtype=torch.int32).reshape(B, -1).clamp_min(OP_IDENTITY).contiguous()
     host = _lib.int_array(t.flatten().tolist())
     return t.to(device, non_blocking=True), host
 

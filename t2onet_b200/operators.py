@@ -114,10 +114,19 @@ class Operator(nn.Module):
             param = param + param_noise
             param = torch.clamp(param, self.lb, self.ub)
         self.param = param
-        self.mask = mask
+        self._mask, self._mask_like = mask, (img if mask is None else None)
         if param.device != img.device:
             param = param.to(img.device)
         return TF.chain(img, [self.op_id], [param.float()], mask, self.curve_steps)
+
+    @property
+    def mask(self):
+        """The mask of the last execute (models/operators.py:123-125 stores ones_like(img) when none was given; the
+        kernels need no such tensor, so it is only materialised if somebody reads the attribute)."""
+        m = getattr(self, '_mask', None)
+        if m is None and getattr(self, '_mask_like', None) is not None:
+            m = torch.ones_like(self._mask_like)
+        return m
 
     def param_loss_fn(self):
         return F.mse_loss

@@ -28,6 +28,15 @@ from .nelder_mead import nelder_mead, run_lockstep
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 NM_INIT_ZERO, NM_INIT_ONE = (0, 1, 2, 6), (3, 5)
+# utils/beam_search_eps_greedy.py:24 seeds the global `random` module at import (random.seed(0)) and draws from it
+# (:299-300).  The drop-in keeps its own generator in the same state instead of re-seeding the caller's global one:
+# the draws are identical as long as nothing else consumes the reference's global stream.
+_eps_rng = random.Random(0)
+
+
+def eps_greedy_seed(seed=0):
+    """Re-seed the eps-greedy planner's generator (what re-importing utils/beam_search_eps_greedy.py does)."""
+    _eps_rng.seed(seed)
 
 
 def get_dist(x1, x2, dist_type='L1'):
@@ -235,12 +244,16 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor):
 
 
 def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type='L1',
-                      optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None):
+                      optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None,
+                      trace=None):
     """`beam_search` (utils/beam_search.py:196-264) for M image pairs at once: I_0, I_gt (M,3,H,W).
 
     Every pair runs the reference's beam search unchanged; what is shared is the work: all (pair, beam state,
     operator) fits of a step advance in lock-step on the device and are applied / scored by one launch.
-    Returns a list of M (actions, Is) tuples, each exactly what `beam_search` returns for that pair."""
+    Returns a list of M (actions, Is) tuples, each exactly what `beam_search` returns for that pair.
+    `trace`: an empty list that receives, per pair, {'steps': [{'candidates': [{'parent', 'op', 'param', 'dist', 'nfev'}],
+    'sort_dists', 'sort_order'}]} -- every candidate evaluated and the array / order of the step's argsort (the
+    transcript format of oracle/make_planner_golden_full.py)."""
     assert dist_type == 'L1', 'only the L1 distance is implemented'
     I_0 = I_0.to(device) if not I_0.is_cuda else I_0
     I_gt = I_gt.to(I_0.device)
@@ -248,6 +261,8 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     numel = float(I_gt[0:1].numel())
     st = [{'min_dist': float('inf'), 'sequences': [[[], float('inf')]], 'I_buff': [I_0[m:m + 1]], 'alive': True}
           for m in range(M)]
+    if trace is not None:
+        trace.extend({'steps': []} for _ in range(M))
     for i in range(max_step):
         live = [m for m in range(M) if st[m]['alive']]
         if not live:
@@ -270,21 +285,23 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
             fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _ in problems],
                                           executor, state_target=state_pair, counter=counter, numel=numel)
             params = [np.asarray(r.x, dtype=np.float64)[None, :] for r in fits]     # (1, n) float64, as the reference's tensors
+            nfevs = [r.nfev for r in fits]
         else:
             params = [get_param(states[s], I_gt[m:m + 1], txt, op, executor, None, dist_type, optimizer)[0]
                       for s, op, m, _ in problems]
+            nfevs = [0] * len(problems)
         # -- apply + score (utils/beam_search.py:230-237)
         outs, dists = _score_outputs([states[s] for s, _, _, _ in problems], [op for _, op, _, _ in problems], params,
                                      [I_gt[m:m + 1] for _, _, m, _ in problems], executor)
         # -- the reference's bookkeeping, pair by pair (utils/beam_search.py:239-259)
         by_pair = {m: [] for m in live}
         for k, (s, op, m, j) in enumerate(problems):
-            by_pair[m].append((j, op, params[k], outs[k], dists[k]))
+            by_pair[m].append((j, op, params[k], outs[k], dists[k], nfevs[k]))
         for m in live:
             S = st[m]
             all_candidates, I_tmp_list, tmp_min_dists = [], [], []
             no_update_flag, finish_flag = True, False
-            for j, operation, param, I_out, dist in by_pair[m]:
+            for j, operation, param, I_out, dist, _ in by_pair[m]:
                 if _variant == 'eps_greedy' or dist < S['min_dist']:
                     tmp_min_dists.append(dist)
                     candidate = [S['sequences'][j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out)], dist]
@@ -300,20 +317,33 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                 I_tmp_list += S['I_buff']
             dists_arr = np.array([v[1] for v in all_candidates])
             order = np.argsort(dists_arr)
-            if _variant == 'eps_greedy' and random.random() < _eps:
-                chosen = random.choices(range(len(all_candidates)), k=beam_size)
+            buf_idx = [int(v) for v in order[:beam_size]]
+            if _variant == 'eps_greedy' and _eps_rng.random() < _eps:
+                # utils/beam_search_eps_greedy.py:299-302: the SEQUENCES are drawn at random (random.choices draws
+                # the same floor(random() * n) indices for a list and for a range), the image buffer stays the sorted one
+                seq_idx = _eps_rng.choices(range(len(all_candidates)), k=beam_size)
             else:
-                chosen = list(order)[:beam_size]
+                seq_idx = buf_idx
+            if trace is not None:
+                trace[m]['steps'].append({
+                    'candidates': [{'parent': j, 'op': int(op), 'param': [float(v) for v in np.asarray(p).reshape(-1)],
+                                    'dist': float(d), 'nfev': int(nf)} for j, op, p, _, d, nf in by_pair[m]],
+                    'sort_dists': [float(v) for v in dists_arr], 'sort_order': [int(v) for v in order]})
             # the kept images are rows of this step's output tensor: copy them out (once) so that it can be freed
-            S['sequences'], S['I_buff'] = [], []
-            for idx in chosen:
-                seq, img = all_candidates[idx], I_tmp_list[idx]
-                if img._base is not None:
-                    img = img.clone()
-                    if seq[0] and seq[0][-1][-1] is I_tmp_list[idx]:
-                        seq = [seq[0][:-1] + [seq[0][-1][:-1] + (img,)], seq[1]]
-                S['sequences'].append(seq)
-                S['I_buff'].append(img)
+            clones = {}
+
+            def own(idx):
+                if idx not in clones:
+                    img = I_tmp_list[idx]
+                    clones[idx] = img.clone() if img._base is not None else img
+                return clones[idx]
+            seqs = []
+            for idx in seq_idx:
+                seq = all_candidates[idx]
+                if seq[0] and seq[0][-1][-1] is I_tmp_list[idx]:
+                    seq = [seq[0][:-1] + [seq[0][-1][:-1] + (own(idx),)], seq[1]]
+                seqs.append(seq)
+            S['sequences'], S['I_buff'] = seqs, [own(idx) for idx in buf_idx]
             if no_update_flag or finish_flag:
                 S['alive'] = False
     results = []

@@ -1,0 +1,96 @@
+"""Compare a planner run with a transcript recorded from the reference (test infrastructure).
+
+Transcript format (oracle/make_planner_golden_full.py; planner.beam_search_batch(trace=...) and the oracle planner emit
+the same): per step, every candidate the planner evaluated -- {'parent' (beam index), 'op', 'param', 'dist'} in
+evaluation order -- plus 'sort_dists' / 'sort_order', the array handed to np.argsort and its result.
+
+The north star's rule: the chosen action sequences must be identical "whenever no candidate scores are tied within
+tolerance".  This module makes the exception checkable instead of asserted: a step of the run under test may keep a
+different beam than the reference only if the REFERENCE'S OWN recorded distances of the two competing candidates (or of
+the candidate and the threshold it was compared with) differ by at most `tie_tol`.  From the first tolerated
+divergence on the two runs explore different states, so the comparison of that pair stops there (its end result is
+still bounded: final distance within `tie_tol` of the reference's)."""
+NAMES = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+CURVE_OPS = (3, 5)
+
+
+def replay_selection(steps, beam, err, variant='default'):
+    """Re-run the reference's bookkeeping (utils/beam_search.py:239-259) over a transcript.
+    Returns per step: {'beam_in': [op-name tuples], 'cands': {(parent seq, op): dist}, 'all': [(seq, dist)] the list
+    that was sorted, 'beam_out': [(seq, dist)], 'min_dist_in': float, 'finish': bool, 'no_update': bool}."""
+    sequences = [((), float('inf'))]
+    min_dist = float('inf')
+    out = []
+    for st in steps:
+        kept, cands = [], {}
+        finish, no_update = False, True
+        for c in st['candidates']:
+            pseq = sequences[c['parent']][0]
+            seq = pseq + (NAMES[c['op']],)
+            cands[(pseq, c['op'])] = c['dist']
+            if variant == 'eps_greedy' or c['dist'] < min_dist:
+                kept.append((seq, c['dist']))
+                if variant != 'eps_greedy':
+                    no_update = False
+                if c['dist'] < err:
+                    finish = True
+        rec = {'beam_in': [s for s, _ in sequences], 'cands': cands, 'min_dist_in': min_dist}
+        if kept:
+            min_dist = min(d for _, d in kept)
+        all_c = kept + (sequences if len(kept) < beam else [])
+        assert len(all_c) == len(st['sort_dists']), 'transcript inconsistent with the selection rule'
+        for (s, d), d2 in zip(all_c, st['sort_dists']):
+            assert d == d2 or (d != d and d2 != d2), 'transcript inconsistent with the selection rule'
+        sequences = [all_c[i] for i in st['sort_order']][:beam]
+        rec.update({'all': all_c, 'beam_out': sequences, 'finish': finish, 'no_update': no_update})
+        out.append(rec)
+    return out
+
+
+def compare_runs(ref_steps, got_steps, beam, err, tie_tol, fit_tol_scalar, fit_tol_curve, variant='default'):
+    """-> (verdict, detail).  verdict: 'exact' (same candidates within the fit tolerances, identical beams at every
+    step, same number of steps), 'tie' (first divergence justified by the reference's own distances; detail says
+    where), or raises AssertionError with the evidence."""
+    R = replay_selection(ref_steps, beam, err, variant)
+    G = replay_selection(got_steps, beam, err, variant)
+    worst = {'scalar': 0.0, 'curve': 0.0}
+    for s in range(max(len(R), len(G))):
+        if s >= len(R) or s >= len(G):
+            # one run stopped earlier: finish_flag / no_update_flag disagreed at step s-1
+            r, g = R[s - 1], G[s - 1]
+            near_err = any(abs(d - err) <= tie_tol for d in r['cands'].values())
+            near_min = any(abs(d - r['min_dist_in']) <= tie_tol for d in r['cands'].values())
+            assert near_err or near_min, ('step count differs without a tie', s, len(R), len(G))
+            return 'tie', 'stopped at step %d vs %d: a candidate within %.0e of err / of the previous minimum' % (len(G), len(R), tie_tol)
+        r, g = R[s], G[s]
+        assert r['beam_in'] == g['beam_in'], ('beams differ entering step %d' % s, r['beam_in'], g['beam_in'])
+        assert set(r['cands']) == set(g['cands']), ('different candidates evaluated at step %d' % s)
+        for key, d_ref in r['cands'].items():
+            kind = 'curve' if key[1] in CURVE_OPS else 'scalar'
+            diff = abs(g['cands'][key] - d_ref)
+            worst[kind] = max(worst[kind], diff)
+            tol = fit_tol_curve if kind == 'curve' else fit_tol_scalar
+            assert diff <= tol, ('candidate distance off', s, key, g['cands'][key], d_ref)
+        rb, gb = [q for q, _ in r['beam_out']], [q for q, _ in g['beam_out']]
+        if rb != gb:
+            # every position where the kept sequences differ must be a tie IN THE REFERENCE'S OWN numbers
+            ref_d = {q: d for q, d in r['all']}
+            ref_d.update({pseq + (NAMES[op],): d for (pseq, op), d in r['cands'].items() if pseq + (NAMES[op],) not in ref_d})
+            ev = []
+            for k in range(max(len(rb), len(gb))):
+                a = rb[k] if k < len(rb) else None
+                b = gb[k] if k < len(gb) else None
+                if a == b:
+                    continue
+                da = ref_d.get(a, r['min_dist_in']) if a is not None else r['min_dist_in']
+                db = ref_d.get(b, r['min_dist_in']) if b is not None else r['min_dist_in']
+                assert abs(da - db) <= tie_tol, ('beam differs at step %d position %d without a tie in the reference' % (s, k),
+                                                 a, da, b, db)
+                ev.append('pos %d: ref %s (%.6f) vs got %s (ref dist %.6f)' % (k, '>'.join(a or ()), da, '>'.join(b or ()), db))
+            return 'tie', 'step %d: %s' % (s, '; '.join(ev))
+        if r['finish'] != g['finish'] or r['no_update'] != g['no_update']:
+            near_err = any(abs(d - err) <= tie_tol for d in r['cands'].values())
+            near_min = any(abs(d - r['min_dist_in']) <= tie_tol for d in r['cands'].values())
+            assert near_err or near_min, ('termination differs without a tie', s)
+            return 'tie', 'step %d: termination flag flipped by a candidate within %.0e of err / the previous minimum' % (s, tie_tol)
+    return 'exact', 'max |dist - ref|: scalar ops %.1e, curve ops %.1e' % (worst['scalar'], worst['curve'])

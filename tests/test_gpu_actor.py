@@ -1,0 +1,151 @@
+"""The reference's own seq2seqL1 Actor (models/actor.py, unmodified, byte-compiled into oracle/_ref by
+oracle/build_ref.py) running on the new Executor: SURVEY.md section 8d C2(ii).
+
+The only switch is the one INTEGRATION.md describes: the name `Executor` that models/actor.py imported from
+executors.executor is bound to t2onet_b200.Executor.  Everything else -- ResNet-18 image encoder, LSTM request encoder,
+attention decoder, divide_op_group + index_select call sites, the training step of
+experiments/t2onet/train_seq2seqL1.py:54-88 -- is the reference's code, executed on the GPU, once on the reference's
+Executor (eager PyTorch operators) and once on the kernels, from the same seed."""
+import pytest
+import torch
+
+from oracle import ref_shims
+from parity_util import TOL_GRAD, TOL_PIX, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_shims.available(), reason='reference tree (oracle/_ref) not built')]
+HEADS = ('brightness_op', 'contrast_op', 'saturation_op', 'color_op', 'tone_op', 'sharpness_op')
+
+
+@pytest.fixture(scope='module')
+def actors():
+    import t2onet_b200 as T
+    opt = ref_shims.actor_options()
+    ref = ref_shims.build_actor(opt, None, seed=10).cuda()
+    new = ref_shims.build_actor(opt, T.Executor, seed=10).cuda()
+    assert type(ref.executor).__module__ == 'executors.executor' and isinstance(new.executor, T.Executor)
+    sr, sn = ref.state_dict(), new.state_dict()
+    assert list(sr.keys()) == list(sn.keys())                       # checkpoints are interchangeable
+    for k in sr:
+        assert torch.equal(sr[k], sn[k]), k                         # same construction order -> same seeded initialisation
+    return opt, ref, new
+
+
+def _batch(opt, B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(4, 200, (B, opt.encoder_max_len), generator=g)
+    x[:, 0] = opt.start_id
+    lens = torch.randint(5, opt.encoder_max_len - 1, (B,), generator=g)
+    for b in range(B):
+        x[b, lens[b]] = opt.end_id
+        x[b, lens[b] + 1:] = opt.null_id
+    img = torch.rand(B, 3, H, W, generator=g) * 0.8 + 0.1
+    tgt = (img * (0.8 + 0.4 * torch.rand(B, 3, 1, 1, generator=g))).clamp(0, 1)
+    return x.cuda(), img.cuda(), tgt.cuda()
+
+
+def _grads(actor):
+    out = {}
+    for name in HEADS:
+        op = getattr(actor.executor, name)
+        for pn, p in op.named_parameters():
+            out['executor.%s.%s' % (name, pn)] = None if p.grad is None else p.grad.detach().clone()
+    for pn, p in actor.decoder.named_parameters():
+        out['decoder.' + pn] = None if p.grad is None else p.grad.detach().clone()
+    return out
+
+
+def _compare_grads(ga, gb, heads_tol, rest_tol):
+    checked = 0
+    for k in ga:
+        assert (ga[k] is None) == (gb[k] is None), k
+        if ga[k] is None or float(ga[k].abs().max()) == 0.0:
+            continue
+        tol = heads_tol if k.startswith('executor.') else rest_tol
+        e = rel_err(gb[k].cpu(), ga[k].cpu())
+        assert e <= tol, (k, e)
+        checked += 1
+    return checked
+
+
+def test_episode_forward_l1_step(actors):
+    """experiments/t2onet/train_seq2seqL1.py:75-88: episode_forward, image at the first <END>, mean L1, backward."""
+    opt, ref, new = actors
+    x, img, tgt = _batch(opt, 16, 64, 64, seed=20)
+    res = []
+    for actor in (ref, new):
+        actor.train()
+        actor.zero_grad()
+        torch.manual_seed(123)                                        # dropout masks and the Categorical sampling
+        _, pred_imgs, pred_ops, _ = actor.episode_forward(x, img, None)
+        bs, max_len = pred_imgs.shape[:2]
+        end = []
+        for b in range(bs):
+            idxs = (pred_ops[b] == opt.end_id).nonzero()
+            end.append(pred_imgs[b, idxs[0][0] if len(idxs) > 0 else max_len - 1])
+        loss = torch.abs(torch.stack(end) - tgt).mean()
+        loss.backward()
+        res.append((pred_ops.clone(), pred_imgs.detach().clone(), loss.item(), _grads(actor)))
+    (ops_r, imgs_r, loss_r, g_r), (ops_n, imgs_n, loss_n, g_n) = res
+    assert torch.equal(ops_r, ops_n)                                  # the sampled operator sequences
+    assert (ops_n == opt.end_id).any() and (ops_n >= 3).any()
+    assert (imgs_r - imgs_n).abs().max().item() <= TOL_PIX
+    assert abs(loss_r - loss_n) <= TOL_PIX, (loss_r, loss_n)
+    # FC-head gradients: the north star's relative 1e-4; the decoder sits behind the ResNet / BatchNorm path, where the
+    # edited pixels' 1e-6 differences are amplified
+    n = _compare_grads(g_r, g_n, TOL_GRAD, 5e-3)
+    assert n >= 20
+
+
+def test_supervised_forward_step_with_padded_rows(actors):
+    """The teacher-forced half of the training loop (train_seq2seqL1.py:54-66): rows shorter than the batch's longest
+    sequence carry <END> / <NONE>, i.e. Executor indices -1 / -3 (models/actor.py:146,165)."""
+    opt, ref, new = actors
+    x, img, tgt = _batch(opt, 8, 32, 32, seed=21)
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    y = torch.zeros(B, 7, dtype=torch.long)
+    y[:, 0] = opt.start_id
+    for b in range(B):
+        n_ops = 1 + b % 4
+        perm = torch.randperm(6, generator=g)[:n_ops]
+        y[b, 1:1 + n_ops] = torch.tensor([3, 4, 5, 6, 8, 9])[perm]
+        y[b, 1 + n_ops] = opt.end_id
+    y = y.cuda()
+    step = (y != opt.null_id).sum(1).max().item()
+    img_y = torch.rand(B, step, 3, 32, 32, generator=g).cuda()
+    gt_params = (torch.rand(B, step - 2, 24, generator=g) * 0.5).cuda()
+    res = []
+    for actor in (ref, new):
+        actor.train()
+        actor.zero_grad()
+        torch.manual_seed(321)
+        pred_imgs, pred_params, pred_logprobs = actor.supervised_forward(x, y, img, img_y, gt_params, mask=None)
+        target = y[:, 1:step].contiguous().view(-1)
+        op_loss = torch.nn.functional.nll_loss(pred_logprobs.view(-1, pred_logprobs.shape[-1]), target)
+        param_loss = torch.nn.functional.mse_loss(pred_params, gt_params[:, :step - 2], reduction='sum') / ((gt_params[:, :step - 2] != 0).sum())
+        loss = op_loss + param_loss + (pred_imgs - img_y[:, :pred_imgs.shape[1]]).abs().mean()
+        loss.backward()
+        res.append((pred_imgs.detach().clone(), pred_params.detach().clone(), loss.item(), _grads(actor)))
+    (imgs_r, prm_r, loss_r, g_r), (imgs_n, prm_n, loss_n, g_n) = res
+    assert (imgs_r - imgs_n).abs().max().item() <= TOL_PIX
+    assert (prm_r - prm_n).abs().max().item() <= 1e-6
+    assert abs(loss_r - loss_n) <= TOL_PIX
+    assert _compare_grads(g_r, g_n, TOL_GRAD, 1e-3) >= 20
+
+
+def test_execute_rows_accepts_the_actors_negative_ids(actors):
+    """executor.execute_rows(img_x, pred_op.view(-1) - 3, ...) with <NONE> / <START> / <END> rows (-3 / -2 / -1):
+    identity rows with zero parameter rows, as Executor.execute's op_ind < 0 branch (executors/executor.py:44-46)."""
+    opt, ref, new = actors
+    _, img, _ = _batch(opt, 6, 16, 24, seed=22)
+    feat = (torch.randn(6, 512) * 0.3).cuda()
+    vocab_ids = torch.tensor([0, 1, 2, 3, 8, 9])
+    for ops in (vocab_ids - 3, (vocab_ids - 3).cuda(), (vocab_ids - 3).tolist()):
+        out, param = new.executor.execute_rows(img, ops, None, features=feat)
+        assert torch.equal(out[:3], img[:3]) and float(param[:3].abs().sum()) == 0.0
+        for b, v in ((3, 0), (4, 5), (5, 6)):
+            o_ref, p_ref = ref.executor.execute(img[b:b + 1], v, None, feat[b:b + 1])
+            assert (out[b:b + 1] - o_ref).abs().max().item() <= TOL_PIX
+            assert (param[b, :p_ref.shape[1]] - p_ref[0]).abs().max().item() <= 1e-6
+    import t2onet_b200.functional as TF
+    assert TF.rows_status(img.device) == 0

@@ -154,14 +154,108 @@ def test_executor_api_and_fc_head_gradients(T):
         assert max_abs(out.detach().cpu(), O.execute(op, img, po)) <= TOL_PIX
 
 
+TIE_TOL = 5e-4          # two candidates count as tied if the REFERENCE'S OWN distances differ by at most this
+FIT_TOL_SCALAR = 1e-4   # Nelder-Mead's fatol: 1-parameter fits converge
+FIT_TOL_CURVE = 2e-3    # 8- / 24-parameter fits stop unconverged at maxfev = 200 N; their end value depends on the path
+
+
+def _load_full(golden_dir, mode):
+    path = os.path.join(golden_dir, 'planner_full_%s.json' % mode)
+    if not os.path.exists(path):
+        pytest.skip('planner_full_%s golden not recorded' % mode)
+    rec = json.load(open(path))
+    d = np.load(os.path.join(golden_dir, 'planner_full_%s.npz' % mode))
+    I0 = (torch.from_numpy(d['I0']).float() / 255).cuda()          # 8-bit inputs, x / 255 as utils/visual_utils.py:61-70
+    Igt = (torch.from_numpy(d['Igt']).float() / 255).cuda()
+    return rec, I0, Igt
+
+
+def _check_against_transcripts(T, rec, I0, Igt, capsys, label):
+    from planner_compare import compare_runs
+    st = rec['settings']
+    ex = T.Executor(T.default_options()).cuda()
+    trace = []
+    res = T.planner.beam_search_batch(I0, Igt, ex, st['beam'], st['operations'], O.ACTION_NAMES, st['max_step'], st['err'],
+                                      trace=trace)
+    verdicts = []
+    for m, (pair, (actions, Is)) in enumerate(zip(rec['pairs'], res)):
+        verdict, detail = compare_runs(pair['steps'], trace[m]['steps'], st['beam'], st['err'], TIE_TOL, FIT_TOL_SCALAR,
+                                       FIT_TOL_CURVE)
+        verdicts.append((m, verdict, detail))
+        ref_ops = [[a[0] for a in seq] for seq in pair['actions']]
+        ops = [[a[0] for a in seq] for seq in actions]
+        ref_dist = pair['actions'][0][-1][2] if pair['actions'][0] else pair['init_dist']
+        dist = actions[0][-1][2] if actions[0] else pair['init_dist']
+        if verdict == 'exact':
+            assert ops == ref_ops, (m, ops, ref_ops)                 # every beam's operator sequence, in order
+            assert abs(dist - ref_dist) <= FIT_TOL_CURVE
+        else:
+            assert abs(dist - ref_dist) <= FIT_TOL_CURVE, (m, dist, ref_dist, detail)
+        # replaying the returned top sequence reproduces the returned images and distances
+        img = I0[m:m + 1]
+        for a, I_k in zip(actions[0], Is[0]):
+            img = T.planner.execute(img, O.ACTION_NAMES.index(a[0]), torch.tensor([a[1]], device='cuda'), ex)
+            assert max_abs(img.cpu(), I_k) <= TOL_PIX
+            assert abs(T.planner.get_dist(img, Igt[m:m + 1]).item() - a[2]) <= 1e-6
+    with capsys.disabled():
+        n_exact = sum(v == 'exact' for _, v, _ in verdicts)
+        print('\n[%s] %d pairs: %d identical to the reference at every step, %d diverge at a tie (|ref dist difference| <= %.0e)'
+              % (label, len(verdicts), n_exact, len(verdicts) - n_exact, TIE_TOL))
+        for m, v, detail in verdicts:
+            print('   pair %2d %-5s %s' % (m, v, detail))
+    return verdicts
+
+
+def test_beam_search_matches_reference_at_baseline_config_3(T, golden_dir, capsys):
+    """BASELINE config 3's shape: 3x128x128 pairs, beam 8, operations [0,1,2,3,5,6], err 1e-2, max_step 6
+    (preprocess/gen_greedy_seqs_FiveK.py:37-43 with beam 8), against the full transcripts of the unmodified reference
+    (oracle/make_planner_golden_full.py c3: every candidate of every step).  Per step: same beams in, the same
+    candidates evaluated, every candidate's distance within the fit tolerance, the same beams out -- a different beam is
+    accepted only where the reference's own distances of the competing candidates are within TIE_TOL (compare_runs
+    raises otherwise, with the evidence), and every such pair is listed."""
+    rec, I0, Igt = _load_full(golden_dir, 'c3')
+    verdicts = _check_against_transcripts(T, rec, I0, Igt, capsys, 'C3 128x128 beam 8')
+    assert len(verdicts) == len(rec['pairs']) >= 16
+
+
+def test_beam_search_matches_reference_gier_shape(T, golden_dir, capsys):
+    """The same at 3x256x256 (GIER-shaped inputs, preprocess/gen_greedy_seqs_GIER.py:36; BASELINE config 5)."""
+    rec, I0, Igt = _load_full(golden_dir, 'c5')
+    _check_against_transcripts(T, rec, I0, Igt, capsys, 'C5 256x256 beam 8')
+
+
+def test_beam_search_eps_greedy_matches_reference(T, golden_dir):
+    """utils/beam_search_eps_greedy.py:238-309 with its random.seed(0) (:24): every candidate is kept, with
+    probability eps the SEQUENCES are random.choices of all candidates (the recorded pairs alternate eps = 0.05, where
+    seed 0's first draw 0.844 takes the greedy branch, and eps = 0.9, which takes the random one), and the search stops
+    after its first step (no_update_flag is never cleared).  The op sequences must equal the reference's exactly."""
+    from planner_compare import compare_runs
+    rec, I0, Igt = _load_full(golden_dir, 'eps')
+    st = rec['settings']
+    ex = T.Executor(T.default_options()).cuda()
+    for m, pair in enumerate(rec['pairs']):
+        T.planner.eps_greedy_seed(0)
+        trace = []
+        actions, Is = T.planner.beam_search_batch(I0[m:m + 1], Igt[m:m + 1], ex, st['beam'], st['operations'], O.ACTION_NAMES,
+                                                  st['max_step'], st['err'], _variant='eps_greedy', _eps=pair['eps'], trace=trace)[0]
+        verdict, detail = compare_runs(pair['steps'], trace[0]['steps'], st['beam'], st['err'], TIE_TOL, FIT_TOL_SCALAR,
+                                       FIT_TOL_CURVE, variant='eps_greedy')
+        assert len(trace[0]['steps']) == len(pair['steps']) == 1
+        ops, ref_ops = [[a[0] for a in seq] for seq in actions], [[a[0] for a in seq] for seq in pair['actions']]
+        if verdict == 'exact':
+            assert ops == ref_ops, (m, pair['eps'], ops, ref_ops)
+        assert len(actions) == st['beam'] or pair['eps'] < 0.5
+    # the public wrapper draws from the same generator
+    T.planner.eps_greedy_seed(0)
+    a2, _ = T.planner.beam_search_eps_greedy(I0[1:2], Igt[1:2], None, ex, None, st['beam'], st['operations'], O.ACTION_NAMES,
+                                             st['max_step'], st['err'], 'L1', 'Nelder-Mead', eps=rec['pairs'][1]['eps'])
+    assert [[a[0] for a in seq] for seq in a2] == [[a[0] for a in seq] for seq in rec['pairs'][1]['actions']]
+
+
 def test_beam_search_batch_matches_reference_on_recorded_pairs(T, golden_dir):
-    """The reference's own driver settings (preprocess/gen_greedy_seqs_FiveK.py:37-43: beam 3, six operators, err 1e-2,
-    max_step 6) on the pairs recorded by oracle/make_planner_golden.py from the unmodified reference: the chosen
-    operator sequences must be identical unless the competing candidates were tied within the fit tolerance.
-    The 8- and 24-parameter curve fits stop unconverged at maxfev = 200 N, so their final distance depends on the
-    simplex path, i.e. on the L1's low bits; where tone and colour candidates end within ~5e-4 of each other the beam
-    order can flip (5 of the 16 recorded pairs, |final distance - reference's| <= 6e-4 on each).  A different top
-    sequence is therefore accepted only if its final distance is within 1e-3 of the reference's, and on a minority."""
+    """Round-1 transcripts (beam 3, 32x32, kept beams only: oracle/make_planner_golden.py): every returned top sequence
+    ends within the curve-fit tolerance of the reference's and replays exactly.  The per-step tie analysis lives in the
+    full-transcript tests above."""
     path = os.path.join(golden_dir, 'planner_pairs.json')
     if not os.path.exists(path):
         pytest.skip('planner_pairs golden not recorded')
@@ -171,24 +265,16 @@ def test_beam_search_batch_matches_reference_on_recorded_pairs(T, golden_dir):
     st = rec['settings']
     ex = T.Executor(T.default_options()).cuda()
     res = T.planner.beam_search_batch(I0, Igt, ex, st['beam'], st['operations'], O.ACTION_NAMES, st['max_step'], st['err'])
-    exact = 0
     for m, (pair, (actions, Is)) in enumerate(zip(rec['pairs'], res)):
         ref_top, top = pair['actions'][0], actions[0]
-        ref_ops, ops = [a[0] for a in ref_top], [a[0] for a in top]
         ref_dist = ref_top[-1][2] if ref_top else pair['init_dist']
         dist = top[-1][2] if top else pair['init_dist']
-        assert abs(dist - ref_dist) <= 1e-3, (m, ops, ref_ops, dist, ref_dist)
-        if ops == ref_ops:
-            exact += 1
-            for a, r in zip(top, ref_top):
-                assert abs(a[2] - r[2]) <= 2e-3, (m, a[0], a[2], r[2])
-        # replaying the returned sequence reproduces the returned images and distances
+        assert abs(dist - ref_dist) <= 1e-3, (m, dist, ref_dist)
         img = I0[m:m + 1]
         for a, I_k in zip(top, Is[0]):
             img = T.planner.execute(img, O.ACTION_NAMES.index(a[0]), torch.tensor([a[1]], device='cuda'), ex)
             assert max_abs(img.cpu(), I_k) <= TOL_PIX
             assert abs(T.planner.get_dist(img, Igt[m:m + 1]).item() - a[2]) <= 1e-6
-    assert exact * 8 >= 5 * len(rec['pairs']), 'only %d of %d top sequences identical to the reference' % (exact, len(rec['pairs']))
 
 
 def test_plan_record_roundtrip_and_lossless_replay(T, pair, tmp_path):

@@ -23,7 +23,7 @@ def test_library_exports_every_symbol_declared_in_the_header():
     lib = _lib.lib()                               # builds if stale; loads without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.t2o_version() == 103
+    assert lib.t2o_version() == 104
     assert lib.t2o_status_string(2) == b'unsupported configuration'
     assert [lib.t2o_num_params(op, 8) for op in (-1, 0, 1, 2, 3, 5, 6, 7, 8, 9)] == [0, 1, 1, 1, 24, 8, 1, 1, 1, 3]
     assert lib.t2o_num_params(42, 8) == -1
