@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the T2ONet hot path on B200 (contract: see DESIGN.md section 7).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c1|c3]
 
-Metric (BASELINE.json): edited Mpixel/s of the operator chain forward+backward.  One "step" = one pass of
-the fused chain  [brightness, contrast, saturation, color, tone, sharpness]  over one synthetic batch:
-edited image + per-image L1 to the target + gradients to all 36 operator parameters.
-Default workload = BASELINE config 2 (batch 64 of 3x128x128, the seq2seqL1 training shape).
+Metric (BASELINE.json): edited Mpixel/s of the operator chain forward+backward (& planner candidates/s).  One "step" =
+one pass of the fused chain  [brightness, contrast, saturation, color, tone, sharpness]  over one synthetic batch:
+edited image + per-image L1 to the target + gradients to all 36 operator parameters, ONE kernel launch.
+Default workload = BASELINE config 4 (batch 16 of 3x2048x3072: the roofline configuration, 3.6 GB >> L2); the line also
+carries config 2 (batch 64 of 3x128x128, the seq2seqL1 training shape) under "c2" and the planner (config 3's shape)
+under "planner", each with its own CPU baseline.
 
   value  : inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e    : the same step through the public API from pinned HOST buffers (H2D of img+target, D2H of L1+grads)
+  e2e    : the same step through the public API from pinned HOST buffers: 8-bit images host -> device (the form the
+           reference's images have on the host, utils/visual_utils.py:61-70), x / 255 on the device, fused step,
+           device -> host of the L1 terms and parameter gradients
   roofline / cpu_baseline / clocks : see DESIGN.md
-`--impl reference` times the reference's own algorithm (the CPU oracle port, torch fp32 with autograd) on the
-host cores for the same config.
+`--impl reference` times the reference's own CPU implementation on the host cores for the same config: the unmodified
+reference operators byte-compiled into oracle/_ref (kind "reference") when present, else the oracle port (kind "port").
 """
 import argparse
 import json
@@ -34,6 +38,9 @@ WORKLOADS = {
     'c2': dict(B=64, H=128, W=128, desc='C2: batch 64 of 3x128x128 (seq2seqL1 training shape), 6-op chain fwd+L1+bwd to all operator params'),
     'c4': dict(B=16, H=2048, W=3072, desc='C4: batch 16 of 3x2048x3072, 6-op chain fwd+L1+bwd (bandwidth stress)'),
 }
+# bounded CPU sample of each workload (one reference-arm step / the cpu_baseline sample): the full C2 batch, one image
+# of C1, a quarter image of C4 (autograd keeps ~50 planes per operator alive: a full 3x2048x3072 image needs > 10 GB)
+CPU_SAMPLE = {'c1': (1, 512, 512), 'c2': (64, 128, 128), 'c4': (1, 1024, 1536)}
 L2_BYTES = 126 * 1024 * 1024
 BYTES_PER_PX_FUSED = 36       # read img 12 + read target 12 + write out 12 (one fused fwd+bwd launch), DESIGN.md section 4
 
@@ -103,16 +110,6 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(clocks)}
 
 
-def profiled_traffic(key):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            e = json.load(f)[key]
-        return e['dram_read_bytes'] + e['dram_write_bytes'], e['source']
-    except Exception:
-        return None, None
-
-
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -122,13 +119,49 @@ def measured_peak_hbm():
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def oracle_step(img, tgt, params):
-    from oracle import ops as O
-    ps = [p.clone().requires_grad_() for p in params]
-    out = O.chain(img, CHAIN, ps)
-    loss = (out - tgt).abs().mean()
-    loss.backward()
-    return loss.item()
+def workload_config(wl):
+    """The `config` object both arms print (identical keys and values)."""
+    return {'workload': wl['desc'], 'chain': CHAIN_NAMES, 'batch_per_gpu': wl['B'], 'H': wl['H'], 'W': wl['W']}
+
+
+_REF = {}
+
+
+def reference_backend():
+    """-> (kind, step(img, tgt, params) -> loss).  kind "reference": the reference's own Executor / operators
+    (models/operators.py, executors/executor.py, byte-compiled into oracle/_ref by oracle/build_ref.py; kornia = the
+    oracle's restatement) with torch autograd; kind "port": the oracle's restatement of them (oracle/ops.py)."""
+    if 'step' in _REF:
+        return _REF['kind'], _REF['step']
+    try:
+        from oracle import ref_shims
+        if not ref_shims.available():
+            raise RuntimeError('no reference tree')
+        R = ref_shims.load()
+        torch.manual_seed(10)
+        ex = R.executor.Executor(R.options())
+
+        def step(img, tgt, params):
+            ps = [p.clone().requires_grad_() for p in params]
+            x = img
+            for op, p in zip(CHAIN, ps):
+                x = ex.execute(x, op, None, specified_param=p)[0]
+            loss = (x - tgt).abs().mean()                         # experiments/t2onet/train_seq2seqL1.py:85
+            loss.backward()
+            return loss.item()
+        _REF.update(kind='reference', step=step)
+    except Exception as exc:
+        print('[bench] reference tree unavailable (%r): timing the oracle port' % (exc,), file=sys.stderr)
+        from oracle import ops as O
+
+        def step(img, tgt, params):
+            ps = [p.clone().requires_grad_() for p in params]
+            out = O.chain(img, CHAIN, ps)
+            loss = (out - tgt).abs().mean()
+            loss.backward()
+            return loss.item()
+        _REF.update(kind='port', step=step)
+    return _REF['kind'], _REF['step']
 
 
 def run_reference(args, wl):
@@ -136,34 +169,27 @@ def run_reference(args, wl):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
+    kind, step = reference_backend()
     B, H, W = wl['B'], wl['H'], wl['W']
-    # bounded sample: shrink the batch until (steps + warmup) steps fit in ~150 s
-    img, tgt, params = make_batch(min(B, 8), min(H, 512), min(W, 512), 10 + 2000, 'cpu')
-    t0 = time.perf_counter()
-    oracle_step(img, tgt, params)
-    per_px = (time.perf_counter() - t0) / (img.shape[0] * img.shape[2] * img.shape[3])
-    budget_px = 150.0 / per_px / max(1, args.steps + args.warmup)
-    sB, sH, sW = B, H, W
-    while sB * sH * sW > budget_px and sB > 1:
-        sB = max(1, sB // 2)
-    while sB * sH * sW > budget_px and sH > 128:
-        sH //= 2
+    sB, sH, sW = CPU_SAMPLE[args.workload]
     img, tgt, params = make_batch(sB, sH, sW, 10 + 2000, 'cpu')
-    for _ in range(args.warmup):
-        oracle_step(img, tgt, params)
+    for _ in range(max(1, args.warmup)):
+        step(img, tgt, params)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(img, tgt, params)
+        step(img, tgt, params)
     dt = time.perf_counter() - t0
     mpix = sB * sH * sW * args.steps / dt / 1e6
-    sample = '%d steps of %dx3x%dx%d (full workload is %dx3x%dx%d)' % (args.steps, sB, sH, sW, B, H, W)
+    sample = '%d timed steps (+ %d warm-up) of %dx3x%dx%d per step (the configured batch is %dx3x%dx%d); %s' % (
+        args.steps, max(1, args.warmup), sB, sH, sW, B, H, W,
+        'unmodified reference operators (oracle/_ref) with torch CPU autograd' if kind == 'reference'
+        else 'oracle port of the reference operators (oracle/ops.py), torch CPU autograd')
     line = {
         'impl': 'reference', 'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': mpix, 'unit': 'Mpixel/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'chain': CHAIN_NAMES, 'batch': B, 'H': H, 'W': W},
-        'cpu_baseline': {'value': mpix, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': sample},
+        'config': workload_config(wl),
+        'cpu_baseline': {'value': mpix, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample},
         'e2e': {'value': mpix, 'unit': 'Mpixel/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -182,18 +208,9 @@ def timed_region(fn, steps, stream_sync):
     return start.elapsed_time(end)
 
 
-def run_ours(args, wl):
-    import t2onet_b200.functional as TF
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
-    torch.cuda.set_device(local)
-    dev = 'cuda:%d' % local
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+def measure_fused(TF, dev, wl, steps, warmup, rank, use_graph, barrier):
+    """The fused step (forward + L1 + backward, one launch) over rotating device-resident batches.
+    -> dict(ms, ms_eager, nb, graph, batches, packed, batch_bytes)"""
     B, H, W = wl['B'], wl['H'], wl['W']
     px_step = B * H * W
     batch_bytes = 3 * px_step * 12
@@ -208,17 +225,11 @@ def run_ours(args, wl):
         j = i % nb
         return fused[j](batches[j][0], packed[j], batches[j][1])
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for i in range(max(3, args.warmup, nb)):
+    for i in range(max(3, warmup, nb)):
         step(i)
     # the timed region replays a CUDA graph of the step launches (one kernel node per step) unless --no-graph
-    graph, gsteps = None, args.steps
-    if not args.no_graph:
+    graph = None
+    if use_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -229,35 +240,35 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                for i in range(args.steps):
+                for i in range(steps):
                     step(i)
             graph.replay()
             torch.cuda.synchronize()
         except Exception as exc:      # report, never hide
             print('[bench] CUDA graph capture failed, timing eager launches: %r' % (exc,), file=sys.stderr)
             graph = None
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    if graph is not None:
-        ms = timed_region(lambda i: graph.replay(), 1, barrier)      # one replay = exactly args.steps step launches
-    else:
-        ms = timed_region(step, args.steps, barrier)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_eager = timed_region(step, args.steps, barrier)
-    if dist is not None:
-        t = torch.tensor([ms, ms_eager], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_eager = t.tolist()
-    value = world * px_step * args.steps / (ms * 1e-3) / 1e6
+    return dict(step=step, graph=graph, nb=nb, batches=batches, packed=packed, batch_bytes=batch_bytes, px_step=px_step)
 
-    # ---- end to end through the public API from pinned host memory: every step copies its inputs host -> device,
-    # runs the prepared step, and copies the loss terms and parameter gradients back; two steps are in flight (two
-    # streams with their own device buffers), the host consumes the result of step i before it issues step i + 2
+
+def measure_e2e(TF, dev, wl, batches, packed, steps, barrier, u8):
+    """The same step through the public API from pinned HOST memory.  Every step copies its inputs host -> device
+    (u8: the 8-bit images + visual_utils.u8_to_float on the device; else the float32 tensors), runs the prepared step and
+    copies the loss terms and parameter gradients back; two steps are in flight (two streams with their own device
+    buffers), the host consumes the result of step i before it issues step i + 2.  -> (ms, steps, h2d bytes, d2h bytes)"""
+    from t2onet_b200 import visual_utils as V
+    B, H, W = wl['B'], wl['H'], wl['W']
+    px_step = B * H * W
     NSLOT = 2
-    himg = [b[0].cpu().pin_memory() for b in batches[:2]]
-    htgt = [b[1].cpu().pin_memory() for b in batches[:2]]
-    hpar = [p.cpu().pin_memory() for p in packed[:2]]
+    nh = min(2, len(batches))
+    if u8:
+        himg = [V.float_to_u8(b[0]).cpu().pin_memory() for b in batches[:nh]]
+        htgt = [V.float_to_u8(b[1]).cpu().pin_memory() for b in batches[:nh]]
+        stage_i = [torch.empty(B, 3, H, W, dtype=torch.uint8, device=dev) for _ in range(NSLOT)]
+        stage_t = [torch.empty(B, 3, H, W, dtype=torch.uint8, device=dev) for _ in range(NSLOT)]
+    else:
+        himg = [b[0].cpu().pin_memory() for b in batches[:nh]]
+        htgt = [b[1].cpu().pin_memory() for b in batches[:nh]]
+    hpar = [p.cpu().pin_memory() for p in packed[:nh]]
     streams = [torch.cuda.Stream() for _ in range(NSLOT)]
     dimg = [torch.empty_like(batches[0][0]) for _ in range(NSLOT)]
     dtgt = [torch.empty_like(batches[0][1]) for _ in range(NSLOT)]
@@ -269,13 +280,19 @@ def run_ours(args, wl):
     losses = []
 
     def e2e_step(i):
-        s, j = i % NSLOT, i % len(himg)
+        s, j = i % NSLOT, i % nh
         if done[s] is not None:
             done[s].synchronize()                       # the caller consumes the loss of step i - NSLOT
             losses.append(float(res_l1[s][0]))
         with torch.cuda.stream(streams[s]):
-            dimg[s].copy_(himg[j], non_blocking=True)
-            dtgt[s].copy_(htgt[j], non_blocking=True)
+            if u8:
+                stage_i[s].copy_(himg[j], non_blocking=True)
+                stage_t[s].copy_(htgt[j], non_blocking=True)
+                V.u8_to_float(stage_i[s], out=dimg[s])
+                V.u8_to_float(stage_t[s], out=dtgt[s])
+            else:
+                dimg[s].copy_(himg[j], non_blocking=True)
+                dtgt[s].copy_(htgt[j], non_blocking=True)
             dpar[s].copy_(hpar[j], non_blocking=True)
             _, l1, gp, _ = fused_e2e[s](dimg[s], dpar[s], dtgt[s])
             res_l1[s].copy_(l1, non_blocking=True)
@@ -283,14 +300,14 @@ def run_ours(args, wl):
             done[s] = torch.cuda.Event()
             done[s].record()
 
-    def e2e_region(steps):
+    def e2e_region(n):
         cur = torch.cuda.current_stream()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         start.record()
         for st in streams:
             st.wait_event(start)
-        for i in range(steps):
+        for i in range(n):
             e2e_step(i)
         for st in streams:
             cur.wait_stream(st)
@@ -301,15 +318,98 @@ def run_ours(args, wl):
         return start.elapsed_time(end)
 
     e2e_region(4)
-    e2e_steps = max(4, min(args.steps, 50))
-    ms_e2e = e2e_region(e2e_steps)
-    if dist is not None:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
-    e2e_value = world * px_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
-    h2d = 2 * px_step * 12 + hpar[0].numel() * 4
+    ms = e2e_region(steps)
+    h2d = 2 * px_step * (3 if u8 else 12) + hpar[0].numel() * 4
     d2h = B * 4 + B * 36 * 4
+    return ms, h2d, d2h, (3 if u8 else 1)
+
+
+def kernel_counters(key):
+    """Counters of the dominant kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)[key]
+    except Exception:
+        return {}
+
+
+def roofline_block(workload, px_step, kernel_ms, clocks):
+    peak, peak_src = measured_peak_hbm()
+    achieved = BYTES_PER_PX_FUSED * px_step / (kernel_ms * 1e-3) / 1e9
+    kc = kernel_counters(workload)
+    traffic = kc['dram_read_bytes'] + kc['dram_write_bytes'] if 'dram_read_bytes' in kc else None
+    blk = {'bound': 'hbm', 'kernel': kc.get('kernel', 'step_sharp_kernel<4,0,256,0,SP_C6>') + ' (fused forward + L1 + backward, one launch per step)',
+           'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+           'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram read + write)', 'traffic_source': kc.get('source'),
+           'algorithmic_bytes': BYTES_PER_PX_FUSED * px_step, 'peak_source': peak_src,
+           'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0}
+    # the second roofline: the kernel is FP32-issue-bound (DESIGN.md section 4) -- thread-instructions per pixel from the ncu
+    # capture against 148 SMs x 4 schedulers x 32 lanes per clock at the SM clock sampled during the timed region
+    ipp = kc.get('thread_instr_per_px')
+    mhz = (clocks or {}).get('sm_mhz') or (clocks or {}).get('sm_max_mhz')
+    if ipp and mhz:
+        issue_peak = 148 * 4 * 32 * mhz * 1e6
+        achieved_issue = ipp * px_step / (kernel_ms * 1e-3)
+        blk['issue'] = {'thread_instr_per_px': ipp, 'achieved_thread_instr_per_s': achieved_issue, 'peak_thread_instr_per_s': issue_peak,
+                        'frac': achieved_issue / issue_peak, 'sm_mhz': mhz, 'source': kc.get('source'),
+                        'note': 'issue-slot roofline: the time the same instruction stream needs at one warp-instruction per '
+                                'scheduler and clock is frac x the measured time'}
+    return blk
+
+
+def run_ours(args, wl):
+    import t2onet_b200.functional as TF
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        if dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def run_workload(key, w, steps, warmup, sample_clocks):
+        m = measure_fused(TF, dev, w, steps, warmup, rank, not args.no_graph, barrier)
+        sampler = ClockSampler(local)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        if m['graph'] is not None:
+            ms = timed_region(lambda i: m['graph'].replay(), 1, barrier)      # one replay = exactly `steps` step launches
+        else:
+            ms = timed_region(m['step'], steps, barrier)
+        clocks = sampler.stop() if sample_clocks and rank == 0 else None
+        ms_eager = timed_region(m['step'], steps, barrier)
+        e2e_steps = max(4, min(steps, 50 if m['px_step'] < (1 << 24) else 10))
+        ms_e2e, h2d, d2h, per_step_launches = measure_e2e(TF, dev, w, m['batches'], m['packed'], e2e_steps, barrier, u8=True)
+        ms, ms_eager, ms_e2e = max_over_ranks(ms, ms_eager, ms_e2e)
+        res = dict(m, ms=ms, ms_eager=ms_eager, clocks=clocks, steps=steps, e2e_ms=ms_e2e, e2e_steps=e2e_steps, h2d=h2d, d2h=d2h,
+                   value=world * m['px_step'] * steps / (ms * 1e-3) / 1e6,
+                   e2e_value=world * m['px_step'] * e2e_steps / (ms_e2e * 1e-3) / 1e6, e2e_launches_per_step=per_step_launches)
+        return res
+
+    main = run_workload(args.workload, wl, args.steps, args.warmup, True)
+    second = None
+    if args.workload != 'c2' and not args.no_extras:
+        # free the main workload's buffers first (C4 holds ~5 GB per rotating batch)
+        for k in ('batches', 'packed', 'step', 'graph'):
+            main[k] = None
+        torch.cuda.empty_cache()
+        second = run_workload('c2', WORKLOADS['c2'], max(args.steps, 50), args.warmup, False)
 
     planner_line = None
     if world > 1 and not args.no_extras:
@@ -328,60 +428,234 @@ def run_ours(args, wl):
             planner_line = {'error': err or 'a rank failed'}
         else:
             planner_line = planner_e2e_line(tmax[0].item(), int(tsum[1].item()), tsum[2].item() / world, n_gpus=world)
+    ddp_line = None
+    if world > 1 and not args.no_extras:
+        try:
+            ddp_line = ddp_actor_leg(dev, dist, rank, world)
+        except Exception as exc:
+            ddp_line = {'error': repr(exc)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peak_hbm()
-    kernel_ms = ms / args.steps
-    achieved = BYTES_PER_PX_FUSED * px_step / (kernel_ms * 1e-3) / 1e9
-    traffic, traffic_src = profiled_traffic(args.workload)
+    kernel_ms = main['ms'] / args.steps
+    nb, batch_bytes = main['nb'], main['batch_bytes']
     line = {
-        'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': value, 'unit': 'Mpixel/s', 'n_gpus': world,
+        'metric': 'edited Mpixel/s (op-chain fwd+bwd)', 'value': main['value'], 'unit': 'Mpixel/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': kernel_ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'chain': CHAIN_NAMES, 'batch_per_gpu': B, 'H': H, 'W': W,
-                   'l2_policy': ('rotating %d distinct batches (%.0f MB) > 126 MB L2' % (nb, nb * batch_bytes / 1e6)) if nb > 1
-                   else 'one batch of %.0f MB >> 126 MB L2' % (batch_bytes / 1e6),
-                   'sharding': 'images sharded across ranks, no data-path collective',
-                   'launch': 'CUDA graph replay of %d step launches' % args.steps if graph is not None else 'eager launches',
-                   'eager_ms_per_step': ms_eager / args.steps},
-        'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'Mpixel/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps,
-                'how': 'FusedStep from pinned host buffers, %d steps in flight on %d streams' % (NSLOT, NSLOT)},
+        'config': workload_config(wl),
+        'run': {'l2_policy': ('rotating %d distinct batches (%.0f MB) > 126 MB L2' % (nb, nb * batch_bytes / 1e6)) if nb > 1
+                else 'one batch of %.0f MB >> 126 MB L2' % (batch_bytes / 1e6),
+                'sharding': 'images sharded across ranks, no data-path collective',
+                'launch': 'CUDA graph replay of %d step launches' % args.steps if not args.no_graph else 'eager launches',
+                'eager_ms_per_step': main['ms_eager'] / args.steps},
+        'clocks': main['clocks'],
+        'e2e': {'value': main['e2e_value'], 'unit': 'Mpixel/s', 'h2d_bytes_per_step': main['h2d'], 'd2h_bytes_per_step': main['d2h'],
+                'ms_per_step': main['e2e_ms'] / main['e2e_steps'], 'steps': main['e2e_steps'],
+                'how': '8-bit images + float32 parameters from pinned host buffers, x / 255 on the device (visual_utils.u8_to_float), '
+                       'FusedStep, L1 terms + parameter gradients back to pinned host buffers; 2 steps in flight on 2 streams'},
         'gpu_launches': args.steps,
-        'roofline': {'bound': 'hbm', 'kernel': 'step_sharp_kernel<4,0,256,0> (fused forward + L1 + backward, one launch per step)',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram read + write)', 'traffic_source': traffic_src,
-                     'algorithmic_bytes': BYTES_PER_PX_FUSED * px_step, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_px': BYTES_PER_PX_FUSED, 'frac_of_nominal_8TBs': achieved / 8000.0,
-                     'note': 'FP32-issue-bound in practice (DESIGN.md section 4): ~610 thread-instructions per pixel, issue-active 71 % (profiles/r01f_step_c4_summary.txt)'},
+        'roofline': roofline_block(args.workload, main['px_step'], kernel_ms, main['clocks']),
     }
+    if second is not None:
+        c2ms = second['ms'] / second['steps']
+        line['c2'] = {'config': workload_config(WORKLOADS['c2']), 'value': second['value'], 'unit': 'Mpixel/s', 'ms_per_step': c2ms,
+                      'steps': second['steps'], 'eager_ms_per_step': second['ms_eager'] / second['steps'],
+                      'l2_policy': 'rotating %d distinct batches (%.0f MB) > 126 MB L2' % (second['nb'], second['nb'] * second['batch_bytes'] / 1e6),
+                      'e2e': {'value': second['e2e_value'], 'unit': 'Mpixel/s', 'h2d_bytes_per_step': second['h2d'],
+                              'd2h_bytes_per_step': second['d2h'], 'ms_per_step': second['e2e_ms'] / second['e2e_steps']},
+                      'roofline': roofline_block('c2', second['px_step'], c2ms, main['clocks'])}
     if world == 1 and not args.no_extras:
-        line['cpu_baseline'] = cpu_baseline(wl)
-        line['extras'] = extras(TF, dev, wl)
+        line['cpu_baseline'] = cpu_baseline(args.workload, wl)
+        if second is not None:
+            line['c2']['cpu_baseline'] = cpu_baseline('c2', WORKLOADS['c2'], seconds=6.0)
+        ex = extras(TF, dev, wl)
+        line['planner'] = planner_block(ex)
+        line['extras'] = ex
     if planner_line is not None:
-        line['extras'] = {'planner_e2e': planner_line}
+        line['planner'] = {'metric': 'planner candidates/s', 'value': planner_line.get('candidates_per_s'), 'unit': 'candidates/s',
+                           'e2e': planner_line}
+    if ddp_line is not None:
+        line['ddp_actor'] = ddp_line
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(wl):
-    """The oracle port of the reference operators (torch CPU fp32 + autograd) on the host cores, bounded sample."""
-    torch.set_num_threads(os.cpu_count() or 1)
-    B, H, W = min(wl['B'], 64), min(wl['H'], 512), min(wl['W'], 512)
-    img, tgt, params = make_batch(B, H, W, 10 + 2000, 'cpu')
-    oracle_step(img, tgt, params)
+def planner_block(ex):
+    """The planner half of the metric (candidates/s) as a top-level object: the scorer's sweep, the public-API run and
+    the reference's CPU planner beside it."""
+    blk = {'metric': 'planner candidates/s', 'unit': 'candidates/s'}
+    e2e, sweep = ex.get('planner_e2e', {}), ex.get('planner_scoring', {})
+    blk['value'] = e2e.get('candidates_per_s')
+    blk['e2e'] = e2e
+    blk['scoring_sweep'] = sweep
+    try:
+        cpu = planner_cpu_baseline()
+        if e2e.get('candidates') and e2e.get('pairs_per_s') and cpu.get('value'):
+            per_pair = e2e['candidates'] / float(PLANNER_M)
+            cpu['pairs_per_s_extrapolated'] = cpu['value'] / per_pair
+            cpu['extrapolation'] = 'candidates/s divided by the GPU run\'s %.0f candidates per pair' % per_pair
+        blk['cpu_baseline'] = cpu
+    except Exception as exc:
+        blk['cpu_baseline'] = {'error': repr(exc)}
+    return blk
+
+
+def _planner_cpu_worker(job):
+    """One process, one torch thread: the reference's beam_search (or the oracle port) on one synthetic pair, first step only."""
+    seed, max_step = job
+    torch.set_num_threads(1)
+    sys.path.insert(0, ROOT)
+    names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+    img, tgt, _ = make_batch(1, 128, 128, seed, 'cpu')
+    cnt = [0]
+    kind = 'port'
     t0 = time.perf_counter()
-    n = 0
-    while time.perf_counter() - t0 < 12.0 and n < 40:
-        oracle_step(img, tgt, params)
-        n += 1
-    dt = time.perf_counter() - t0
-    return {'value': B * H * W * n / dt / 1e6, 'unit': 'Mpixel/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '%d steps of %dx3x%dx%d, 6-op chain fwd+L1+bwd (oracle/ops.py, torch CPU fp32 autograd)' % (n, B, H, W)}
+    try:
+        from oracle import ref_shims
+        if not ref_shims.available():
+            raise RuntimeError('no reference tree')
+        R = ref_shims.load()
+        torch.manual_seed(10)
+        ex = R.executor.Executor(R.options())
+        mod = R.beam_search
+        orig = mod.get_dist
+
+        def counted(x1, x2, dist_type):
+            cnt[0] += 1
+            return orig(x1, x2, dist_type)
+        mod.get_dist = counted
+        t0 = time.perf_counter()
+        try:
+            mod.beam_search(img, tgt, None, ex, None, 8, CHAIN, names, max_step, 1e-2, 'L1', 'Nelder-Mead', replace=False)
+        finally:
+            mod.get_dist = orig
+        kind = 'reference'
+    except Exception:
+        from oracle import ops as O
+        from oracle import planner as OP
+        cnt[0] = 0
+        t0 = time.perf_counter()
+        OP.beam_search(img, tgt, None, O.OracleExecutor(), None, 8, CHAIN, names, max_step, 1e-2, 'L1', 'Nelder-Mead', counter=cnt)
+    return cnt[0], time.perf_counter() - t0, kind
+
+
+def planner_cpu_baseline(max_procs=16):
+    """The reference's own planner on the host cores: utils/beam_search.beam_search, beam 8, the six
+    operators, Nelder-Mead, on synthetic 3x128x128 pairs of the GPU workload's kind -- one pair per process (the search of a
+    pair is sequential: scipy's Nelder-Mead evaluates one candidate at a time), max_step = 1 (6 fits, ~7 000 candidates:
+    the bounded sample), all processes timed together."""
+    import multiprocessing as mp
+    procs = max(1, min(max_procs, os.cpu_count() or 1))
+    jobs = [(3010 + 7 * i, 1) for i in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context('spawn').Pool(procs) as pool:
+        res = pool.map(_planner_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    cand = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    kind = res[0][2]
+    return {'value': cand / busy, 'unit': 'candidates/s', 'cores': procs, 'kind': kind,
+            'sample': '%d pairs of 3x128x128 (one per process, 1 torch thread each), %s beam_search beam 8, ops [0,1,2,3,5,6], '
+                      'Nelder-Mead, first step only (max_step 1): %d candidates in %.1f s (slowest process; %.1f s wall with '
+                      'process start-up)' % (procs, 'the unmodified reference\'s' if kind == 'reference' else 'the oracle port\'s',
+                                             cand, busy, wall),
+            'per_process_candidates_per_s': cand / sum(r[1] for r in res)}
+
+
+def ddp_actor_leg(dev, dist, rank, world, B=64, H=128, W=128, iters=6):
+    """BASELINE config 5 / SURVEY.md section 8e row 1: the seq2seqL1 training step (episode_forward + mean L1 + backward,
+    experiments/t2onet/train_seq2seqL1.py:75-88) of the reference's own Actor on the new Executor, wrapped in
+    DistributedDataParallel: batch 64 per GPU, the 22.17 M-parameter gradient all-reduce over NCCL.  Needs the compiled
+    reference tree (oracle/_ref); -> per-step time, max over ranks."""
+    from oracle import ref_shims
+    if not ref_shims.available():
+        return {'unavailable': 'oracle/_ref (the byte-compiled reference Actor) is not present'}
+    import t2onet_b200 as T
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    opt = ref_shims.actor_options()
+    actor = ref_shims.build_actor(opt, T.Executor, seed=10).to(dev)
+    ddp = DDP(_EpisodeL1(actor, opt), device_ids=[torch.device(dev).index], find_unused_parameters=True)
+    g = torch.Generator().manual_seed(10 + 9000 + rank)
+    x = torch.randint(4, 200, (B, opt.encoder_max_len), generator=g)
+    x[:, 0], x[:, -1] = opt.start_id, opt.end_id
+    img = torch.rand(B, 3, H, W, generator=g).to(dev)
+    tgt = torch.rand(B, 3, H, W, generator=g).to(dev)
+    x = x.to(dev)
+    optim = torch.optim.Adam(ddp.parameters(), lr=1e-4)
+    times = []
+    for it in range(iters):
+        torch.cuda.synchronize()
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        optim.zero_grad(set_to_none=True)
+        loss = ddp(x, img, tgt)
+        loss.backward()
+        optim.step()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    # rank-identical gradients after the all-reduce
+    gsum = torch.stack([p.grad.double().sum() for p in ddp.parameters() if p.grad is not None]).sum().view(1)
+    gall = [torch.zeros_like(gsum) for _ in range(world)]
+    dist.all_gather(gall, gsum)
+    t = torch.tensor([min(times[2:])], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nparam = sum(p.numel() for p in ddp.parameters())
+    return {'workload': 'reference Actor (models/actor.py, unmodified) on t2onet_b200.Executor under DistributedDataParallel: '
+                        'episode_forward + mean L1 + backward + Adam, batch %d x 3x%dx%d per GPU' % (B, H, W),
+            'n_gpus': world, 'ms_per_step': t.item(), 'images_per_s': world * B / t.item() * 1e3,
+            'allreduce_bytes_per_step': nparam * 4, 'parameters': nparam,
+            'gradients_identical_across_ranks': bool(all(torch.equal(gall[0], v) for v in gall)),
+            'loss': float(loss.item())}
+
+
+class _EpisodeL1(torch.nn.Module):
+    """experiments/t2onet/train_seq2seqL1.py:75-85 as a module, so that DDP's forward hook sees the whole step."""
+
+    def __init__(self, actor, opt):
+        super().__init__()
+        self.actor, self.opt = actor, opt
+
+    def forward(self, x, img_x, img_y):
+        _, pred_imgs, pred_ops, _ = self.actor.episode_forward(x, img_x, None)
+        bs, max_len = pred_imgs.shape[:2]
+        end = []
+        for b in range(bs):
+            idxs = (pred_ops[b] == self.opt.end_id).nonzero()
+            end.append(pred_imgs[b, idxs[0][0] if len(idxs) > 0 else max_len - 1])
+        return torch.abs(torch.stack(end) - img_y).mean()
+
+
+def cpu_baseline(key, wl, seconds=12.0):
+    """The reference's CPU operators (unmodified, oracle/_ref) -- or their oracle port -- with torch autograd on the host
+    cores, bounded sample; all cores and one thread."""
+    kind, step = reference_backend()
+    B, H, W = CPU_SAMPLE[key]
+    img, tgt, params = make_batch(B, H, W, 10 + 2000, 'cpu')
+
+    def run(threads, budget):
+        torch.set_num_threads(threads)
+        step(img, tgt, params)
+        t0 = time.perf_counter()
+        n = 0
+        while (time.perf_counter() - t0 < budget and n < 40) or n < 1:
+            step(img, tgt, params)
+            n += 1
+        return B * H * W * n / (time.perf_counter() - t0) / 1e6, n
+    cores = os.cpu_count() or 1
+    v_all, n_all = run(cores, seconds)
+    v_one, n_one = run(1, seconds / 2)
+    torch.set_num_threads(cores)
+    what = 'unmodified reference operators (oracle/_ref), torch CPU fp32 autograd' if kind == 'reference' \
+        else 'oracle port of the reference operators (oracle/ops.py), torch CPU fp32 autograd'
+    return {'value': v_all, 'unit': 'Mpixel/s', 'cores': cores, 'kind': kind,
+            'sample': '%d steps of %dx3x%dx%d (configured batch %dx3x%dx%d), 6-op chain fwd+L1+bwd; %s' % (
+                n_all, B, H, W, wl['B'], wl['H'], wl['W'], what),
+            'one_thread': {'value': v_one, 'unit': 'Mpixel/s', 'cores': 1, 'sample': '%d steps of the same sample, torch.set_num_threads(1)' % n_one}}
 
 
 def fused_scale(B, H, W, dev):
@@ -690,7 +964,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS) + ['c3'])
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS) + ['c3'])
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()

@@ -12,7 +12,8 @@ Nelder-Mead, max_step 6).  Unlike make_planner_golden.py it records, per beam st
 evaluated -- (parent beam index, parent operator sequence, operator, fitted parameters, distance, kept or not) -- and
 the distance array / order of its np.argsort, so that a test can show whether a candidate displaced in another
 implementation's run was tied within tolerance in the reference's own run.  The reference's code is not modified: the
-module-level names `get_param`, `get_dist` and `np` that beam_search looks up are wrapped by recording pass-throughs.
+module-level names `get_param`, `get_dist`, `minimize` and `np` that beam_search looks up are wrapped by recording
+pass-throughs.  For the 1-parameter fits the whole Nelder-Mead evaluation history (x, f) is kept as well.
 
 Inputs are 8-bit images (x / 255, as utils/visual_utils.py:61-70 produces them): a smooth random colour field plus
 noise, the target a planted chain of 2-4 operators re-quantised to 8 bits, so the fixture stores uint8.
@@ -80,10 +81,22 @@ def run_pair(job):
     mod = R.beam_search_eps_greedy if cfg['variant'] == 'eps_greedy' else R.beam_search
     rec = {'sort': [], 'cands': []}
     state = {'in_fit': False, 'op': None, 'parent': None, 'param': None, 'nfev': 0}
-    orig_get_param, orig_get_dist, orig_np = mod.get_param, mod.get_dist, mod.np
+    orig_get_param, orig_get_dist, orig_np, orig_minimize = mod.get_param, mod.get_dist, mod.np, mod.minimize
+
+    def minimize(func, x0, **kw):
+        """scipy.optimize.minimize as the reference calls it, with every evaluation (x, f) of the fit recorded"""
+        hist = []
+
+        def f2(x):
+            v = func(x)
+            hist.append(([float(t) for t in np.atleast_1d(x)], float(v)))
+            return v
+        res = orig_minimize(f2, x0, **kw)
+        state['hist'] = hist
+        return res
 
     def get_param(I, I_gt, txt, operation, *a, **k):
-        state['in_fit'], state['op'], state['nfev'] = True, operation, 0
+        state['in_fit'], state['op'], state['nfev'], state['hist'] = True, operation, 0, None
         state['parent'] = I
         try:
             param, ok = orig_get_param(I, I_gt, txt, operation, *a, **k)
@@ -99,10 +112,14 @@ def run_pair(job):
         else:
             rec['cands'].append({'step': len(rec['sort']), 'op': int(state['op']),
                                  'param': [float(v) for v in state['param'][0].tolist()], 'dist': float(d.item()),
-                                 'nfev': state['nfev'], 'parent_id': id(state['parent'])})
+                                 'nfev': state['nfev'], 'parent_id': id(state['parent']),
+                                 # the whole Nelder-Mead evaluation history of the 1-parameter fits (x, f): lets a test
+                                 # show whether a fit that ends elsewhere was decided by two evaluations tied within the
+                                 # L1's own rounding noise (the 8- / 24-parameter histories would be ~0.5 MB per fit)
+                                 'hist': [[h[0][0], h[1]] for h in state['hist']] if len(state['param'][0]) == 1 else None})
         return d
 
-    mod.get_param, mod.get_dist, mod.np = get_param, get_dist, _NumpyProxy(rec)
+    mod.get_param, mod.get_dist, mod.np, mod.minimize = get_param, get_dist, _NumpyProxy(rec), minimize
     t0 = time.time()
     try:
         if cfg['variant'] == 'eps_greedy':
@@ -114,7 +131,7 @@ def run_pair(job):
                                           1e-2, 'L1', 'Nelder-Mead', replace=False)
         init_dist = orig_get_dist(I0, Igt, 'L1').item()
     finally:
-        mod.get_param, mod.get_dist, mod.np = orig_get_param, orig_get_dist, orig_np
+        mod.get_param, mod.get_dist, mod.np, mod.minimize = orig_get_param, orig_get_dist, orig_np, orig_minimize
     # parent tensors -> the beam index they had in that step's I_buff (first-seen order within the step)
     steps = []
     for s in range(len(rec['sort'])):
@@ -124,7 +141,7 @@ def run_pair(job):
             if c['parent_id'] not in seen:
                 seen.append(c['parent_id'])
             c['parent'] = seen.index(c['parent_id'])
-        steps.append({'candidates': [{k: c[k] for k in ('parent', 'op', 'param', 'dist', 'nfev')} for c in cs],
+        steps.append({'candidates': [{k: c[k] for k in ('parent', 'op', 'param', 'dist', 'nfev', 'hist')} for c in cs],
                       'sort_dists': rec['sort'][s]['dists'], 'sort_order': rec['sort'][s]['order']})
     out = {'index': i, 'planted': PLANTED[i % len(PLANTED)], 'init_dist': init_dist, 'eps': eps,
            'actions': [[[a[0], [float(v) for v in a[1]], float(a[2])] for a in seq] for seq in actions],

@@ -23,11 +23,14 @@ import types
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+EXT = '.t2oc'          # oracle/build_ref.py: importlib MAGIC_NUMBER + marshal.dumps(code object)
+
+
 def _find_root():
     cands = [os.environ.get('T2O_REFERENCE_ROOT'), '/root/reference', os.path.join(_HERE, '_ref', 't2onet')]
     for c in cands:
         if c and (os.path.isfile(os.path.join(c, 'models', 'operators.py')) or
-                  os.path.isfile(os.path.join(c, 'models', 'operators.pyc'))):
+                  os.path.isfile(os.path.join(c, 'models', 'operators' + EXT))):
             return c
     return cands[0] or '/root/reference'
 
@@ -37,11 +40,53 @@ REF_ROOT = _find_root()
 
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.py')) or \
-        os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.pyc'))
+        os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators' + EXT))
 
 
 def is_source_tree():
     return os.path.isfile(os.path.join(REF_ROOT, 'models', 'operators.py'))
+
+
+class _CompiledTreeFinder:
+    """Import hook for the byte-compiled reference tree (oracle/_ref/t2onet/<package>/<module>.t2oc): the reference's
+    top-level packages (models, executors, utils, options, datasets; most of them namespace packages, as in the source
+    tree) resolve to the compiled files."""
+    TOP = ('models', 'executors', 'utils', 'options', 'datasets')
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if name.split('.')[0] not in self.TOP:
+            return None
+        rel = os.path.join(self.root, *name.split('.'))
+        if os.path.isfile(rel + EXT):
+            return importlib.util.spec_from_loader(name, self, origin=rel + EXT)
+        if os.path.isfile(os.path.join(rel, '__init__' + EXT)):
+            spec = importlib.util.spec_from_loader(name, self, origin=os.path.join(rel, '__init__' + EXT), is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        if os.path.isdir(rel):
+            spec = importlib.machinery.ModuleSpec(name, None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import importlib.util
+        import marshal
+        with open(module.__spec__.origin, 'rb') as f:
+            data = f.read()
+        n = len(importlib.util.MAGIC_NUMBER)
+        if data[:n] != importlib.util.MAGIC_NUMBER:
+            raise ImportError('%s was compiled by another Python version; rerun python -m oracle.build_ref' % module.__spec__.origin)
+        module.__file__ = module.__spec__.origin
+        exec(marshal.loads(data[n:]), module.__dict__)
 
 
 _loaded = None
@@ -73,8 +118,11 @@ def load():
         except Exception:
             sys.modules['h5py'] = types.ModuleType('h5py')
 
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if is_source_tree():
+        if REF_ROOT not in sys.path:
+            sys.path.insert(0, REF_ROOT)
+    elif not any(isinstance(f, _CompiledTreeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledTreeFinder(REF_ROOT))
     import models.operators as operators
 
     class _InpaintStub(operators.Operator):

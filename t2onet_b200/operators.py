@@ -128,6 +128,10 @@ class Operator(nn.Module):
             m = torch.ones_like(self._mask_like)
         return m
 
+    @mask.setter
+    def mask(self, value):
+        self._mask, self._mask_like = value, None
+
     def param_loss_fn(self):
         return F.mse_loss
 

@@ -243,9 +243,58 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor):
     return outs, vals
 
 
+def _fit_sharded(states, I_gt, problems, executor, state_pair, counter, numel, group):
+    """Candidate-sharded fitting: every rank holds the same states and the same problem
+    list; rank r runs the Nelder-Mead fits of problems r, r + R, ... and ONE all_gather of a (n, nfev, x[24]) float64 record
+    per fit gives every rank the whole table.  A fit does not depend on which other fits share its launches, so the
+    table -- and everything selected from it -- is the same for every rank count."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = list(range(rank, len(problems), world))
+    per = (len(problems) + world - 1) // world
+    local = torch.zeros(per, 26, dtype=torch.float64)
+    fits = fit_params_nelder_mead(states, I_gt, [problems[k][:2] for k in mine], executor, state_target=state_pair, numel=numel)
+    for slot, r in enumerate(fits):
+        local[slot, 0], local[slot, 1] = len(r.x), r.nfev
+        local[slot, 2:2 + len(r.x)] = torch.from_numpy(np.asarray(r.x, dtype=np.float64))
+    local = local.to(states.device)
+    table = torch.empty(world * per, 26, dtype=torch.float64, device=states.device)
+    dist.all_gather_into_tensor(table, local, group=group)
+    table = table.cpu().view(world, per, 26)
+    params, nfevs = [], []
+    for k in range(len(problems)):
+        row = table[k % world, k // world]
+        n = int(row[0])
+        params.append(row[2:2 + n].numpy().copy()[None, :])
+        nfevs.append(int(row[1]))
+    if counter is not None:
+        counter[0] += sum(nfevs)
+    return params, nfevs
+
+
+def _step_minima_sharded(dists, problems, live, device_, group):
+    """The lowest candidate distance of every live pair, agreed by ONE all_reduce(MIN) over packed (distance, candidate)
+    keys (dist.best_candidate): rank r contributes the candidates it fitted.  -> {pair: (min dist, problem index)}"""
+    import torch.distributed as dist
+    from . import dist as D
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    row = {m: r for r, m in enumerate(live)}
+    width = max(1, max(sum(1 for k in range(rank0, len(problems), world)) for rank0 in range(world)))
+    sc = torch.full((len(live), width), float('inf'))
+    ids = torch.full((len(live), width), 0x7FFFFFFF, dtype=torch.int64)
+    fill = [0] * len(live)
+    for k in range(rank, len(problems), world):
+        r = row[problems[k][2]]
+        sc[r, fill[r]], ids[r, fill[r]] = dists[k], k
+        fill[r] += 1
+    best, bid = D.best_candidate(sc.to(device_), ids.to(device_), group=group)
+    best, bid = best.tolist(), bid.tolist()
+    return {m: (best[row[m]], bid[row[m]]) for m in live}
+
+
 def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type='L1',
                       optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None,
-                      trace=None):
+                      trace=None, shard_fits=False, group=None):
     """`beam_search` (utils/beam_search.py:196-264) for M image pairs at once: I_0, I_gt (M,3,H,W).
 
     Every pair runs the reference's beam search unchanged; what is shared is the work: all (pair, beam state,
@@ -253,8 +302,15 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     Returns a list of M (actions, Is) tuples, each exactly what `beam_search` returns for that pair.
     `trace`: an empty list that receives, per pair, {'steps': [{'candidates': [{'parent', 'op', 'param', 'dist', 'nfev'}],
     'sort_dists', 'sort_order'}]} -- every candidate evaluated and the array / order of the step's argsort (the
-    transcript format of oracle/make_planner_golden_full.py)."""
+    transcript format of oracle/make_planner_golden_full.py).
+    `shard_fits` (inside an initialised process group, every rank calling with the SAME pairs): candidate-sharded mode --
+    the fits of a step are split over the ranks, the table of fitted parameters is all-gathered and the step's best
+    candidate per pair is agreed with one all_reduce(MIN) (NCCL on GPUs); the result is the same for every rank count."""
     assert dist_type == 'L1', 'only the L1 distance is implemented'
+    if shard_fits:
+        import torch.distributed as _dist
+        shard_fits = _dist.is_available() and _dist.is_initialized() and _dist.get_world_size(group) > 1
+        assert not shard_fits or optimizer == 'Nelder-Mead', 'candidate sharding covers the Nelder-Mead fits'
     I_0 = I_0.to(device) if not I_0.is_cuda else I_0
     I_gt = I_gt.to(I_0.device)
     M = I_0.shape[0]
@@ -281,7 +337,10 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                         continue
                     problems.append((s_idx, operation, m, j))
         # -- fit all of them (utils/beam_search.py:229)
-        if optimizer == 'Nelder-Mead' and problems:
+        if shard_fits and problems:
+            params, nfevs = _fit_sharded(torch.cat(states, 0).contiguous(), I_gt, problems, executor, state_pair, counter,
+                                         numel, group)
+        elif optimizer == 'Nelder-Mead' and problems:
             fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _ in problems],
                                           executor, state_target=state_pair, counter=counter, numel=numel)
             params = [np.asarray(r.x, dtype=np.float64)[None, :] for r in fits]     # (1, n) float64, as the reference's tensors
@@ -294,6 +353,7 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
         outs, dists = _score_outputs([states[s] for s, _, _, _ in problems], [op for _, op, _, _ in problems], params,
                                      [I_gt[m:m + 1] for _, _, m, _ in problems], executor)
         # -- the reference's bookkeeping, pair by pair (utils/beam_search.py:239-259)
+        minima = _step_minima_sharded(dists, problems, live, I_0.device, group) if shard_fits and problems else None
         by_pair = {m: [] for m in live}
         for k, (s, op, m, j) in enumerate(problems):
             by_pair[m].append((j, op, params[k], outs[k], dists[k], nfevs[k]))
@@ -312,6 +372,11 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                     if dist < err:
                         finish_flag = True
             S['min_dist'] = min(tmp_min_dists) if len(tmp_min_dists) > 0 else S['min_dist']
+            if minima is not None and by_pair[m]:
+                # candidate-sharded mode: the all-reduced minimum is the step's new min_dist (utils/beam_search.py:250)
+                agreed = minima[m][0] if _variant == 'eps_greedy' else min(S['min_dist'], minima[m][0])
+                assert agreed == S['min_dist'], ('ranks disagree on the best candidate', m, agreed, S['min_dist'])
+                S['min_dist'] = agreed
             if len(all_candidates) < beam_size:
                 all_candidates += S['sequences']
                 I_tmp_list += S['I_buff']
@@ -356,11 +421,11 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
 
 
 def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,
-                dist_type, optimizer, replace=False, _variant='default', _eps=0.05, counter=None):
+                dist_type, optimizer, replace=False, _variant='default', _eps=0.05, counter=None, shard_fits=False, group=None):
     """utils/beam_search.py:196-264 -- same arguments and return value:
     actions: list(beam) of list(step) of (op_name, param list, dist); Is: same nesting of CPU images."""
     return beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type,
-                             optimizer, replace, _variant, _eps, counter, txt)[0]
+                             optimizer, replace, _variant, _eps, counter, txt, shard_fits=shard_fits, group=group)[0]
 
 
 def beam_search_fixed_order(I_0, I_gt, txt, executor, beam_size, operations, operation_names, max_step, err, dist_type,

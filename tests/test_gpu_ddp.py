@@ -1,0 +1,117 @@
+"""Multi-GPU legs on real NCCL (skipped on a single-GPU box; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_ddp.py -m gpu`):
+the DDP gradient all-reduce of the reference's Actor on the new Executor (BASELINE config 5) and
+the planner's two sharded modes (rows 2 and 3) over NCCL instead of gloo."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_shims
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world, device_id=dev)
+    try:
+        import bench
+        import t2onet_b200 as T
+        from t2onet_b200 import dist as D, planner
+        out = {}
+        # ---- 1. DDP step of the reference Actor on the new Executor
+        if ref_shims.available():
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            opt = ref_shims.actor_options()
+            actor = ref_shims.build_actor(opt, T.Executor, seed=10).to(dev)
+            mod = bench._EpisodeL1(actor, opt)
+            ddp = DDP(mod, device_ids=[rank], find_unused_parameters=True)
+            g = torch.Generator().manual_seed(100 + rank)                   # every rank its own shard of the batch
+            B = 8
+            x = torch.randint(4, 200, (B, opt.encoder_max_len), generator=g)
+            x[:, 0], x[:, -1] = opt.start_id, opt.end_id
+            img = torch.rand(B, 3, 32, 32, generator=g).to(dev)
+            tgt = torch.rand(B, 3, 32, 32, generator=g).to(dev)
+            x = x.to(dev)
+            params = [p for p in ddp.parameters()]
+            # local gradients (no all-reduce) ...
+            ddp.zero_grad(set_to_none=True)
+            torch.manual_seed(7)
+            with ddp.no_sync():
+                ddp(x, img, tgt).backward()
+            local = [None if p.grad is None else p.grad.detach().clone() for p in params]
+            # ... and the DDP step from the same RNG state
+            ddp.zero_grad(set_to_none=True)
+            torch.manual_seed(7)
+            loss = ddp(x, img, tgt)
+            loss.backward()
+            used = [i for i, p in enumerate(params) if p.grad is not None and local[i] is not None]
+            flat = torch.cat([params[i].grad.flatten() for i in used])
+            flat_local = torch.cat([local[i].flatten() for i in used])
+            mean_local = flat_local.clone()
+            dist.all_reduce(mean_local)
+            mean_local /= world
+            gathered = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(gathered, flat)
+            out['ddp_identical'] = bool(all(torch.equal(gathered[0], v) for v in gathered))
+            out['ddp_vs_mean_local'] = float((flat - mean_local).abs().max() / (mean_local.abs().max() + 1e-20))
+            out['ddp_nparams'] = int(flat.numel())
+            out['ddp_heads_have_grad'] = bool(actor.executor.brightness_op.fc1.weight.grad is not None)
+        # ---- 2. image-sharded planning, records gathered over NCCL: identical to the single-rank run
+        names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+        exe = T.Executor(T.default_options()).to(dev)
+        g = torch.Generator().manual_seed(5)
+        I0 = torch.rand(6, 3, 32, 32, generator=g) * 0.8 + 0.1
+        Igt = (I0 * 1.15).clamp(0, 1)
+        ops = [0, 1, 2, 6]
+
+        def batch_fn(idx, items, ex):
+            a = torch.cat([it[0] for it in items]).to(dev)
+            b = torch.cat([it[1] for it in items]).to(dev)
+            res = planner.beam_search_batch(a, b, ex, 2, ops, names, 2, 1e-3)
+            return [[[[act[0], act[1], act[2]] for act in seq] for seq in r[0]] for r in res]
+        pairs = [(I0[i:i + 1], Igt[i:i + 1]) for i in range(6)]
+        recs = D.plan_dataset_batched(pairs, exe, batch_fn, batch=4)
+        single = batch_fn(list(range(6)), pairs, exe)
+        out['image_sharded_equal'] = recs == single
+        # ---- 3. candidate-sharded planning: the fits of ONE pair split over the ranks, best candidate by all_reduce(MIN)
+        for beam in (1, 2):
+            ref_a, _ = planner.beam_search(I0[:1].to(dev), Igt[:1].to(dev), None, exe, None, beam, ops, names, 2, 1e-3, 'L1', 'Nelder-Mead')
+            got_a, _ = planner.beam_search(I0[:1].to(dev), Igt[:1].to(dev), None, exe, None, beam, ops, names, 2, 1e-3, 'L1', 'Nelder-Mead',
+                                           shard_fits=True)
+            out['candidate_sharded_equal_beam%d' % beam] = [[(a[0], a[1], a[2]) for a in s] for s in ref_a] == \
+                [[(a[0], a[1], a[2]) for a in s] for s in got_a]
+        q.put((rank, out))
+    except Exception as exc:            # pragma: no cover
+        import traceback
+        q.put((rank, {'error': repr(exc), 'trace': traceback.format_exc()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_and_sharded_planner_on_nccl():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+    for r in (0, 1):
+        assert 'error' not in res[r], res[r].get('trace')
+        if 'ddp_identical' in res[r]:
+            assert res[r]['ddp_identical'] and res[r]['ddp_heads_have_grad'] and res[r]['ddp_nparams'] > 1e7
+            assert res[r]['ddp_vs_mean_local'] <= 1e-5, res[r]
+        assert res[r]['image_sharded_equal']
+        assert res[r]['candidate_sharded_equal_beam1'] and res[r]['candidate_sharded_equal_beam2']
+    print(res[0])

@@ -201,3 +201,14 @@ def test_planner_compare_flags_untied_divergence(golden_dir):
         with pytest.raises(AssertionError):
             compare_runs(steps, bad, st['beam'], st['err'], 5e-4, 1.0, 1.0)
     assert compare_runs(steps, bad, st['beam'], st['err'], gap + 1e-9, 1.0, 1.0)[0] == 'tie'
+
+
+def test_fit_level_tie_rule():
+    """planner_compare.fit_level_tie: a reversed pair counts only if the reference's own values are within 2 eval_tol."""
+    from planner_compare import fit_level_tie
+    hist = [(0.0, 0.0750565), (0.00025, 0.0750567), (0.0005, 0.0750559), (0.001, 0.0750546)]
+    same = [h[1] for h in hist]
+    assert fit_level_tie(hist, same, 2e-6) is None                             # same order everywhere: no evidence
+    flipped = [0.0750574, 0.0750567, 0.0750560, 0.0750546]                     # f(0) re-scored above f(0.00025)
+    assert fit_level_tie(hist, flipped, 2e-6) == (0, 1)
+    assert fit_level_tie(hist, flipped, 5e-8) is None                          # ... but not a tie at a 1e-7 tolerance
