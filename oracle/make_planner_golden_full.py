@@ -3,6 +3,7 @@
     python -m oracle.make_planner_golden_full c3   [n_pairs]   # 3x128x128, beam 8 (BASELINE config 3's shape)
     python -m oracle.make_planner_golden_full c5   [n_pairs]   # 3x256x256, beam 8 (GIER-shaped, config 5)
     python -m oracle.make_planner_golden_full eps  [n_pairs]   # utils/beam_search_eps_greedy.py, random.seed(0), 32x32
+    python -m oracle.make_planner_golden_full c3a | c5a [n]    # the same pairs with the L1 summed in float64 (see below)
 
 writes tests/golden/planner_full_<mode>.npz (uint8 image pairs) and planner_full_<mode>.json.
 
@@ -14,6 +15,15 @@ the distance array / order of its np.argsort, so that a test can show whether a 
 implementation's run was tied within tolerance in the reference's own run.  The reference's code is not modified: the
 module-level names `get_param`, `get_dist`, `minimize` and `np` that beam_search looks up are wrapped by recording
 pass-throughs.  For the 1-parameter fits the whole Nelder-Mead evaluation history (x, f) is kept as well.
+
+The `a` modes (c3a, c5a: json only, the images are those of c3 / c5) change ONE thing, and say so in their settings
+('l1_sum': 'float64'): get_dist's `(x1 - x2).norm(1)` (utils/beam_search.py:173) is summed in float64 and rounded to the
+tensors' dtype.  Why: on the CPU torch sums an fp32 norm(1) in a few long fp32 accumulator chains, which at 49 152 /
+196 608 elements carries 1e-5 / 1e-4 of accumulation noise (measured against float64; it depends on the thread count and the
+vector width) -- more than the change of the L1 across Nelder-Mead's first steps of 2.5e-4, so the unmodified reference's
+1-parameter fits stop inside that noise after 6-14 evaluations on this host.  On the device the reference is written
+for (utils/beam_search.py:29, CUDA) norm(1) is a tree reduction that is accurate to an ulp or two; the `a` transcripts
+are what the reference's planner does with such a sum.  Both kinds are committed and tested.
 
 Inputs are 8-bit images (x / 255, as utils/visual_utils.py:61-70 produces them): a smooth random colour field plus
 noise, the target a planted chain of 2-4 operators re-quantised to 8 bits, so the fixture stores uint8.
@@ -33,6 +43,8 @@ PLANTED = [[0, 1], [2, 6], [5, 0], [1, 2, 6], [6, 0], [0, 2], [1, 5], [2, 0, 1],
            [2, 5], [3, 6, 0], [0, 1, 2, 5], [6, 2, 1]]
 MODES = {'c3': dict(H=128, W=128, beam=8, seed=4000, variant='default'),
          'c5': dict(H=256, W=256, beam=8, seed=5000, variant='default'),
+         'c3a': dict(H=128, W=128, beam=8, seed=4000, variant='default', accurate_l1=True, images='c3'),
+         'c5a': dict(H=256, W=256, beam=8, seed=5000, variant='default', accurate_l1=True, images='c5'),
          'eps': dict(H=32, W=32, beam=8, seed=6000, variant='eps_greedy')}
 
 
@@ -106,7 +118,11 @@ def run_pair(job):
         return param, ok
 
     def get_dist(x1, x2, dist_type):
-        d = orig_get_dist(x1, x2, dist_type)
+        if cfg.get('accurate_l1'):
+            assert dist_type == 'L1'
+            d = ((x1 - x2).double().norm(1) / x1.numel()).to(torch.result_type(x1, x2))
+        else:
+            d = orig_get_dist(x1, x2, dist_type)
         if state['in_fit']:
             state['nfev'] += 1
         else:
@@ -166,11 +182,17 @@ def main():
         jobs = [(mode, i, None) for i in range(n)]
     with mp.get_context('spawn').Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
         res = pool.map(run_pair, jobs, chunksize=1)
-    np.savez_compressed(os.path.join(OUT, 'planner_full_%s.npz' % mode), I0=np.concatenate([r[1] for r in res]),
-                        Igt=np.concatenate([r[2] for r in res]))
+    if cfg.get('images'):
+        d = np.load(os.path.join(OUT, 'planner_full_%s.npz' % cfg['images']))      # same seeds -> the same pairs
+        assert np.array_equal(d['I0'][:n], np.concatenate([r[1] for r in res])) and np.array_equal(d['Igt'][:n], np.concatenate([r[2] for r in res]))
+    else:
+        np.savez_compressed(os.path.join(OUT, 'planner_full_%s.npz' % mode), I0=np.concatenate([r[1] for r in res]),
+                            Igt=np.concatenate([r[2] for r in res]))
     with open(os.path.join(OUT, 'planner_full_%s.json' % mode), 'w') as f:
         json.dump({'settings': {'beam': cfg['beam'], 'operations': GLOBAL_OPS, 'max_step': len(GLOBAL_OPS), 'err': 1e-2,
-                                'variant': cfg['variant'], 'shape': [3, cfg['H'], cfg['W']]},
+                                'variant': cfg['variant'], 'shape': [3, cfg['H'], cfg['W']],
+                                'l1_sum': 'float64' if cfg.get('accurate_l1') else 'torch CPU fp32 norm(1), 1 thread',
+                                'images': 'planner_full_%s.npz' % cfg.get('images', mode)},
                    'pairs': [r[0] for r in res]}, f, separators=(',', ':'))
 
 

@@ -166,6 +166,24 @@ def actor_options(**over):
     return opt
 
 
+def _lengths_compat():
+    """models/lang_encoder.py:94 hands pack_padded_sequence the lengths as a tensor on the model's device, which the
+    torch the reference was written for accepted; this image's torch (2.11) wants them on the CPU.  Version shim, like
+    the import shims above: the lengths are moved, nothing else changes."""
+    import torch
+    import torch.nn.utils.rnn as rnn
+    if getattr(rnn.pack_padded_sequence, '_t2o_compat', False):
+        return
+    orig = rnn.pack_padded_sequence
+
+    def pack_padded_sequence(input, lengths, *a, **k):
+        if isinstance(lengths, torch.Tensor) and lengths.is_cuda:
+            lengths = lengths.cpu()
+        return orig(input, lengths, *a, **k)
+    pack_padded_sequence._t2o_compat = True
+    rnn.pack_padded_sequence = pack_padded_sequence
+
+
 def build_actor(opt, executor_cls=None, seed=10):
     """models/actor.py:Actor of the reference, unmodified.  `executor_cls` stands in for the name `Executor` the module
     imported from executors.executor (models/actor.py:11,49) -- this is the whole switch a user of the reference makes
@@ -173,6 +191,7 @@ def build_actor(opt, executor_cls=None, seed=10):
     by a seeded random table of the same shape; everything else is the reference's own code and initialisation."""
     import torch
     load()
+    _lengths_compat()
     import models.actor as actor_mod
     from utils.text_utils import load_vocab
     n_vocab = len(load_vocab(opt.vocab_dir, opt.dataset, opt.session)[0])

@@ -393,7 +393,19 @@ T2O_HD void acc_to_slots(const GradAcc &a, float *v) {     // v[ACC_SLOTS]
 // Each *_bwd takes the operator input x = (r,g,b), the mask, the upstream gradient
 // (gr,gg,gb) = dLoss/d(out) and returns dLoss/d(x) in place.  The parameter-gradient contribution goes
 // to `acc` when `own` is true (halo pixels recompute but must not accumulate).
-template <bool HM>
+// Routing of a gradient that arrives at max(r, g, b) / min(r, g, b): torch's max(dim) / min(dim) send it to the FIRST
+// channel attaining the value (v is one of r, g, b, so equality tests find it).
+T2O_HD void route3(float r, float g, float b, float v, float G, float &gr, float &gg, float &gb) {
+    const bool e0 = r == v, e1 = !e0 && g == v, e2 = !e0 && !e1;     // three independent predicated adds, no branch
+    if (e0) gr += G;
+    if (e1) gg += G;
+    if (e2) gb += G;
+}
+
+// CL: the input is the clamped output of another operator (in [0, 1]).  The outputs of brightness and saturation then lie
+// in [0, 1] by construction (y_c = v' w_c with v', w_c in [0, 1]; y_c = v - u_c v s'/d in [0, v]), so the output clamp
+// always passes the gradient and its gate (recompute y_c, compare, select) is dropped.
+template <bool HM, bool CL = false>
 T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
                            float &gr, float &gg, float &gb, float &acc, bool own) {
     const float q = tab[1];
@@ -405,24 +417,24 @@ T2O_HD void brightness_bwd(const float *tab, float r, float g, float b, float mr
     const float ipq = ip ? q : 0.0f;
     const float wr = fmaf(r - v, inv, 1.0f), wg = fmaf(g - v, inv, 1.0f), wb = fmaf(b - v, inv, 1.0f);
     float gyr, gyg, gyb, gdr, gdg, gdb;
-    blend_bwd<HM>(v2 * wr, r, mr, gr, gyr, gdr);
-    blend_bwd<HM>(v2 * wg, g, mg, gg, gyg, gdg);
-    blend_bwd<HM>(v2 * wb, b, mb, gb, gyb, gdb);
-    const float G = gyr * wr + gyg * wg + gyb * wb;                   // dLoss/d v'
-    if (own) acc += ip ? v * G : 0.0f;
-    if (v == mn) {          // gray pixel: the reference routes everything through max -> channel 0
-        gr = gdr + G * ipq; gg = gdg; gb = gdb;
-        return;
+    if (HM || !CL) {
+        blend_bwd<HM>(v2 * wr, r, mr, gr, gyr, gdr);
+        blend_bwd<HM>(v2 * wg, g, mg, gg, gyg, gdg);
+        blend_bwd<HM>(v2 * wb, b, mb, gb, gyb, gdb);
+    } else {
+        gyr = gr; gyg = gg; gyb = gb; gdr = 0.0f; gdg = 0.0f; gdb = 0.0f;
     }
-    const float k = v2 * inv;
-    const float Gv = G * (ipq - k);
-    const int im = argmax3(r, g, b);
-    gr = fmaf(gyr, k, gdr) + (im == 0 ? Gv : 0.0f);
-    gg = fmaf(gyg, k, gdg) + (im == 1 ? Gv : 0.0f);
-    gb = fmaf(gyb, k, gdb) + (im == 2 ? Gv : 0.0f);
+    const float G = gyr * wr + gyg * wg + gyb * wb;                   // dLoss/d v'
+    if (own) acc = fmaf(ip ? v : 0.0f, G, acc);
+    // y_c = v' (1 + (c - v) inv): the direct path has slope k = v' inv, the path through v = max the slope
+    // G (dv'/dv - k).  A gray pixel (v == mn) has no direct path in the reference (hsv_to_rgb with s = 0 returns v for
+    // every channel): everything goes through max -> channel 0, which is k = 0 here.
+    const float k = v == mn ? 0.0f : v2 * inv;
+    gr = fmaf(gyr, k, gdr); gg = fmaf(gyg, k, gdg); gb = fmaf(gyb, k, gdb);
+    route3(r, g, b, v, G * (ipq - k), gr, gg, gb);
 }
 
-template <bool HM>
+template <bool HM, bool CL = false>
 T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr, float mg, float mb,
                            float &gr, float &gg, float &gb, float &acc, bool own) {
     const float q = tab[1];
@@ -432,34 +444,33 @@ T2O_HD void saturation_bwd(const float *tab, float r, float g, float b, float mr
     const float t = d * inv * q;
     const float s2 = sat01(t);
     const float id = rcp(fmaxf(d, 1e-30f));
-    const float rho = s2 * id;
+    const float rho = s2 * id;                                         // s' / d  (d == 0  =>  s' == 0  =>  rho == 0)
     const float ur = v - r, ug = v - g, ub = v - b;
     const float vr = v * rho;
     float gyr, gyg, gyb, gdr, gdg, gdb;
-    blend_bwd<HM>(fmaf(-ur, vr, v), r, mr, gr, gyr, gdr);
-    blend_bwd<HM>(fmaf(-ug, vr, v), g, mg, gg, gyg, gdg);
-    blend_bwd<HM>(fmaf(-ub, vr, v), b, mb, gb, gyb, gdb);
+    if (HM || !CL) {
+        blend_bwd<HM>(fmaf(-ur, vr, v), r, mr, gr, gyr, gdr);
+        blend_bwd<HM>(fmaf(-ug, vr, v), g, mg, gg, gyg, gdg);
+        blend_bwd<HM>(fmaf(-ub, vr, v), b, mb, gb, gyb, gdb);
+    } else {
+        gyr = gr; gyg = gg; gyb = gb; gdr = 0.0f; gdg = 0.0f; gdb = 0.0f;
+    }
     const float Sg = gyr + gyg + gyb;
-    if (!(d > 0.0f)) {      // gray pixel: y = v for every channel, max -> channel 0
-        gr = gdr + Sg; gg = gdg; gb = gdb;
-        return;
-    }
     const float Su = gyr * ur + gyg * ug + gyb * ub;
-    float rho_v, rho_mn;
-    if (in01(t)) {          // s' = s q  ->  rho = q / (v + eps)
-        if (own) acc -= v * inv * Su;
-        rho_v = -q * inv * inv; rho_mn = 0.0f;
-    } else if (t > 1.0f) {  // s' = 1    ->  rho = 1 / d
-        rho_v = -id * id; rho_mn = id * id;
-    } else {                // s' = 0
-        rho_v = 0.0f; rho_mn = 0.0f;
-    }
-    const float Gv = Sg - rho * Su - vr * Sg - v * rho_v * Su;
-    const float Gmn = -v * rho_mn * Su;
-    const int im = argmax3(r, g, b), in = argmin3(r, g, b);
-    gr = fmaf(gyr, vr, gdr) + (im == 0 ? Gv : 0.0f) + (in == 0 ? Gmn : 0.0f);
-    gg = fmaf(gyg, vr, gdg) + (im == 1 ? Gv : 0.0f) + (in == 1 ? Gmn : 0.0f);
-    gb = fmaf(gyb, vr, gdb) + (im == 2 ? Gv : 0.0f) + (in == 2 ? Gmn : 0.0f);
+    // y_c = v - u_c v rho with rho = s'/d in three regimes of s' = clamp(s q): linear (rho = q/(v+eps)), saturated at 1
+    // (rho = 1/d), cut at 0 (rho = 0).  In all of them d rho/dv = -rho e and d rho/d mn = rho eB with
+    // e = 1/(v+eps) | 1/d | 0 and eB = 0 | 1/d | 0.  A gray pixel (d == 0) is the linear regime with rho = 0: all that is
+    // left is Sg through max -> channel 0, as the reference routes it.
+    const bool lin = in01(t);
+    const float eB = t > 1.0f ? id : 0.0f;
+    const float e = lin ? inv : eB;
+    if (own) acc = fmaf(lin ? -(v * inv) : 0.0f, Su, acc);
+    const float A1 = fmaf(-(v * e), rho, rho);                          // rho + v d rho/dv
+    const float Gv = fmaf(-Su, A1, fmaf(-vr, Sg, Sg));
+    const float Gmn = -(vr * eB) * Su;
+    gr = fmaf(gyr, vr, gdr); gg = fmaf(gyg, vr, gdg); gb = fmaf(gyb, vr, gdb);
+    route3(r, g, b, v, Gv, gr, gg, gb);
+    route3(r, g, b, mn, Gmn, gr, gg, gb);
 }
 
 template <bool HM>
@@ -468,9 +479,9 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     const float p = tab[0];
     const float lum = lum_rn(r, g, b);
     const float L = sat01(lum);
-    // torch.min(torch.max(lum, 0), 1): binary max/min split the gradient 0.5/0.5 on ties
-    const float f0 = lum > 0.0f ? 1.0f : (lum == 0.0f ? 0.5f : 0.0f);
-    const float f1 = L < 1.0f ? 1.0f : (fmaxf(lum, 0.0f) == 1.0f ? 0.5f : 0.0f);
+    // torch.min(torch.max(lum, 0), 1) splits the gradient 0.5 / 0.5 on ties.  Only the upper one can matter: for
+    // lum <= 0 the factor it multiplies, dR below, is exactly 0 (L = 0 gives sin = 0).
+    const float pf = lum < 1.0f ? p : (lum == 1.0f ? 0.5f * p : 0.0f);
     const float sh = sin_halfpi(L), ch = cos_halfpi(L);
     const float cl = sh * sh;                       // 0.5 - 0.5 cos(pi L)
     const float dcl = PI_F * sh * ch;               // 0.5 pi sin(pi L)
@@ -484,10 +495,10 @@ T2O_HD void contrast_bwd(const float *tab, float r, float g, float b, float mr, 
     blend_bwd<HM>(b * F, b, mb, gb, gyb, gdb);
     const float Sgc = gyr * r + gyg * g + gyb * b;
     if (own) acc = fmaf(R - 1.0f, Sgc, acc);
-    const float k = p * dR * f0 * f1 * Sgc;
-    gr = fmaf(gyr, F, gdr) + 0.27f * k;
-    gg = fmaf(gyg, F, gdg) + 0.67f * k;
-    gb = fmaf(gyb, F, gdb) + 0.06f * k;
+    const float k = pf * dR * Sgc;
+    gr = fmaf(0.27f, k, fmaf(gyr, F, gdr));
+    gg = fmaf(0.67f, k, fmaf(gyg, F, gdg));
+    gb = fmaf(0.06f, k, fmaf(gyb, F, gdb));
 }
 
 template <bool HM>
@@ -565,9 +576,9 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
                           float mr, float mg, float mb,
                           float &gr, float &gg, float &gb, GradAcc &A, bool own) {
     switch (op) {
-        case OP_BRIGHTNESS: brightness_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.bright, own); break;
+        case OP_BRIGHTNESS: brightness_bwd<HM, CL>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.bright, own); break;
         case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.contrast, own); break;
-        case OP_SATURATION: saturation_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.satur, own); break;
+        case OP_SATURATION: saturation_bwd<HM, CL>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.satur, own); break;
         case OP_TONE:
             gr = curve_bwd<HM, CL>(tab, L, r, mr, gr, A.tone, own);
             gg = curve_bwd<HM, CL>(tab, L, g, mg, gg, A.tone, own);

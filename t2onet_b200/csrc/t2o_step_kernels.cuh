@@ -174,9 +174,9 @@ __device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, cons
             pointwise_bwd<HM, CL>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],    \
                                   g[0][v], g[1][v], g[2][v], A, own);
     switch (op) {
-        case OP_BRIGHTNESS: T2O_CASE(OP_BRIGHTNESS, false) break;
+        case OP_BRIGHTNESS: if (cl) { T2O_CASE(OP_BRIGHTNESS, true) } else { T2O_CASE(OP_BRIGHTNESS, false) } break;
         case OP_CONTRAST: T2O_CASE(OP_CONTRAST, false) break;
-        case OP_SATURATION: T2O_CASE(OP_SATURATION, false) break;
+        case OP_SATURATION: if (cl) { T2O_CASE(OP_SATURATION, true) } else { T2O_CASE(OP_SATURATION, false) } break;
         case OP_COLOR: if (cl) { T2O_CASE(OP_COLOR, true) } else { T2O_CASE(OP_COLOR, false) } break;
         case OP_TONE: if (cl) { T2O_CASE(OP_TONE, true) } else { T2O_CASE(OP_TONE, false) } break;
         case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
