@@ -11,7 +11,7 @@ G = os.path.join(ROOT, 'tests', 'golden')
 
 def load(mode):
     rec = json.load(open(os.path.join(G, 'planner_full_%s.json' % mode)))
-    d = np.load(os.path.join(G, 'planner_full_%s.npz' % mode))
+    d = np.load(os.path.join(G, rec['settings'].get('images', 'planner_full_%s.npz' % mode)))
     return rec, (torch.from_numpy(d['I0']).float() / 255).cuda(), (torch.from_numpy(d['Igt']).float() / 255).cuda()
 
 def eval_fn(ex, I0_m, Igt_m):

@@ -44,7 +44,7 @@ constexpr int MAX_CHAIN = 8;
 constexpr int MAX_L = 8;    // even (the gradient accumulators are paired)
 constexpr int TAB = 128;   // floats in one (image, op) table
 constexpr int CT = 40;     // floats in one curve table: 9 segments x (k', Q, knot slope, 0), then 1/S, L/S
-constexpr int CT_INVS = 36, CT_SCALE = 37;
+constexpr int CT_INVS = 36, CT_SCALE = 37, CT_INRANGE = 38;   // CT_INRANGE: 1.0f if the curve maps [0, 1] into [0, 1] (see build_curve)
 constexpr int NBIN = MAX_L + 1;   // segments of one curve table (entry L repeats L-1: it serves x == 1.0)
 constexpr float HSV_EPS = 1e-6f;     // kornia.rgb_to_hsv eps
 constexpr float LUM_EPS = 1e-6f;     // models/operators.py:244
@@ -150,7 +150,8 @@ T2O_HD float lum_rn(float r, float g, float b) {
 // whitebal.  : tab[0..2]
 // tone       : one curve table at tab[0]
 // color      : three curve tables at tab[0], tab[CT], tab[2*CT]
-// curve table: segment j = 0..L at ct[4j]: (k'_j, Q_j, K_j, 0) with K_j = k'_j + k'_{j-1} for 0 < j < L, else k'_j:
+// curve table: segment j = 0..L at ct[4j]: (k'_j, Q_j, K_j, k'_j) with K_j = k'_j + k'_{j-1} for 0 < j < L, else k'_j
+//              (the forward loads the first half of a record, the gate-free backward the second, the gated backward all of it):
 //              at an exact knot x = j/L both neighbouring clamp terms of the reference pass the gradient (closed
 //              intervals), so dy/dx = K_j there.  Segment L repeats L-1 and serves x == 1.0.
 //              ct[CT_INVS] = 1/S, ct[CT_SCALE] = L/S
@@ -171,7 +172,7 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
         ct[4 * j] = kp;
         ct[4 * j + 1] = q;
         ct[4 * j + 2] = (j > 0 && j < L) ? kp + k[j - 1] * scale : kp;
-        ct[4 * j + 3] = 0.0f;
+        ct[4 * j + 3] = kp;
     }
     // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
     // which would make the output clamp swallow the gradient of every saturated (x == 1.0) pixel.
@@ -185,9 +186,18 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     ct[4 * L] = ct[4 * (L - 1)];
     ct[4 * L + 1] = ct[4 * (L - 1) + 1];
     ct[4 * L + 2] = ct[4 * (L - 1)];
-    ct[4 * L + 3] = 0.0f;
+    ct[4 * L + 3] = ct[4 * (L - 1)];
     ct[CT_INVS] = 1.0f / S;
     ct[CT_SCALE] = scale;
+    // Does the output clamp ever cut this curve?  y is linear on a segment and fmaf is monotone in x, so it is enough to
+    // evaluate both ends of every segment the way the kernels do.  All k_i >= 0 (every curve the Actor's regressors
+    // produce) gives 1: the backward then skips the clamp gate of this curve.
+    bool inr = true;
+    for (int j = 0; j < L; ++j) {
+        const float y0 = fmaf(ct[4 * j], (float)j * invL, ct[4 * j + 1]), y1 = fmaf(ct[4 * j], (float)(j + 1) * invL, ct[4 * j + 1]);
+        inr = inr && y0 >= 0.0f && y0 <= 1.0f && y1 >= 0.0f && y1 <= 1.0f;
+    }
+    ct[CT_INRANGE] = inr ? 1.0f : 0.0f;
 }
 
 T2O_HD void build_table(int op, const float *p, int L, float *tab) {
@@ -279,28 +289,69 @@ T2O_HD void hue_y(const float *tab, float r, float g, float b, float &yr, float 
     yr = fmaf(-tab[1], vs, v); yg = fmaf(-tab[2], vs, v); yb = fmaf(-tab[3], vs, v);
 }
 
-// bin of a clamped input xs in [0, 1]: j = floor(L xs) in 0..L, t = L xs, tf = float(j); returns the segment
-// record of bin j.  On the device the record's address comes straight from the bit pattern of 2^23 + floor(t)
-// (0x4B000000 + j): one shift-add, no mask (xs is clamped, so j <= L always).
-T2O_HD const float *curve_seg(const float *ct, float xs, int L, float &t, float &tf) {
-    t = xs * (float)L;
-#if defined(__CUDA_ARCH__)
-    const float u = __fadd_rd(t, 8388608.0f);       // 2^23 + floor(t): the low mantissa bits are the bin
-    tf = u - 8388608.0f;
-    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(ct) +
-                                           (((unsigned)__float_as_int(u) << 4) - (0x4B000000u << 4)));
-#else
-    tf = floorf(t);
-    return ct + 4 * (int)tf;
-#endif
-}
+// Segment lookup of a clamped input xs in [0, 1]: bin j = floor(L xs) in 0..L, record j of the table.
+// On the device the bin comes from a round-down add against 2.0f: with tt = xs * (L * 2^-22) the sum 2 + tt rounds down to
+// 2 + j * 2^-22 (the ulp of [2, 4) is 2^-22), whose bit pattern is 0x40000000 + j.  Shifted left by 4 the exponent drops
+// out and 16 j is left: the record's SHARED-MEMORY address is ONE shift-add on top of the table's base, no mask (xs is
+// clamped, so j <= L always), no float->int conversion.  Every kernel keeps its operator tables in shared memory
+// (StepShared::tabs, ChainShared::tabs, the scorer's wtab).  The scaling by 2^-22 is exact, so tt == u - 2 exactly when
+// L xs is an integer (the knot test of the backward), and fma(tt, 2^22, -i) is the correctly rounded L xs - i.
 struct F4 { float a, b, c, d; };   // == float4
+constexpr float CURVE_TT = 1.0f / 4194304.0f, CURVE_TT_INV = 4194304.0f;   // 2^-22, 2^22
+// -> tt = L xs 2^-22, tfs = j 2^-22; seg = (k'_j, Q_j[, K_j, 0])
+T2O_HD F2 curve_seg2(const float *ct, float xs, int L, float &tt, float &tfs) {
+    tt = xs * ((float)L * CURVE_TT);
+    F2 seg;
+#if defined(__CUDA_ARCH__)
+    const float u = __fadd_rd(tt, 2.0f);
+    tfs = u - 2.0f;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(seg.a), "=f"(seg.b)
+        : "r"((__float_as_uint(u) << 4) + (unsigned)__cvta_generic_to_shared(ct)));
+#else
+    const float tf = floorf(tt * CURVE_TT_INV);
+    tfs = tf * CURVE_TT;
+    seg.a = ct[4 * (int)tf]; seg.b = ct[4 * (int)tf + 1];
+#endif
+    return seg;
+}
+// the second half of the record: (K_j, k'_j)
+T2O_HD F2 curve_seg2hi(const float *ct, float xs, int L, float &tt, float &tfs) {
+    tt = xs * ((float)L * CURVE_TT);
+    F2 seg;
+#if defined(__CUDA_ARCH__)
+    const float u = __fadd_rd(tt, 2.0f);
+    tfs = u - 2.0f;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(seg.a), "=f"(seg.b)
+        : "r"((__float_as_uint(u) << 4) + (unsigned)__cvta_generic_to_shared(ct)));
+#else
+    const float tf = floorf(tt * CURVE_TT_INV);
+    tfs = tf * CURVE_TT;
+    seg.a = ct[4 * (int)tf + 2]; seg.b = ct[4 * (int)tf + 3];
+#endif
+    return seg;
+}
+T2O_HD F4 curve_seg4(const float *ct, float xs, int L, float &tt, float &tfs) {
+    tt = xs * ((float)L * CURVE_TT);
+    F4 seg;
+#if defined(__CUDA_ARCH__)
+    const float u = __fadd_rd(tt, 2.0f);
+    tfs = u - 2.0f;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(seg.a), "=f"(seg.b), "=f"(seg.c), "=f"(seg.d)
+        : "r"((__float_as_uint(u) << 4) + (unsigned)__cvta_generic_to_shared(ct)));
+#else
+    const float tf = floorf(tt * CURVE_TT_INV);
+    tfs = tf * CURVE_TT;
+    const float *q = ct + 4 * (int)tf;
+    seg.a = q[0]; seg.b = q[1]; seg.c = q[2]; seg.d = q[3];
+#endif
+    return seg;
+}
 // CL: the input is known to lie in [0, 1] (it is the clamped output of the previous operator)
 template <bool CL>
 T2O_HD float curve_y(const float *ct, int L, float x) {
     const float xs = CL ? x : sat01(x);
-    float t, tf;
-    const F2 seg = *reinterpret_cast<const F2 *>(curve_seg(ct, xs, L, t, tf));
+    float tt, tfs;
+    const F2 seg = curve_seg2(ct, xs, L, tt, tfs);
     return fmaf(seg.a, xs, seg.b);
 }
 
@@ -544,23 +595,33 @@ T2O_HD void hue_bwd(const float *tab, float r, float g, float b, float mr, float
 }
 
 // one channel of a curve operator: G[i] += g * clamp(L x - i, 0, 1)
-template <bool HM, bool CL>
+// NG: the curve maps [0, 1] into [0, 1] (ct[CT_INRANGE]) and there is no mask: the output clamp passes every gradient
+template <bool HM, bool CL, bool NG = false>
 T2O_HD float curve_bwd(const float *ct, int L, float x, float m, float g, F2 *G, bool own) {
     const float xs = CL ? x : sat01(x);
-    float t, tf;
-    const F4 seg = *reinterpret_cast<const F4 *>(curve_seg(ct, xs, L, t, tf));
-    const float y = fmaf(seg.a, xs, seg.b);
-    float gy, gd;
-    blend_bwd<HM>(y, x, m, g, gy, gd);
+    float tt, tfs, gy = g, gd = 0.0f, k_knot, k_seg;
+    if (HM || !NG) {
+        const F4 seg = curve_seg4(ct, xs, L, tt, tfs);
+        blend_bwd<HM>(fmaf(seg.a, xs, seg.b), x, m, g, gy, gd);
+        k_knot = seg.c; k_seg = seg.a;
+    } else {
+        const F2 seg = curve_seg2hi(ct, xs, L, tt, tfs);
+        k_knot = seg.a; k_seg = seg.b;
+    }
     const float ga = own ? gy : 0.0f;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < MAX_L / 2; ++i)
-        G[i] = fma2(F2{ga, ga}, F2{sat01(t - (float)(2 * i)), sat01(t - (float)(2 * i + 1))}, G[i]);
-    const float slope = t == tf ? seg.c : seg.a;                    // exact knot: both clamp terms pass
+        G[i] = fma2(F2{ga, ga}, F2{sat01(fmaf(tt, CURVE_TT_INV, -(float)(2 * i))), sat01(fmaf(tt, CURVE_TT_INV, -(float)(2 * i + 1)))}, G[i]);
+    const float slope = tt == tfs ? k_knot : k_seg;                 // exact knot: both clamp terms pass
     const float gx = gy * slope;
     return gd + ((CL || in01(x)) ? gx : 0.0f);
+}
+// may the backward of this curve operator skip its clamp gates?  (uniform per image and operator)
+T2O_HD bool curve_in_range(int op, const float *tab) {
+    return op == OP_TONE ? tab[CT_INRANGE] != 0.0f
+                         : (tab[CT_INRANGE] != 0.0f && tab[CT + CT_INRANGE] != 0.0f && tab[2 * CT + CT_INRANGE] != 0.0f);
 }
 
 // dLoss/dk_i of one curve from its reduced accumulators G[0..L): (G[i] - C) / S with C = sum_j (k_j / S) G[j]
@@ -571,7 +632,7 @@ T2O_HD float curve_param_grad(const float *ct, int L, const float *G, int i) {
     return ct[CT_INVS] * (G[i] - C / (float)L);
 }
 
-template <bool HM, bool CL = false>
+template <bool HM, bool CL = false, bool NG = false>
 T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, float b,
                           float mr, float mg, float mb,
                           float &gr, float &gg, float &gb, GradAcc &A, bool own) {
@@ -580,14 +641,14 @@ T2O_HD void pointwise_bwd(int op, const float *tab, int L, float r, float g, flo
         case OP_CONTRAST: contrast_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.contrast, own); break;
         case OP_SATURATION: saturation_bwd<HM, CL>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.satur, own); break;
         case OP_TONE:
-            gr = curve_bwd<HM, CL>(tab, L, r, mr, gr, A.tone, own);
-            gg = curve_bwd<HM, CL>(tab, L, g, mg, gg, A.tone, own);
-            gb = curve_bwd<HM, CL>(tab, L, b, mb, gb, A.tone, own);
+            gr = curve_bwd<HM, CL, NG>(tab, L, r, mr, gr, A.tone, own);
+            gg = curve_bwd<HM, CL, NG>(tab, L, g, mg, gg, A.tone, own);
+            gb = curve_bwd<HM, CL, NG>(tab, L, b, mb, gb, A.tone, own);
             break;
         case OP_COLOR:
-            gr = curve_bwd<HM, CL>(tab, L, r, mr, gr, A.color[0], own);
-            gg = curve_bwd<HM, CL>(tab + CT, L, g, mg, gg, A.color[1], own);
-            gb = curve_bwd<HM, CL>(tab + 2 * CT, L, b, mb, gb, A.color[2], own);
+            gr = curve_bwd<HM, CL, NG>(tab, L, r, mr, gr, A.color[0], own);
+            gg = curve_bwd<HM, CL, NG>(tab + CT, L, g, mg, gg, A.color[1], own);
+            gb = curve_bwd<HM, CL, NG>(tab + 2 * CT, L, b, mb, gb, A.color[2], own);
             break;
         case OP_BNW: bnw_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.bnw, own); break;
         case OP_HUE: hue_bwd<HM>(tab, r, g, b, mr, mg, mb, gr, gg, gb, A.hue, own); break;

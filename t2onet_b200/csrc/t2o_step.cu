@@ -97,7 +97,7 @@ static size_t rows_smem_bytes(int n, int sharp, int vec, bool has_mask, int SNT)
     return (stage + (has_mask ? 3 : 2) * ringf + ntp * RING * 3 * 32 * vec + ntq * 3 * SNT * vec) * sizeof(float);
 }
 
-template <int VEC, bool HM, int NTH, unsigned int SP>
+template <int VEC, bool HM, int NTH, unsigned int SP, int MINB = 2>
 static int launch_step_sp(StepArgs &a, cudaStream_t stream) {
     const bool rows = a.ch.sharp >= 0;
     const int B = a.g.B, H = a.g.H, W = a.g.W;
@@ -114,11 +114,11 @@ static int launch_step_sp(StepArgs &a, cudaStream_t stream) {
     } else {
         if constexpr (SP == 0u || sp_sharp(SP) >= 0) {
             smem = rows_smem_bytes(a.ch.n, a.ch.sharp, VEC, HM, NTH);
-            int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, false, SP>, smem);
+            int st = step_set_smem(step_sharp_kernel<VEC, HM, NTH, false, SP, MINB>, smem);
             if (st) return st;
-            geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, false, SP>, NTH, smem), NTH, 4);
+            geom_step_rows(a.g, B, H, W, VEC, NUM_SMS * resident_ctas(step_sharp_kernel<VEC, HM, NTH, false, SP, MINB>, NTH, smem), NTH, 4);
             dim3 grid(a.g.nchunks, B);
-            step_sharp_kernel<VEC, HM, NTH, false, SP><<<grid, NTH, smem, stream>>>(a);
+            step_sharp_kernel<VEC, HM, NTH, false, SP, MINB><<<grid, NTH, smem, stream>>>(a);
         }
     }
     T2O_CUDA_OK(cudaGetLastError());
@@ -136,7 +136,11 @@ template <int VEC, bool HM, int NTH>
 static int launch_step(StepArgs &a, cudaStream_t stream) {
     if constexpr (VEC == 4 && !HM) {       // chain-specialised instantiations (unmasked, 128-bit groups)
         if (use_specialized()) {
-            if (a.ch.ops_packed == SP_C6) return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
+            if (a.ch.ops_packed == SP_C6) {
+                const char *e = getenv("T2O_STEP_VARIANT");       // experiment: 2-pixel groups, 3 CTAs per SM
+                if (e && e[0] == '2') { return launch_step_sp<2, HM, NTH, SP_C6, 3>(a, stream); }
+                return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
+            }
             if (a.ch.ops_packed == SP_P5) return launch_step_sp<VEC, HM, NTH, SP_P5>(a, stream);
         }
     }

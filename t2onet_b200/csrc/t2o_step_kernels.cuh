@@ -166,19 +166,39 @@ __device__ __forceinline__ void fwd_op_grp(int op, const float *tab, int L, floa
 #undef T2O_CASE
 }
 
+// every value of the group lies in [0, 1]: one unsigned compare on the bits of each pixel's max and min
+template <int VEC>
+__device__ __forceinline__ bool grp_in01(const float (&x)[3][VEC]) {
+    bool ok = true;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) ok = ok && in01(max3(x[0][v], x[1][v], x[2][v])) && in01(min3(x[0][v], x[1][v], x[2][v]));
+    return ok;
+}
+
 template <int VEC, bool HM>
 __device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, const float (&x)[3][VEC],
                                            const float (&m)[3][VEC], float (&g)[3][VEC], GradAcc &A, bool own, bool cl) {
-#define T2O_CASE(OPC, CL)                                                                               \
-        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                 \
-            pointwise_bwd<HM, CL>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],    \
-                                  g[0][v], g[1][v], g[2][v], A, own);
+#define T2O_CASE_NG(OPC, CL, NG)                                                                            \
+        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                     \
+            pointwise_bwd<HM, CL, NG>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v],    \
+                                      g[0][v], g[1][v], g[2][v], A, own);
+#define T2O_CASE(OPC, CL) T2O_CASE_NG(OPC, CL, false)
+    // curves that map [0, 1] into [0, 1] (every curve with non-negative parameters) take the variant without clamp gates:
+    // a branch that is uniform over the CTA (one image, one table)
+    // brightness / saturation on an input that is not known to be clamped (the first operator of a chain): the gates can
+    // only fire for pixels outside [0, 1]; a thread whose pixels are all inside takes the gate-free variant
+#define T2O_CASE_HSV(OPC)                                                                                    \
+        if (cl) { T2O_CASE(OPC, true) }                                                                      \
+        else if (!HM && grp_in01<VEC>(x)) { T2O_CASE(OPC, true) }                                            \
+        else { T2O_CASE(OPC, false) }
+#define T2O_CASE_CURVE(OPC, CL)                                                                              \
+        if (!HM && curve_in_range(OPC, tab)) { T2O_CASE_NG(OPC, CL, true) } else { T2O_CASE_NG(OPC, CL, false) }
     switch (op) {
-        case OP_BRIGHTNESS: if (cl) { T2O_CASE(OP_BRIGHTNESS, true) } else { T2O_CASE(OP_BRIGHTNESS, false) } break;
+        case OP_BRIGHTNESS: T2O_CASE_HSV(OP_BRIGHTNESS) break;
         case OP_CONTRAST: T2O_CASE(OP_CONTRAST, false) break;
-        case OP_SATURATION: if (cl) { T2O_CASE(OP_SATURATION, true) } else { T2O_CASE(OP_SATURATION, false) } break;
-        case OP_COLOR: if (cl) { T2O_CASE(OP_COLOR, true) } else { T2O_CASE(OP_COLOR, false) } break;
-        case OP_TONE: if (cl) { T2O_CASE(OP_TONE, true) } else { T2O_CASE(OP_TONE, false) } break;
+        case OP_SATURATION: T2O_CASE_HSV(OP_SATURATION) break;
+        case OP_COLOR: if (cl) { T2O_CASE_CURVE(OP_COLOR, true) } else { T2O_CASE_CURVE(OP_COLOR, false) } break;
+        case OP_TONE: if (cl) { T2O_CASE_CURVE(OP_TONE, true) } else { T2O_CASE_CURVE(OP_TONE, false) } break;
         case OP_WHITE: T2O_CASE(OP_WHITE, false) break;
         case OP_EXPOSURE: T2O_CASE(OP_EXPOSURE, false) break;
         case OP_WHITEBALANCE: T2O_CASE(OP_WHITEBALANCE, false) break;
@@ -187,6 +207,9 @@ __device__ __forceinline__ void bwd_op_grp(int op, const float *tab, int L, cons
         default: break;
     }
 #undef T2O_CASE
+#undef T2O_CASE_NG
+#undef T2O_CASE_CURVE
+#undef T2O_CASE_HSV
 }
 
 template <int VEC, bool HM>
@@ -491,8 +514,8 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
 // Shared-memory layout (compile-time strides): a ring row holds 3 planes of 34 groups (one zero pad group each
 // side of the 32 lanes); the tape of the operators before the stencil holds, per operator 1 .. sp-1, RING rows of
 // 3 x 32 vectors; the operators after the stencil keep a per-thread tape.
-template <int VEC, bool HM, int NTH, bool ROWS, unsigned int SP = 0u>
-__global__ void __launch_bounds__(NTH, 2) step_sharp_kernel(const __grid_constant__ StepArgs a) {
+template <int VEC, bool HM, int NTH, bool ROWS, unsigned int SP = 0u, int MINB = 2>
+__global__ void __launch_bounds__(NTH, MINB) step_sharp_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!(ROWS && SP), "per-row chains are dispatched at run time");
     constexpr int UNR = SP ? MAX_CHAIN : 1;
     constexpr int SPN = sp_count(SP), SPS = sp_sharp(SP), SPC = sp_clamped(SP);   // compile-time chain facts (SP != 0)

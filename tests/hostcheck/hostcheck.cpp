@@ -118,6 +118,9 @@ extern "C" int hc_chain(int n_ops, const int *ops, const int *poff, const float 
                 if (has_mask) {
                     if (cl) pointwise_bwd<true, true>(ops[k], tab, L, xr, xg, xb, M(0, i), M(1, i), M(2, i), gr, gg, gb, A, true);
                     else pointwise_bwd<true, false>(ops[k], tab, L, xr, xg, xb, M(0, i), M(1, i), M(2, i), gr, gg, gb, A, true);
+                } else if (op_is_curve(ops[k]) && curve_in_range(ops[k], tab)) {       // as bwd_op_grp dispatches
+                    if (cl) pointwise_bwd<false, true, true>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
+                    else pointwise_bwd<false, false, true>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
                 } else {
                     if (cl) pointwise_bwd<false, true>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
                     else pointwise_bwd<false, false>(ops[k], tab, L, xr, xg, xb, 1.f, 1.f, 1.f, gr, gg, gb, A, true);
