@@ -3,7 +3,7 @@
 by opcode class.  Usage: python scripts/dev/sass_phases.py ['<demangled kernel substring>'] [lib.so]"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-want = sys.argv[1] if len(sys.argv) > 1 else 'step_sharp_kernel<4, false, 256, false, 7750433u>'
+want = sys.argv[1] if len(sys.argv) > 1 else 'step_sharp_kernel<4, false, 256, false, 7750433u, 2>'
 lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, 't2onet_b200', 'lib', 'libt2o_b200.so')
 syms = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 mangled = re.findall(r'Function : (\S+)', syms)

@@ -136,11 +136,7 @@ template <int VEC, bool HM, int NTH>
 static int launch_step(StepArgs &a, cudaStream_t stream) {
     if constexpr (VEC == 4 && !HM) {       // chain-specialised instantiations (unmasked, 128-bit groups)
         if (use_specialized()) {
-            if (a.ch.ops_packed == SP_C6) {
-                const char *e = getenv("T2O_STEP_VARIANT");       // experiment: 2-pixel groups, 3 CTAs per SM
-                if (e && e[0] == '2') { return launch_step_sp<2, HM, NTH, SP_C6, 3>(a, stream); }
-                return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
-            }
+            if (a.ch.ops_packed == SP_C6) return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
             if (a.ch.ops_packed == SP_P5) return launch_step_sp<VEC, HM, NTH, SP_P5>(a, stream);
         }
     }
