@@ -155,6 +155,9 @@ T2O_HD float lum_rn(float r, float g, float b) {
 //              at an exact knot x = j/L both neighbouring clamp terms of the reference pass the gradient (closed
 //              intervals), so dy/dx = K_j there.  Segment L repeats L-1 and serves x == 1.0.
 //              ct[CT_INVS] = 1/S, ct[CT_SCALE] = L/S
+// BWD: also set CT_INRANGE (only the backward kernels read it; the forward kernels and the scorer, which builds a table per
+// candidate and round, skip the 2 L evaluations)
+template <bool BWD = true>
 T2O_HD void build_curve(const float *k, int L, float *ct) {
     float S = 0.0f;
     for (int i = 0; i < L; ++i) S += k[i];
@@ -192,6 +195,7 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     // Does the output clamp ever cut this curve?  y is linear on a segment and fmaf is monotone in x, so it is enough to
     // evaluate both ends of every segment the way the kernels do.  All k_i >= 0 (every curve the Actor's regressors
     // produce) gives 1: the backward then skips the clamp gate of this curve.
+    if (!BWD) return;
     bool inr = true;
     for (int j = 0; j < L; ++j) {
         const float y0 = fmaf(ct[4 * j], (float)j * invL, ct[4 * j + 1]), y1 = fmaf(ct[4 * j], (float)(j + 1) * invL, ct[4 * j + 1]);
@@ -200,6 +204,7 @@ T2O_HD void build_curve(const float *k, int L, float *ct) {
     ct[CT_INRANGE] = inr ? 1.0f : 0.0f;
 }
 
+template <bool BWD = true>
 T2O_HD void build_table(int op, const float *p, int L, float *tab) {
     switch (op) {
         case OP_BRIGHTNESS: case OP_SATURATION: tab[0] = p[0]; tab[1] = 1.0f + p[0]; break;
@@ -231,17 +236,18 @@ T2O_HD void build_table(int op, const float *p, int L, float *tab) {
         }
         case OP_EXPOSURE: tab[0] = p[0]; tab[1] = expf(p[0] * LN2_F); break;
         case OP_WHITEBALANCE: tab[0] = p[0]; tab[1] = p[1]; tab[2] = p[2]; break;
-        case OP_TONE: build_curve(p, L, tab); break;
-        case OP_COLOR: for (int c = 0; c < 3; ++c) build_curve(p + c * L, L, tab + c * CT); break;
+        case OP_TONE: build_curve<BWD>(p, L, tab); break;
+        case OP_COLOR: for (int c = 0; c < 3; ++c) build_curve<BWD>(p + c * L, L, tab + c * CT); break;
         default: break;
     }
 }
 
 // The same split in three: part c builds the c-th curve of a color operator, part 0 everything else -- so that three
 // threads per operator share the one table whose construction is long (3 x 9 segments, each with a division).
+template <bool BWD = true>
 T2O_HD void build_table_part(int op, int part, const float *p, int L, float *tab) {
-    if (op == OP_COLOR) build_curve(p + part * L, L, tab + part * CT);
-    else if (part == 0) build_table(op, p, L, tab);
+    if (op == OP_COLOR) build_curve<BWD>(p + part * L, L, tab + part * CT);
+    else if (part == 0) build_table<BWD>(op, p, L, tab);
 }
 
 // ---------------------------------------------------------------- blend + clamp (models/operators.py:129-130)

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         // few candidates: their tables are built while the tiles are in flight
         if (coop && warp < cend - cbeg && lane == 0) {
             const int op = a.cand_op[cbeg + warp];
-            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
+            if (op != OP_SKIP) build_table<false>(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
         }
         // bounded wait: a broken descriptor must fail loudly, not hang the GPU
         bool done = false;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         }
         if (coop && warp < cend - cbeg && lane == 0) {
             const int op = a.cand_op[cbeg + warp];
-            if (op != OP_SKIP) build_table(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
+            if (op != OP_SKIP) build_table<false>(op, a.cand_param + (size_t)(cbeg + warp) * T2O_MAX_OP_PARAMS, a.L, wtab[warp]);
         }
         __syncthreads();
     }
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
             const int op = a.cand_op[ci];
             if (op == OP_SKIP) continue;
             __syncwarp();
-            if (lane == 0) build_table(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
+            if (lane == 0) build_table<false>(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
             __syncwarp();
             const float sum = warp_sum(tile_sum(op, tab, lane, 32));
             if (lane == 0) a.part[(size_t)ci * a.ntiles + tile] = sum;
