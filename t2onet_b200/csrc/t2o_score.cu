@@ -59,6 +59,71 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, ui
         : "memory");
 }
 
+// One pixel group (VEC pixels x 3 channels) of a candidate: x = op(state group), sum += |x - target| element by element in
+// (channel, pixel) order.  `src` points at the group's first pixel in the staged state tile (rows `spitch` floats apart,
+// channels `cs` floats apart, one halo row / HX halo floats around it), `tsrc` at the same pixel of the staged target
+// (channels `ct` floats apart).  Shared by both scorer kernels so that their sums agree to the bit.
+template <int VEC>
+__device__ __forceinline__ void score_group(float &sum, int op, const float *tab, int L, float p, const float *src, int spitch, int cs,
+                                            const float *tsrc, int ct) {
+    float x[3][VEC], t[3][VEC];
+    if (op == OP_SHARPNESS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float *row = src + c * cs;
+            float ctr[VEC], up[VEC], dn[VEC];
+            lds_vec<VEC>(row, ctr);
+            lds_vec<VEC>(row - spitch, up);
+            lds_vec<VEC>(row + spitch, dn);
+            const float lf = row[-1], rt = row[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float l = v > 0 ? ctr[v - 1] : lf;
+                const float r = v < VEC - 1 ? ctr[v + 1] : rt;
+                x[c][v] = sat01(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]));
+            }
+        }
+    } else if (op == OP_BLUR) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float *row = src + c * cs, *ru = row - spitch, *rd = row + spitch;
+            float ctr[VEC], up[VEC], dn[VEC];
+            lds_vec<VEC>(row, ctr);
+            lds_vec<VEC>(ru, up);
+            lds_vec<VEC>(rd, dn);
+            const float lf = row[-1], rt = row[VEC], ul = ru[-1], ur = ru[VEC], dl = rd[-1], dr = rd[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
+                const float e = v > 0 ? up[v - 1] : ul, f = v < VEC - 1 ? up[v + 1] : ur;
+                const float g = v > 0 ? dn[v - 1] : dl, h = v < VEC - 1 ? dn[v + 1] : dr;
+                x[c][v] = sat01(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lds_vec<VEC>(src + c * cs, x[c]);
+        switch (op) {
+#define T2O_CASE(OPC)                                                                                         \
+    case OPC:                                                                                                 \
+        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                       \
+            op_apply<false>(OPC, tab, L, x[0][v], x[1][v], x[2][v], 1.0f, 1.0f, 1.0f);                             \
+        break;
+            T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
+            T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+            T2O_CASE(OP_BNW) T2O_CASE(OP_HUE)
+#undef T2O_CASE
+            default: break;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lds_vec<VEC>(tsrc + c * ct, t[c]);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum += fabsf(x[c][v] - t[c][v]);
+    }
+}
+
 // VEC = 4: W % 4 == 0, state rows padded by 4 floats each side (keeps 128-bit LDS aligned)
 // VEC = 1: any W, 1 float each side
 template <int VEC, bool USE_TMA>
@@ -148,64 +213,8 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         for (int gi = first; gi < ngroups; gi += stride) {
             const int ly = gi / TWg, lx = (gi - ly * TWg) * VEC;
             if (y0 + ly >= H || x0 + lx >= W) continue;       // ragged edge (W % VEC == 0)
-            float x[3][VEC], t[3][VEC];
-            const float *src = sS + (ly + 1) * spitch + HX + lx;
-            if (op == OP_SHARPNESS) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float *row = src + c * srows * spitch;
-                    float ctr[VEC], up[VEC], dn[VEC];
-                    lds_vec<VEC>(row, ctr);
-                    lds_vec<VEC>(row - spitch, up);
-                    lds_vec<VEC>(row + spitch, dn);
-                    const float lf = row[-1], rt = row[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float l = v > 0 ? ctr[v - 1] : lf;
-                        const float r = v < VEC - 1 ? ctr[v + 1] : rt;
-                        x[c][v] = sat01(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]));
-                    }
-                }
-            } else if (op == OP_BLUR) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float *row = src + c * srows * spitch, *ru = row - spitch, *rd = row + spitch;
-                    float ctr[VEC], up[VEC], dn[VEC];
-                    lds_vec<VEC>(row, ctr);
-                    lds_vec<VEC>(ru, up);
-                    lds_vec<VEC>(rd, dn);
-                    const float lf = row[-1], rt = row[VEC], ul = ru[-1], ur = ru[VEC], dl = rd[-1], dr = rd[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
-                        const float e = v > 0 ? up[v - 1] : ul, f = v < VEC - 1 ? up[v + 1] : ur;
-                        const float g = v > 0 ? dn[v - 1] : dl, h = v < VEC - 1 ? dn[v + 1] : dr;
-                        x[c][v] = sat01(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]));
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) lds_vec<VEC>(src + c * srows * spitch, x[c]);
-                switch (op) {
-#define T2O_CASE(OPC)                                                                                         \
-    case OPC:                                                                                                 \
-        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                       \
-            op_apply<false>(OPC, tab, a.L, x[0][v], x[1][v], x[2][v], 1.0f, 1.0f, 1.0f);                           \
-        break;
-                    T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
-                    T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
-                    T2O_CASE(OP_BNW) T2O_CASE(OP_HUE)
-#undef T2O_CASE
-                    default: break;
-                }
-            }
-            const float *tsrc = sT + ly * TW + lx;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                lds_vec<VEC>(tsrc + c * TH * TW, t[c]);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) sum += fabsf(x[c][v] - t[c][v]);
-            }
+            score_group<VEC>(sum, op, tab, a.L, p, sS + (ly + 1) * spitch + HX + lx, spitch, srows * spitch,
+                             sT + ly * TW + lx, TH * TW);
         }
         return sum;
     };
