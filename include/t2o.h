@@ -199,6 +199,20 @@ int t2o_score_candidates(const float *states, int S, const float *targets, int T
                          void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 
 /*
+ * The same with masks, as the GIER planner driver hands them over (preprocess/gen_greedy_seqs_GIER.py:60-62: a list of
+ * (1, 3, H, W) masks, the global all-ones one first, and the operator each local mask belongs to): candidate c edits
+ * its state inside mask cand_mask[c] of `masks` (n_masks, mask_ch, H, W; mask_ch 1 or 3; fp32 in [0, 1]),
+ *     l1_sum[c] = sum |clamp(op(state; param) * mask + state * (1 - mask)) - target|    (models/operators.py:129-130),
+ * or everywhere if cand_mask[c] < 0.
+ */
+int t2o_score_candidates_masked(const float *states, int S, const float *targets, int T,
+                                const int32_t *state_target, const int32_t *cand_begin,
+                                const int32_t *cand_op, const float *cand_param,
+                                const int32_t *cand_mask, const float *masks, int n_masks, int mask_ch, int C,
+                                float *l1_sum, int H, int W, int curve_steps,
+                                void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
+/*
  * Device-resident Nelder-Mead: P independent fits argmin_param L1(op(state; param), target), one per (state, operator)
  * pair of a planner step -- scipy.optimize.minimize(func, param0, method='Nelder-Mead') as utils/beam_search.py:88
  * calls it (scipy defaults: xatol = fatol = 1e-4, maxiter = maxfev = 200 N, initial simplex step 5 % / 2.5e-4),

@@ -28,13 +28,14 @@ def execute(I, operation, param, executor):
     return executor.execute(I, operation, None, features=None, specified_param=param, has_noise=False)[0]
 
 
-def get_param_naive(img, out, param0, executor, op_ind, counter=None):
-    """utils/beam_search.py:65-91 -- Nelder-Mead over the operator parameters."""
+def get_param_naive(img, out, param0, executor, op_ind, counter=None, mask=None):
+    """utils/beam_search.py:65-91 -- Nelder-Mead over the operator parameters.  `mask`: the argument the reference's
+    signature carries (:65) but never hands to the executor (:79 passes None); the GIER extension below does."""
     def func(param):
         if counter is not None:
             counter[0] += 1
         p = torch.tensor(np.array([param]), dtype=torch.float)
-        pred, _ = executor.execute(img, op_ind, None, specified_param=p, has_noise=False)
+        pred, _ = executor.execute(img, op_ind, mask, specified_param=p, has_noise=False)
         return get_dist(pred, out).item()
     res = minimize(func, param0, method='Nelder-Mead')
     return torch.tensor(np.array([list(res.x)])), res.success
@@ -71,7 +72,7 @@ def gd_minimize(func, param0, method='adam'):
     return param0.detach(), success
 
 
-def get_param(I0, I1, operation, executor, optimizer='Nelder-Mead', counter=None):
+def get_param(I0, I1, operation, executor, optimizer='Nelder-Mead', counter=None, mask=None):
     """utils/beam_search.py:148-162 -- zeros init for ops {0,1,2,6}, ones for {3,5}."""
     n = executor.get_param_num(operation)
     if operation in [0, 1, 2, 6]:
@@ -81,7 +82,8 @@ def get_param(I0, I1, operation, executor, optimizer='Nelder-Mead', counter=None
     else:
         assert False, 'the operation is not global operation'
     if optimizer == 'Nelder-Mead':
-        return get_param_naive(I0, I1, param0, executor, operation, counter)
+        return get_param_naive(I0, I1, param0, executor, operation, counter, mask)
+    assert mask is None
     param0 = param0.view(1, -1).repeat(I0.shape[0], 1)
 
     def func(p):
@@ -93,12 +95,16 @@ def get_param(I0, I1, operation, executor, optimizer='Nelder-Mead', counter=None
 
 
 def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step,
-                err, dist_type, optimizer, replace=False, variant='default', eps=0.05, counter=None, trace=None):
+                err, dist_type, optimizer, replace=False, variant='default', eps=0.05, counter=None, trace=None,
+                mask=None, mask_op_idx=None):
     """utils/beam_search.py:196-264.
 
     variant='fixed_order'  -> utils/beam_search_fixed_order.py:225-293 (one operator per step)
     variant='eps_greedy'   -> utils/beam_search_eps_greedy.py:238-309 (keeps every candidate,
                               random beams with probability eps, never clears no_update_flag)
+    mask / mask_op_idx: the GIER driver's arguments (preprocess/gen_greedy_seqs_GIER.py:60-71; the reference's beam_search
+    does not accept them): every operator is tried once per mask that is global (index < 0) or belongs to it, the edit is
+    blended inside the mask (Operator.execute), the action gets the mask's position as a fourth field.
     Returns (actions, Is) with the reference's nesting.  `trace`: a list that receives one record per step (every
     candidate evaluated + the argsort input / output), in the format of oracle/make_planner_golden_full.py.
     """
@@ -115,20 +121,24 @@ def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, 
             for operation in step_ops:
                 if not replace and operation in [operation_names.index(v[0]) for v in sequences[j][0]]:
                     continue
-                param, _ = get_param(I, I_gt, operation, executor, optimizer, counter)
-                I_out = execute(I, operation, param, executor)
-                dist = get_dist(I_out, I_gt, dist_type).item()
-                step_cands.append({'parent': j, 'op': int(operation), 'param': [float(v) for v in param[0].tolist()],
-                                   'dist': float(dist)})
-                if variant == 'eps_greedy' or dist < min_dist:
-                    tmp_min_dists.append(dist)
-                    cand = [sequences[j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out.cpu())], dist]
-                    all_candidates.append(cand)
-                    I_tmp_list.append(I_out)
-                    if variant != 'eps_greedy':
-                        no_update_flag = False
-                    if dist < err:
-                        finish_flag = True
+                choices = [None] if mask is None else [k for k, oi in enumerate(mask_op_idx) if oi < 0 or oi == operation]
+                for k in choices:
+                    mk = None if k is None or mask_op_idx[k] < 0 else mask[k]
+                    param, _ = get_param(I, I_gt, operation, executor, optimizer, counter, mk)
+                    I_out = executor.execute(I, operation, mk, features=None, specified_param=param, has_noise=False)[0]
+                    dist = get_dist(I_out, I_gt, dist_type).item()
+                    step_cands.append({'parent': j, 'op': int(operation), 'param': [float(v) for v in param[0].tolist()],
+                                       'dist': float(dist), 'mask': k})
+                    if variant == 'eps_greedy' or dist < min_dist:
+                        tmp_min_dists.append(dist)
+                        act = (operation_names[operation], param[0].tolist(), dist) + (() if k is None else (k,)) + (I_out.cpu(),)
+                        cand = [sequences[j][0] + [act], dist]
+                        all_candidates.append(cand)
+                        I_tmp_list.append(I_out)
+                        if variant != 'eps_greedy':
+                            no_update_flag = False
+                        if dist < err:
+                            finish_flag = True
         min_dist = min(tmp_min_dists) if len(tmp_min_dists) > 0 else min_dist
         if len(all_candidates) < beam_size:
             all_candidates += sequences

@@ -62,6 +62,8 @@ def _declare(lib):
     lib.t2o_l1_sum.argtypes = [vp, vp, vp, ci, ctypes.c_int64, vp, ctypes.c_size_t, vp]
     lib.t2o_score_candidates.restype = ci
     lib.t2o_score_candidates.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, ci, vp, ctypes.c_size_t, vp]
+    lib.t2o_score_candidates_masked.restype = ci
+    lib.t2o_score_candidates_masked.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, vp, ctypes.c_size_t, vp]
     lib.t2o_ssim_workspace_bytes.restype = ctypes.c_size_t
     lib.t2o_ssim_workspace_bytes.argtypes = [ci] * 4
     lib.t2o_ssim_sum.restype = ci
@@ -82,7 +84,7 @@ def _declare(lib):
 EXPORTS = ['t2o_version', 't2o_status_string', 't2o_last_cuda_error', 't2o_num_params', 't2o_workspace_bytes',
            't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_rows_forward',
            't2o_rows_backward', 't2o_l1_sum',
-           't2o_score_candidates', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
+           't2o_score_candidates', 't2o_score_candidates_masked', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
            't2o_u8_to_f32', 't2o_f32_to_u8', 't2o_img2tensor', 't2o_tensor2img']
 
 

@@ -25,7 +25,8 @@ int l1_sum_launch(const float *pa, const float *pb, float *l1_sum, int B, long l
                   cudaStream_t stream);
 size_t score_workspace_bytes(int S, int C, int H, int W);
 int score_candidates(const float *states, int S, const float *targets, int T, const int *state_target,
-                     const int *cand_begin, const int *cand_op, const float *cand_param, int C, float *l1_sum,
+                     const int *cand_begin, const int *cand_op, const float *cand_param, const int *cand_mask,
+                     const float *masks, int n_masks, int mask_ch, int C, float *l1_sum,
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
 int nm_start(const t2o_nm_state *st, int P, const int *n_dims, const int *prob_op, const double *x0,
              float *cand_param, int *cand_op, cudaStream_t stream);
@@ -117,8 +118,16 @@ int t2o_l1_sum(const float *a, const float *b, float *l1_sum, int B, int64_t n_p
 int t2o_score_candidates(const float *states, int S, const float *targets, int T, const int32_t *state_target,
                          const int32_t *cand_begin, const int32_t *cand_op, const float *cand_param, int C, float *l1_sum,
                          int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
-    return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, C, l1_sum, H, W,
-                                 curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+    return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, nullptr, nullptr, 0, 0, C,
+                                 l1_sum, H, W, curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_score_candidates_masked(const float *states, int S, const float *targets, int T, const int32_t *state_target,
+                                const int32_t *cand_begin, const int32_t *cand_op, const float *cand_param,
+                                const int32_t *cand_mask, const float *masks, int n_masks, int mask_ch, int C, float *l1_sum,
+                                int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, cand_mask, masks, n_masks,
+                                 mask_ch, C, l1_sum, H, W, curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int t2o_nm_start(const t2o_nm_state *state, int P, const int32_t *n_dims, const int32_t *prob_op, const double *x0,

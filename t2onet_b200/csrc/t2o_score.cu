@@ -28,6 +28,9 @@ constexpr int SCORE_NW = SCORE_NT / 32;
 struct ScoreArgs {
     const float *states, *targets, *cand_param;
     const int *state_target, *cand_begin, *cand_op;
+    const float *masks;         // (n_masks, mask_ch, H, W) or null
+    const int *cand_mask;       // mask of candidate c, or -1 (masked launches only)
+    int mask_ch;
     float *l1_sum, *part;
     unsigned int *counters;
     int S, T, C, H, W, L;
@@ -63,10 +66,21 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, ui
 // (channel, pixel) order.  `src` points at the group's first pixel in the staged state tile (rows `spitch` floats apart,
 // channels `cs` floats apart, one halo row / HX halo floats around it), `tsrc` at the same pixel of the staged target
 // (channels `ct` floats apart).  Shared by both scorer kernels so that their sums agree to the bit.
-template <int VEC>
+// HM: the launch carries masks (Operator.execute's out * mask + img * (1 - mask), models/operators.py:129): `mptr` points at
+// the group's first pixel in the candidate's mask (global memory, channels `mcs` floats apart; 0 for a 1-channel mask),
+// or is null for a candidate without a mask (mask = 1: blend(y, x, 1) == y to the bit).
+template <int VEC, bool HM>
 __device__ __forceinline__ void score_group(float &sum, int op, const float *tab, int L, float p, const float *src, int spitch, int cs,
-                                            const float *tsrc, int ct) {
-    float x[3][VEC], t[3][VEC];
+                                            const float *tsrc, int ct, const float *mptr, size_t mcs) {
+    float x[3][VEC], t[3][VEC], m[3][VEC];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (HM && mptr) ld_vec<VEC>(mptr + c * mcs, m[c]);
+        else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) m[c][v] = 1.0f;
+        }
+    }
     if (op == OP_SHARPNESS) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -80,7 +94,7 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
             for (int v = 0; v < VEC; ++v) {
                 const float l = v > 0 ? ctr[v - 1] : lf;
                 const float r = v < VEC - 1 ? ctr[v + 1] : rt;
-                x[c][v] = sat01(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]));
+                x[c][v] = sat01(blend<HM>(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]), ctr[v], m[c][v]));
             }
         }
     } else if (op == OP_BLUR) {
@@ -97,7 +111,7 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
                 const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
                 const float e = v > 0 ? up[v - 1] : ul, f = v < VEC - 1 ? up[v + 1] : ur;
                 const float g = v > 0 ? dn[v - 1] : dl, h = v < VEC - 1 ? dn[v + 1] : dr;
-                x[c][v] = sat01(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]));
+                x[c][v] = sat01(blend<HM>(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]), ctr[v], m[c][v]));
             }
         }
     } else {
@@ -107,7 +121,7 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
 #define T2O_CASE(OPC)                                                                                         \
     case OPC:                                                                                                 \
         _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                       \
-            op_apply<false>(OPC, tab, L, x[0][v], x[1][v], x[2][v], 1.0f, 1.0f, 1.0f);                             \
+            op_apply<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);                       \
         break;
             T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
             T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
@@ -126,7 +140,7 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
 
 // VEC = 4: W % 4 == 0, state rows padded by 4 floats each side (keeps 128-bit LDS aligned)
 // VEC = 1: any W, 1 float each side
-template <int VEC, bool USE_TMA>
+template <int VEC, bool USE_TMA, bool HM = false>
 __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__ CUtensorMap tm_state,
                                                          const __grid_constant__ CUtensorMap tm_target,
                                                          const __grid_constant__ ScoreArgs a) {
@@ -207,14 +221,21 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
     const int TWg = TW / VEC;
     const int ngroups = TH * TWg;
     // one lane's share of a candidate's |op(state) - target| over the tile: groups first, first + stride, ...
-    auto tile_sum = [&](int op, const float *tab, int first, int stride) -> float {
+    const size_t mcs = HM && a.mask_ch == 3 ? plane : 0;
+    // the mask image of candidate ci, or null
+    auto cand_mask_img = [&](int ci) -> const float * {
+        if (!HM || !a.cand_mask) return nullptr;
+        const int mi = a.cand_mask[ci];
+        return mi >= 0 ? a.masks + (size_t)mi * a.mask_ch * plane : nullptr;
+    };
+    auto tile_sum = [&](int op, const float *tab, int first, int stride, const float *mimg) -> float {
         float sum = 0.0f;
         const float p = tab[0];
         for (int gi = first; gi < ngroups; gi += stride) {
             const int ly = gi / TWg, lx = (gi - ly * TWg) * VEC;
             if (y0 + ly >= H || x0 + lx >= W) continue;       // ragged edge (W % VEC == 0)
-            score_group<VEC>(sum, op, tab, a.L, p, sS + (ly + 1) * spitch + HX + lx, spitch, srows * spitch,
-                             sT + ly * TW + lx, TH * TW);
+            score_group<VEC, HM>(sum, op, tab, a.L, p, sS + (ly + 1) * spitch + HX + lx, spitch, srows * spitch,
+                                 sT + ly * TW + lx, TH * TW, mimg ? mimg + (size_t)(y0 + ly) * W + x0 + lx : nullptr, mcs);
         }
         return sum;
     };
@@ -228,7 +249,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
         for (int c = 0; c < ncand; ++c) {
             const int op = a.cand_op[cbeg + c];
             if (op == OP_SKIP) continue;
-            const float sum = warp_sum(tile_sum(op, wtab[c], warp * 32 + lane, SCORE_NT));
+            const float sum = warp_sum(tile_sum(op, wtab[c], warp * 32 + lane, SCORE_NT, cand_mask_img(cbeg + c)));
             if (lane == 0) wsum[c][warp] = sum;
         }
         __syncthreads();
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
             __syncwarp();
             if (lane == 0) build_table<false>(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
             __syncwarp();
-            const float sum = warp_sum(tile_sum(op, tab, lane, 32));
+            const float sum = warp_sum(tile_sum(op, tab, lane, 32, cand_mask_img(ci)));
             if (lane == 0) a.part[(size_t)ci * a.ntiles + tile] = sum;
         }
     }
@@ -303,9 +324,12 @@ size_t score_workspace_bytes(int S, int C, int H, int W) {
 }
 
 int score_candidates(const float *states, int S, const float *targets, int T, const int *state_target,
-                     const int *cand_begin, const int *cand_op, const float *cand_param, int C, float *l1_sum,
+                     const int *cand_begin, const int *cand_op, const float *cand_param, const int *cand_mask,
+                     const float *masks, int n_masks, int mask_ch, int C, float *l1_sum,
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream) {
     if (!states || !targets || !cand_begin || !cand_op || !cand_param || !l1_sum) return T2O_ERR_INVALID_ARG;
+    const bool hm = masks != nullptr;
+    if (hm && (!cand_mask || n_masks < 1 || (mask_ch != 1 && mask_ch != 3))) return T2O_ERR_INVALID_ARG;
     if (S < 1 || T < 1 || C < 0 || H < 1 || W < 1) return T2O_ERR_INVALID_ARG;
     if ((size_t)S * sizeof(unsigned int) > COUNTER_REGION) return T2O_ERR_UNSUPPORTED;
     if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
@@ -314,11 +338,12 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
     ScoreArgs a;
     a.states = states; a.targets = targets; a.cand_param = cand_param; a.state_target = state_target;
     a.cand_begin = cand_begin; a.cand_op = cand_op; a.l1_sum = l1_sum;
+    a.masks = masks; a.cand_mask = hm ? cand_mask : nullptr; a.mask_ch = hm ? mask_ch : 0;
     a.counters = (unsigned int *)ws;
     a.part = (float *)((char *)ws + COUNTER_REGION);
     a.S = S; a.T = T; a.C = C; a.H = H; a.W = W; a.L = L;
     const bool aligned = ((uintptr_t)states % 16 == 0) && ((uintptr_t)targets % 16 == 0);
-    const int vec = (W % 4 == 0) ? 4 : 1;
+    const int vec = (W % 4 == 0 && (!hm || (uintptr_t)masks % 16 == 0)) ? 4 : 1;
     // tile: up to 128 px wide, 32 rows (state 3x34x136 + target 3x32x128 floats = 105 KB -> 2 CTAs / SM)
     int TW = W < 128 ? (W + vec - 1) / vec * vec : 128;
     int TH = H < 32 ? H : 32;          // (16- and 8-row tiles measured slower in every regime: the cost is per CTA)
@@ -344,17 +369,20 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
     if (grid > 0x7fffffffLL) return T2O_ERR_UNSUPPORTED;
     CUtensorMap tms, tmt;
     memset(&tms, 0, sizeof(tms)); memset(&tmt, 0, sizeof(tmt));
+#define T2O_LAUNCH_SCORE(V, TMA, M)                                                                                              \
+    do {                                                                                                                         \
+        T2O_CUDA_OK(cudaFuncSetAttribute(score_kernel<V, TMA, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        score_kernel<V, TMA, M><<<(unsigned)grid, SCORE_NT, smem, stream>>>(tms, tmt, a);                                         \
+    } while (0)
     if (use_tma) {
         if (!make_map(&tms, states, S, H, W, TW + 8, TH + 2) || !make_map(&tmt, targets, T, H, W, TW, TH)) return T2O_ERR_NO_DEVICE;
-        T2O_CUDA_OK(cudaFuncSetAttribute(score_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_kernel<4, true><<<(unsigned)grid, SCORE_NT, smem, stream>>>(tms, tmt, a);
+        if (hm) T2O_LAUNCH_SCORE(4, true, true); else T2O_LAUNCH_SCORE(4, true, false);
     } else if (vec == 4) {
-        T2O_CUDA_OK(cudaFuncSetAttribute(score_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_kernel<4, false><<<(unsigned)grid, SCORE_NT, smem, stream>>>(tms, tmt, a);
+        if (hm) T2O_LAUNCH_SCORE(4, false, true); else T2O_LAUNCH_SCORE(4, false, false);
     } else {
-        T2O_CUDA_OK(cudaFuncSetAttribute(score_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_kernel<1, false><<<(unsigned)grid, SCORE_NT, smem, stream>>>(tms, tmt, a);
+        if (hm) T2O_LAUNCH_SCORE(1, false, true); else T2O_LAUNCH_SCORE(1, false, false);
     }
+#undef T2O_LAUNCH_SCORE
     T2O_CUDA_OK(cudaGetLastError());
     return T2O_OK;
 }

@@ -434,7 +434,7 @@ def l1_sum(a, b):
 class CandidateBatch:
     """Device-resident candidate list for score_candidates (build once, score many times)."""
 
-    def __init__(self, S, cand_state, cand_op, cand_param, device, state_target=None):
+    def __init__(self, S, cand_state, cand_op, cand_param, device, state_target=None, masks=None, cand_mask=None):
         cs = torch.as_tensor(cand_state, dtype=torch.int64).cpu()
         self.C = int(cs.numel())
         self.S = S
@@ -453,6 +453,16 @@ class CandidateBatch:
         self.prm = prm.to(device).contiguous()
         self.state_target = None if state_target is None else \
             torch.as_tensor(state_target, dtype=torch.int32).to(device).contiguous()
+        # masks (n_masks, 1|3, H, W) + the mask index of every candidate (-1: edit everywhere), the GIER planner's inputs
+        self.masks, self.cand_mask = None, None
+        if masks is not None:
+            if masks.dim() != 4 or masks.shape[1] not in (1, 3) or not masks.is_cuda:
+                raise _lib.T2OError('masks must be a CUDA tensor (n_masks, 1|3, H, W)')
+            cm = torch.as_tensor(cand_mask, dtype=torch.int64).cpu()
+            if cm.numel() != self.C or (self.C and (int(cm.max()) >= masks.shape[0])):
+                raise _lib.T2OError('cand_mask must hold one mask index (< n_masks, or -1) per candidate')
+            self.masks = masks.detach().float().contiguous()
+            self.cand_mask = cm.to(torch.int32).to(device).contiguous()
 
 
 def score_prepared(states, targets, cb, curve_steps=CURVE_STEPS):
@@ -464,21 +474,31 @@ def score_prepared(states, targets, cb, curve_steps=CURVE_STEPS):
         return out
     lib = _lib.lib()
     ws = _lib.workspace(dev, lib.t2o_score_workspace_bytes(S, cb.C, H, W))
-    st = lib.t2o_score_candidates(_lib.ptr(states), S, _lib.ptr(targets), targets.shape[0], _lib.ptr(cb.state_target),
-                                  _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm), cb.C, _lib.ptr(out), H, W,
-                                  curve_steps, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    if cb.masks is not None:
+        if tuple(cb.masks.shape[2:]) != (H, W):
+            raise _lib.T2OError('masks must have the states\' height and width')
+        st = lib.t2o_score_candidates_masked(_lib.ptr(states), S, _lib.ptr(targets), targets.shape[0], _lib.ptr(cb.state_target),
+                                             _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm), _lib.ptr(cb.cand_mask),
+                                             _lib.ptr(cb.masks), cb.masks.shape[0], cb.masks.shape[1], cb.C, _lib.ptr(out), H, W,
+                                             curve_steps, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    else:
+        st = lib.t2o_score_candidates(_lib.ptr(states), S, _lib.ptr(targets), targets.shape[0], _lib.ptr(cb.state_target),
+                                      _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm), cb.C, _lib.ptr(out), H, W,
+                                      curve_steps, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(st)
     return out
 
 
-def score_candidates(states, targets, cand_state, cand_op, cand_param, state_target=None, curve_steps=CURVE_STEPS):
+def score_candidates(states, targets, cand_state, cand_op, cand_param, state_target=None, curve_steps=CURVE_STEPS,
+                     masks=None, cand_mask=None):
     """Score C single-operator candidates: l1_sum[c] = sum |clamp(op_c(states[cand_state[c]]; param_c)) - target|.
 
     states (S,3,H,W), targets (T,3,H,W) on the GPU; cand_state / cand_op: int sequences or tensors (C,),
     cand_state ascending; cand_param (C, <=24) float.  state_target (S,) picks each state's target
-    (default s % T).  Returns a (C,) float32 CUDA tensor in candidate order."""
+    (default s % T).  masks (n_masks, 1|3, H, W) + cand_mask (C,): candidate c edits inside mask cand_mask[c] (-1: everywhere).
+    Returns a (C,) float32 CUDA tensor in candidate order."""
     states, targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
-    cb = CandidateBatch(states.shape[0], cand_state, cand_op, cand_param, states.device, state_target)
+    cb = CandidateBatch(states.shape[0], cand_state, cand_op, cand_param, states.device, state_target, masks, cand_mask)
     return score_prepared(states, targets, cb, curve_steps)
 
 
@@ -493,7 +513,8 @@ class DeviceNelderMead:
 
     ROWS = _lib.MAX_OP_PARAMS + 1
 
-    def __init__(self, states, targets, prob_state, prob_op, x0, state_target=None, curve_steps=CURVE_STEPS, numel=None):
+    def __init__(self, states, targets, prob_state, prob_op, x0, state_target=None, curve_steps=CURVE_STEPS, numel=None,
+                 masks=None, prob_mask=None):
         self.states, self.targets = _prep_img(states, 'states'), _prep_img(targets, 'targets')
         dev = self.states.device
         self.dev, self.L = dev, curve_steps
@@ -508,7 +529,7 @@ class DeviceNelderMead:
         x0m = torch.zeros(P, _lib.MAX_OP_PARAMS, dtype=torch.float64)
         for i, (v, n) in enumerate(zip(x0, n_dims)):
             x0m[i, :n] = torch.as_tensor(v, dtype=torch.float64).flatten()[:n]
-        self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target)
+        self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target, masks, prob_mask)
         self.n_dims = torch.tensor(n_dims, dtype=torch.int32, device=dev)
         self.prob_op = torch.as_tensor(prob_op, dtype=torch.int32).to(dev)
         self.x0 = x0m.to(dev)
@@ -533,10 +554,17 @@ class DeviceNelderMead:
     def _round(self):
         lib, cb = _lib.lib(), self.cb
         sp = _lib.stream_ptr(self.dev)
-        _lib.check(lib.t2o_score_candidates(_lib.ptr(self.states), self.S, _lib.ptr(self.targets), self.targets.shape[0],
-                                            _lib.ptr(cb.state_target), _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm),
-                                            self.P, _lib.ptr(self.l1), self.H, self.W, self.L, _lib.ptr(self.ws),
-                                            self.ws.numel(), sp))
+        if cb.masks is not None:
+            _lib.check(lib.t2o_score_candidates_masked(_lib.ptr(self.states), self.S, _lib.ptr(self.targets), self.targets.shape[0],
+                                                       _lib.ptr(cb.state_target), _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm),
+                                                       _lib.ptr(cb.cand_mask), _lib.ptr(cb.masks), cb.masks.shape[0], cb.masks.shape[1],
+                                                       self.P, _lib.ptr(self.l1), self.H, self.W, self.L, _lib.ptr(self.ws),
+                                                       self.ws.numel(), sp))
+        else:
+            _lib.check(lib.t2o_score_candidates(_lib.ptr(self.states), self.S, _lib.ptr(self.targets), self.targets.shape[0],
+                                                _lib.ptr(cb.state_target), _lib.ptr(cb.begin), _lib.ptr(cb.ops), _lib.ptr(cb.prm),
+                                                self.P, _lib.ptr(self.l1), self.H, self.W, self.L, _lib.ptr(self.ws),
+                                                self.ws.numel(), sp))
         _lib.check(lib.t2o_nm_advance(ctypes.byref(self.state), self.P, _lib.ptr(self.l1), self.numel, _lib.ptr(cb.prm),
                                       _lib.ptr(cb.ops), sp))
 

@@ -117,12 +117,14 @@ class _Fit:
         self.success = status == 0
 
 
-def fit_params_nelder_mead(states, targets, problems, executor, state_target=None, counter=None, numel=None):
+def fit_params_nelder_mead(states, targets, problems, executor, state_target=None, counter=None, numel=None,
+                           masks=None, prob_mask=None):
     """Fit many (state index, operator) problems at once on the device (TF.DeviceNelderMead).
+    masks (n_masks, 1|3, H, W) + prob_mask (one mask index or -1 per problem): the fit edits inside that mask.
 
     states (S,3,H,W) / targets (T,3,H,W) CUDA tensors; problems: list of (state_idx, operation).
     Returns a list of results (x float64 (n,), fun, nit, nfev, status, success) in problem order."""
-    if os.environ.get('T2O_HOST_NM') == '1':
+    if os.environ.get('T2O_HOST_NM') == '1' and masks is None:
         return fit_params_nelder_mead_host(states, targets, problems, executor, state_target, counter)
     if not problems:
         return []
@@ -130,7 +132,8 @@ def fit_params_nelder_mead(states, targets, problems, executor, state_target=Non
     order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))       # the scorer wants candidates sorted by state
     nm = TF.DeviceNelderMead(states, targets, [problems[i][0] for i in order], [problems[i][1] for i in order],
                              [_param0(problems[i][1], executor) for i in order], state_target=state_target,
-                             curve_steps=L, numel=numel)
+                             curve_steps=L, numel=numel, masks=masks,
+                             prob_mask=None if masks is None else [prob_mask[i] for i in order])
     r = nm.run()
     assert bool(r['done'].all()), 'Nelder-Mead fits did not finish'
     if counter is not None:
@@ -215,9 +218,9 @@ def get_param(I0, I1, txt, operation, executor, discriminator, dist_type, optimi
     return get_param_gd(I0, I1, txt, None, param0, executor, discriminator, operation, dist_type, optimizer)
 
 
-def _score_outputs(I_list, ops, params, I_gt_list, executor):
+def _score_outputs(I_list, ops, params, I_gt_list, executor, mask_list=None):
     """I_out and dist for every fitted candidate of a step (utils/beam_search.py:230,237): one per-row launch
-    (every row its own state, operator, parameters and target), one device->host read of the distances."""
+    (every row its own state, operator, parameters, target and -- GIER -- mask), one device->host read of the distances."""
     if not I_list:
         return [], []
     L = getattr(executor.opt, 'curve_steps', 8)
@@ -237,7 +240,13 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor):
         prm = torch.from_numpy(prm)
         row_ops = [[int(o)] for o in ops[c0:c0 + CH]]
         ops_dev, ops_host = TF._prep_row_ops(row_ops, len(Is), dev)
-        out, l1 = TF._rows_forward_raw(ops_dev, ops_host, img, None, 0, prm.to(dev), tgt, True, True, L)
+        mask, mask_ch = None, 0
+        if mask_list is not None and any(mk is not None for mk in mask_list[c0:c0 + CH]):
+            mask_ch = max(mk.shape[1] for mk in mask_list[c0:c0 + CH] if mk is not None)
+            ones = torch.ones(1, mask_ch, img.shape[2], img.shape[3], device=dev)
+            mask = torch.cat([ones if mk is None else mk.to(dev).float().expand(1, mask_ch, -1, -1)
+                              for mk in mask_list[c0:c0 + CH]], 0).contiguous()
+        out, l1 = TF._rows_forward_raw(ops_dev, ops_host, img, mask, mask_ch, prm.to(dev), tgt, True, True, L)
         vals += (l1 / numel).tolist()
         outs += [out[r:r + 1] for r in range(len(Is))]
     return outs, vals
@@ -294,7 +303,7 @@ def _step_minima_sharded(dists, problems, live, device_, group):
 
 def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type='L1',
                       optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None,
-                      trace=None, shard_fits=False, group=None):
+                      trace=None, shard_fits=False, group=None, masks=None, mask_op_idx=None):
     """`beam_search` (utils/beam_search.py:196-264) for M image pairs at once: I_0, I_gt (M,3,H,W).
 
     Every pair runs the reference's beam search unchanged; what is shared is the work: all (pair, beam state,
@@ -303,6 +312,10 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     `trace`: an empty list that receives, per pair, {'steps': [{'candidates': [{'parent', 'op', 'param', 'dist', 'nfev'}],
     'sort_dists', 'sort_order'}]} -- every candidate evaluated and the array / order of the step's argsort (the
     transcript format of oracle/make_planner_golden_full.py).
+    `masks` / `mask_op_idx` (GIER, preprocess/gen_greedy_seqs_GIER.py:60-62): per pair a list of (1, 1|3, H, W) masks and the
+    operator index each belongs to (< 0: the global all-ones mask, offered to every operator); operator `op` is then
+    tried once per mask that is global or belongs to it, edits only inside it (Operator.execute's blend), and the
+    chosen mask's position in the list is recorded as a fourth field of the action.
     `shard_fits` (inside an initialised process group, every rank calling with the SAME pairs): candidate-sharded mode --
     the fits of a step are split over the ranks, the table of fitted parameters is all-gathered and the step's best
     candidate per pair is agreed with one all_reduce(MIN) (NCCL on GPUs); the result is the same for every rank count."""
@@ -317,6 +330,24 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     numel = float(I_gt[0:1].numel())
     st = [{'min_dist': float('inf'), 'sequences': [[[], float('inf')]], 'I_buff': [I_0[m:m + 1]], 'alive': True}
           for m in range(M)]
+    # GIER masks: one device tensor of all local masks; the global (all-ones) mask is "no mask"
+    mask_bank, mask_gidx = [], None
+    if masks is not None:
+        assert len(masks) == M and len(mask_op_idx) == M, 'one list of masks (and of operator indices) per pair'
+        assert not shard_fits, 'candidate sharding does not carry masks'
+        mask_gidx = []
+        for m in range(M):
+            assert len(masks[m]) == len(mask_op_idx[m])
+            idx = []
+            for mk, oi in zip(masks[m], mask_op_idx[m]):
+                if oi < 0:
+                    idx.append(-1)
+                else:
+                    idx.append(len(mask_bank))
+                    mask_bank.append(mk.to(I_0.device).float())
+            mask_gidx.append(idx)
+        chans = max([mk.shape[1] for mk in mask_bank] + [1])
+        masks_dev = torch.cat([mk.expand(1, chans, -1, -1) for mk in mask_bank], 0).contiguous() if mask_bank else None
     if trace is not None:
         trace.extend({'steps': []} for _ in range(M))
     for i in range(max_step):
@@ -335,36 +366,49 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                 for operation in step_ops:
                     if not replace and operation in [operation_names.index(v[0]) for v in seqs[j][0]]:
                         continue
-                    problems.append((s_idx, operation, m, j))
+                    if masks is None:
+                        problems.append((s_idx, operation, m, j, None))
+                    else:
+                        for k, oi in enumerate(mask_op_idx[m]):
+                            if oi < 0 or oi == operation:
+                                problems.append((s_idx, operation, m, j, k))
         # -- fit all of them (utils/beam_search.py:229)
         if shard_fits and problems:
             params, nfevs = _fit_sharded(torch.cat(states, 0).contiguous(), I_gt, problems, executor, state_pair, counter,
                                          numel, group)
         elif optimizer == 'Nelder-Mead' and problems:
-            fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _ in problems],
-                                          executor, state_target=state_pair, counter=counter, numel=numel)
+            use_masks = masks is not None and masks_dev is not None
+            fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _, _ in problems],
+                                          executor, state_target=state_pair, counter=counter, numel=numel,
+                                          masks=masks_dev if use_masks else None,
+                                          prob_mask=[mask_gidx[m][k] for _, _, m, _, k in problems] if use_masks else None)
             params = [np.asarray(r.x, dtype=np.float64)[None, :] for r in fits]     # (1, n) float64, as the reference's tensors
             nfevs = [r.nfev for r in fits]
         else:
+            assert masks is None, 'masks are carried by the Nelder-Mead fits'
             params = [get_param(states[s], I_gt[m:m + 1], txt, op, executor, None, dist_type, optimizer)[0]
-                      for s, op, m, _ in problems]
+                      for s, op, m, _, _ in problems]
             nfevs = [0] * len(problems)
         # -- apply + score (utils/beam_search.py:230-237)
-        outs, dists = _score_outputs([states[s] for s, _, _, _ in problems], [op for _, op, _, _ in problems], params,
-                                     [I_gt[m:m + 1] for _, _, m, _ in problems], executor)
+        mask_list = None
+        if masks is not None:
+            mask_list = [None if mask_gidx[m][k] < 0 else masks_dev[mask_gidx[m][k]:mask_gidx[m][k] + 1] for _, _, m, _, k in problems]
+        outs, dists = _score_outputs([states[s] for s, _, _, _, _ in problems], [op for _, op, _, _, _ in problems], params,
+                                     [I_gt[m:m + 1] for _, _, m, _, _ in problems], executor, mask_list)
         # -- the reference's bookkeeping, pair by pair (utils/beam_search.py:239-259)
         minima = _step_minima_sharded(dists, problems, live, I_0.device, group) if shard_fits and problems else None
         by_pair = {m: [] for m in live}
-        for k, (s, op, m, j) in enumerate(problems):
-            by_pair[m].append((j, op, params[k], outs[k], dists[k], nfevs[k]))
+        for k, (s, op, m, j, mk) in enumerate(problems):
+            by_pair[m].append((j, op, params[k], outs[k], dists[k], nfevs[k], mk))
         for m in live:
             S = st[m]
             all_candidates, I_tmp_list, tmp_min_dists = [], [], []
             no_update_flag, finish_flag = True, False
-            for j, operation, param, I_out, dist, _ in by_pair[m]:
+            for j, operation, param, I_out, dist, _, mk in by_pair[m]:
                 if _variant == 'eps_greedy' or dist < S['min_dist']:
                     tmp_min_dists.append(dist)
-                    candidate = [S['sequences'][j][0] + [(operation_names[operation], param[0].tolist(), dist, I_out)], dist]
+                    act = (operation_names[operation], param[0].tolist(), dist) + (() if mk is None else (mk,)) + (I_out,)
+                    candidate = [S['sequences'][j][0] + [act], dist]
                     all_candidates.append(candidate)
                     I_tmp_list.append(I_out)
                     if _variant != 'eps_greedy':
@@ -392,7 +436,7 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
             if trace is not None:
                 trace[m]['steps'].append({
                     'candidates': [{'parent': j, 'op': int(op), 'param': [float(v) for v in np.asarray(p).reshape(-1)],
-                                    'dist': float(d), 'nfev': int(nf)} for j, op, p, _, d, nf in by_pair[m]],
+                                    'dist': float(d), 'nfev': int(nf), 'mask': mk} for j, op, p, _, d, nf, mk in by_pair[m]],
                     'sort_dists': [float(v) for v in dists_arr], 'sort_order': [int(v) for v in order]})
             # the kept images are rows of this step's output tensor: copy them out (once) so that it can be freed
             clones = {}
@@ -426,6 +470,17 @@ def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, 
     actions: list(beam) of list(step) of (op_name, param list, dist); Is: same nesting of CPU images."""
     return beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type,
                              optimizer, replace, _variant, _eps, counter, txt, shard_fits=shard_fits, group=group)[0]
+
+
+def beam_search_gier(I_0, I_gt, txt, mask, mask_op_idx, executor, beam_size, operations, operation_names, max_step, err, dist_type,
+                     optimizer, replace=False):
+    """The call the GIER planner driver makes (preprocess/gen_greedy_seqs_GIER.py:71):
+    beam_search(input, target, req_idx, mask, mask_op_idx, executor, beam_size, operations, ...), with `mask` the list
+    [global all-ones mask] + local masks and `mask_op_idx` = [-1] + the operator each local mask belongs to.  The
+    reference's own beam_search does not take these arguments (the driver does not run as committed); here every operator
+    is tried once per mask that is global or belongs to it.  Actions: (op_name, param list, dist, position in `mask`)."""
+    return beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type, optimizer,
+                             replace, txt=txt, masks=[list(mask)], mask_op_idx=[list(mask_op_idx)])[0]
 
 
 def beam_search_fixed_order(I_0, I_gt, txt, executor, beam_size, operations, operation_names, max_step, err, dist_type,
