@@ -428,6 +428,20 @@ def run_ours(args, wl):
             planner_line = {'error': err or 'a rank failed'}
         else:
             planner_line = planner_e2e_line(tmax[0].item(), int(tsum[1].item()), tsum[2].item() / world, n_gpus=world)
+    gier_line = None
+    if world > 1 and not args.no_extras:
+        barrier()
+        err = None
+        try:
+            sec, cand, steps = planner_gier_run(dev, 5010 + 17 * rank)
+        except Exception as exc:
+            sec, cand, steps, err = 0.0, 0, 0.0, repr(exc)
+        t = torch.tensor([sec, float(cand), steps, 0.0 if err is None else 1.0], device=dev, dtype=torch.float64)
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        gier_line = {'error': err or 'a rank failed'} if tsum[3].item() > 0 else \
+            planner_gier_line(tmax[0].item(), int(tsum[1].item()), tsum[2].item() / world, n_gpus=world)
     ddp_line = None
     if world > 1 and not args.no_extras:
         try:
@@ -476,6 +490,8 @@ def run_ours(args, wl):
     if planner_line is not None:
         line['planner'] = {'metric': 'planner candidates/s', 'value': planner_line.get('candidates_per_s'), 'unit': 'candidates/s',
                            'e2e': planner_line}
+    if gier_line is not None:
+        line['planner_gier'] = gier_line
     if ddp_line is not None:
         line['ddp_actor'] = ddp_line
     print(json.dumps(line), flush=True)
@@ -491,6 +507,7 @@ def planner_block(ex):
     blk['value'] = e2e.get('candidates_per_s')
     blk['e2e'] = e2e
     blk['scoring_sweep'] = sweep
+    blk['gier'] = ex.get('planner_gier', {})
     try:
         cpu = planner_cpu_baseline()
         if e2e.get('candidates') and e2e.get('pairs_per_s') and cpu.get('value'):
@@ -686,6 +703,44 @@ def planner_e2e_run(dev, seed, reps=3):
         if rep > 0 and (best is None or dt < best[0]):
             best = (dt, cnt[0])
     return best[0], best[1], sum(len(r[0][0]) for r in res) / PLANNER_M
+
+
+GIER_M = 16
+
+
+def planner_gier_run(dev, seed, reps=2):
+    """BASELINE config 5's planner shape: GIER-shaped inputs (3x256x256 pairs, each with the global mask and two local masks that
+    belong to brightness and saturation, preprocess/gen_greedy_seqs_GIER.py:36-62), beam 3 and err 1e-3 as that driver sets them,
+    the six global operators, Nelder-Mead; 16 pairs in lock-step.  -> (seconds, candidates, mean steps)"""
+    import t2onet_b200 as T
+    from t2onet_b200 import planner
+    names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
+    exe = T.Executor(T.default_options()).to(dev)
+    img, tgt, _ = make_batch(GIER_M, 256, 256, seed, dev)
+    masks, idx = [], []
+    for m in range(GIER_M):
+        m1 = torch.zeros(1, 1, 256, 256, device=dev); m1[..., 32:128 + 8 * (m % 4), 32:160] = 1.0
+        m2 = torch.zeros(1, 1, 256, 256, device=dev); m2[..., 128:, 64 + 8 * (m % 3):] = 1.0
+        masks.append([torch.ones(1, 1, 256, 256, device=dev), m1, m2])
+        idx.append([-1, 0, 2])
+    best = None
+    for rep in range(reps + 1):
+        cnt = [0]
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = planner.beam_search_batch(img, tgt, exe, 3, CHAIN, names, 6, 1e-3, counter=cnt, masks=masks, mask_op_idx=idx)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        if rep > 0 and (best is None or dt < best[0]):
+            best = (dt, cnt[0])
+    return best[0], best[1], sum(len(r[0][0]) for r in res) / GIER_M
+
+
+def planner_gier_line(seconds, candidates, mean_steps, n_gpus):
+    return {'workload': '%d GIER-shaped pairs of 3x256x256 per GPU (global mask + 2 local masks), beam 3, ops [0,1,2,3,5,6], max_step 6, '
+                        'err 1e-3, Nelder-Mead' % GIER_M, 'n_gpus': n_gpus, 'seconds': seconds, 'pairs_per_s': GIER_M * n_gpus / seconds,
+            'candidates': candidates, 'candidates_per_s': candidates / seconds, 'mean_steps': mean_steps,
+            'how': 'wall clock around beam_search_batch with masks, best of 2; N > 1: pairs sharded by image, slowest rank\'s time'}
 
 
 def planner_e2e_line(seconds, candidates, mean_steps, n_gpus):
@@ -905,6 +960,10 @@ def extras(TF, dev, wl):
         ex['planner_e2e'] = planner_e2e_line(*planner_e2e_run(dev, 3010), n_gpus=1)
     except Exception as exc:
         ex['planner_e2e'] = {'error': repr(exc)}
+    try:
+        ex['planner_gier'] = planner_gier_line(*planner_gier_run(dev, 5010), n_gpus=1)
+    except Exception as exc:
+        ex['planner_gier'] = {'error': repr(exc)}
     return ex
 
 
