@@ -120,6 +120,12 @@ def int_array(values):
 
 
 def stream_ptr(device):
+    """The stream handle every C entry point takes.  The kernels launch on the process's CURRENT device, so it is made the
+    tensors' device first (a no-op under the one-process-per-GPU convention; without it a tensor on cuda:1 in a process whose
+    current device is cuda:0 would fail with an invalid resource handle)."""
+    device = torch.device(device)
+    if device.index is not None and torch.cuda.current_device() != device.index:
+        torch.cuda.set_device(device)
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

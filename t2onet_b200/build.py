@@ -25,12 +25,28 @@ def nvcc_path():
     return p if os.path.exists(p) else None
 
 
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a copy of the tree)."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for d in sorted(os.path.join(CSRC, s) for s in SOURCES + HEADERS):
+        if os.path.exists(d):
+            with open(d, 'rb') as f:
+                h.update(os.path.basename(d).encode() + b'\0' + f.read())
+    return h.hexdigest()
+
+
 def is_stale():
+    """The library is missing, or was built from other sources than the ones in the tree."""
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    try:
+        with open(LIB + '.srchash') as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        t = os.path.getmtime(LIB)             # a library built before the hash file existed: fall back to mtimes
+        deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+        return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
 def build(force=False, verbose=True):
@@ -40,6 +56,19 @@ def build(force=False, verbose=True):
     if nvcc is None:
         raise RuntimeError('nvcc not found: cannot build %s' % LIB)
     os.makedirs(LIBDIR, exist_ok=True)
+    # one builder at a time (torchrun starts every rank at once): the others wait for the lock and find the result
+    import fcntl
+    with open(os.path.join(LIBDIR, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     objdir = os.path.join(LIBDIR, 'obj')
     os.makedirs(objdir, exist_ok=True)
 
@@ -59,6 +88,8 @@ def build(force=False, verbose=True):
         print('[t2onet_b200.build]', ' '.join(cmd), flush=True)
     subprocess.run(cmd, check=True)
     os.replace(tmp, LIB)
+    with open(LIB + '.srchash', 'w') as f:
+        f.write(source_hash())
     return LIB
 
 
