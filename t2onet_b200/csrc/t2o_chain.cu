@@ -112,6 +112,8 @@ static int launch_fwd_rows(FwdRowsArgs &a, int B, int H, int W, cudaStream_t str
             unsigned int packed = 0u;
             for (int k = 0; k < a.ch.n; ++k) packed |= (unsigned)(a.ch.op[k] + 1) << (4 * k);
             if (packed == SP_C6) return launch_fwd_rows_sp<VEC, HM, ROWS, SP_C6>(a, B, H, W, stream);
+            if (packed == SP_S1) return launch_fwd_rows_sp<VEC, HM, ROWS, SP_S1>(a, B, H, W, stream);
+            if (packed == SP_B1) return launch_fwd_rows_sp<VEC, HM, ROWS, SP_B1>(a, B, H, W, stream);
         }
     }
     return launch_fwd_rows_sp<VEC, HM, ROWS, 0u>(a, B, H, W, stream);

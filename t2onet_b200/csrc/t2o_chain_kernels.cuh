@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
     if (col_ok && rA >= 0 && rA < H && rA <= yb) prefetch_px(img_b, plane, (size_t)rA * W + coff);
     __syncthreads();
     const float p = tabs[sp][0];
-    const bool blur = SP ? false : ch.op[sp] == OP_BLUR;        // which stencil (the specialised chains hold a sharpness)
+    const bool blur = SP ? sp_blur(SP) : ch.op[sp] == OP_BLUR;  // which stencil
 #pragma unroll 1
     for (int s = 0; s < a.g.steps; ++s) {
         const int rB = rA - 1;

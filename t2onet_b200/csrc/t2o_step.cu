@@ -138,6 +138,8 @@ static int launch_step(StepArgs &a, cudaStream_t stream) {
         if (use_specialized()) {
             if (a.ch.ops_packed == SP_C6) return launch_step_sp<VEC, HM, NTH, SP_C6>(a, stream);
             if (a.ch.ops_packed == SP_P5) return launch_step_sp<VEC, HM, NTH, SP_P5>(a, stream);
+            if (a.ch.ops_packed == SP_S1) return launch_step_sp<VEC, HM, NTH, SP_S1, 4>(a, stream);      // light kernels: 4 CTAs per SM
+            if (a.ch.ops_packed == SP_B1) return launch_step_sp<VEC, HM, NTH, SP_B1, 3>(a, stream);
         }
     }
     return launch_step_sp<VEC, HM, NTH, 0u>(a, stream);

@@ -134,7 +134,8 @@ __host__ __device__ constexpr unsigned int pack_ops(int o0 = -1, int o1 = -1, in
            (unsigned)(o4 + 1) << 16 | (unsigned)(o5 + 1) << 20 | (unsigned)(o6 + 1) << 24 | (unsigned)(o7 + 1) << 28;
 }
 __host__ __device__ constexpr int sp_count(unsigned int sp) { int n = 0; for (int k = 0; k < MAX_CHAIN; ++k) if ((sp >> (4 * k)) & 15u) n = k + 1; return n; }
-__host__ __device__ constexpr int sp_sharp(unsigned int sp) { for (int k = 0; k < MAX_CHAIN; ++k) if (packed_op(sp, k) == OP_SHARPNESS) return k; return -1; }   // (no blur chain is specialised)
+__host__ __device__ constexpr int sp_sharp(unsigned int sp) { for (int k = 0; k < MAX_CHAIN; ++k) if (packed_op(sp, k) == OP_SHARPNESS || packed_op(sp, k) == OP_BLUR) return k; return -1; }
+__host__ __device__ constexpr bool sp_blur(unsigned int sp) { return sp_sharp(sp) >= 0 && packed_op(sp, sp_sharp(sp)) == OP_BLUR; }
 __host__ __device__ constexpr int sp_clamped(unsigned int sp) {
     int c = 0;
     for (int k = 1; k < MAX_CHAIN; ++k) if (packed_op(sp, k - 1) >= 0 || ((c >> (k - 1)) & 1)) c |= 1 << k;
@@ -142,6 +143,8 @@ __host__ __device__ constexpr int sp_clamped(unsigned int sp) {
 }
 constexpr unsigned int SP_C6 = pack_ops(OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_TONE, OP_SHARPNESS);
 constexpr unsigned int SP_P5 = pack_ops(OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION, OP_COLOR, OP_TONE);
+constexpr unsigned int SP_S1 = pack_ops(OP_SHARPNESS);      // a single sharpness step: the launch behind Executor.execute(img, 6, ...)'s backward
+constexpr unsigned int SP_B1 = pack_ops(OP_BLUR);
 
 // ---------------------------------------------------------------- operator dispatch over one pixel group
 // `cl`: the operator's input is known to lie in [0, 1] (lets the curve operators skip their input clamp)
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(NTH, MINB) step_sharp_kernel(const __grid_cons
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
-    const bool blur = SP ? false : ch.op[sp] == OP_BLUR;           // which stencil (the specialised chains hold a sharpness)
+    const bool blur = SP ? sp_blur(SP) : ch.op[sp] == OP_BLUR;     // which stencil
     const bool need_c = gi_b != nullptr || sp > 0;
     const int clamped = SP ? SPC : ch.clamped;
     const unsigned int opsp = SP ? SP : ch.ops_packed;
