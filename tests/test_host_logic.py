@@ -256,6 +256,13 @@ def _dist_worker(rank, world, port, q):
         tied = torch.full((1, 5), 0.25)
         best, bid = D.best_candidate(tied, torch.arange(5).view(1, 5) + 5 * rank)
         assert bid.item() == 0 and best.item() == 0.25
+        # the candidate-sharded planner's per-step agreement (planner._step_minima_sharded): every rank contributes the
+        # candidates it fitted (problems rank, rank + R, ...), every rank ends with each live pair's minimum and its problem
+        from t2onet_b200 import planner as P
+        problems = [(0, 0, 3, 0, None), (0, 1, 3, 0, None), (1, 0, 5, 0, None), (1, 2, 5, 0, None), (2, 6, 5, 1, None)]
+        dists = [0.5, 0.25, 0.75, 0.125, 0.0625]
+        res = P._step_minima_sharded(dists, problems, [3, 5], torch.device('cpu'), None)
+        assert res == {3: (0.25, 1), 5: (0.0625, 4)}, res
         q.put((rank, 'ok'))
     except Exception as exc:            # pragma: no cover
         q.put((rank, repr(exc)))
