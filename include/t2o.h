@@ -213,6 +213,15 @@ int t2o_score_candidates_masked(const float *states, int S, const float *targets
                                 void *workspace, size_t workspace_bytes, t2o_stream_t stream);
 
 /*
+ * The beam selection of a planner step for many searches at once (utils/beam_search.py:252-256: np.argsort of the candidates'
+ * distances, the first beam_size kept): values[seg_begin[s] .. seg_begin[s+1]) are the distances of search s
+ * (n_seg + 1 ints); out_idx / out_val (n_seg, k) receive the k smallest in ascending order -- global indices into `values`,
+ * exact ties by the smaller index, NaN last; -1 / +inf where a segment holds fewer than k values.
+ */
+int t2o_topk_min(const float *values, const int32_t *seg_begin, int n_seg, int k,
+                 int32_t *out_idx, float *out_val, t2o_stream_t stream);
+
+/*
  * Device-resident Nelder-Mead: P independent fits argmin_param L1(op(state; param), target), one per (state, operator)
  * pair of a planner step -- scipy.optimize.minimize(func, param0, method='Nelder-Mead') as utils/beam_search.py:88
  * calls it (scipy defaults: xatol = fatol = 1e-4, maxiter = maxfev = 200 N, initial simplex step 5 % / 2.5e-4),

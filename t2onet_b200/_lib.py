@@ -74,6 +74,8 @@ def _declare(lib):
     for name in ('t2o_img2tensor', 't2o_tensor2img'):
         getattr(lib, name).restype = ci
         getattr(lib, name).argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.t2o_topk_min.restype = ci
+    lib.t2o_topk_min.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.t2o_nm_start.restype = ci
     lib.t2o_nm_start.argtypes = [ctypes.POINTER(NMState), ci, vp, vp, vp, vp, vp, vp]
     lib.t2o_nm_advance.restype = ci
@@ -84,7 +86,7 @@ def _declare(lib):
 EXPORTS = ['t2o_version', 't2o_status_string', 't2o_last_cuda_error', 't2o_num_params', 't2o_workspace_bytes',
            't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_rows_forward',
            't2o_rows_backward', 't2o_l1_sum',
-           't2o_score_candidates', 't2o_score_candidates_masked', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
+           't2o_score_candidates', 't2o_score_candidates_masked', 't2o_topk_min', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
            't2o_u8_to_f32', 't2o_f32_to_u8', 't2o_img2tensor', 't2o_tensor2img']
 
 

@@ -28,6 +28,7 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
                      const int *cand_begin, const int *cand_op, const float *cand_param, const int *cand_mask,
                      const float *masks, int n_masks, int mask_ch, int C, float *l1_sum,
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int topk_min(const float *values, const int *seg_begin, int n_seg, int k, int *out_idx, float *out_val, cudaStream_t stream);
 int nm_start(const t2o_nm_state *st, int P, const int *n_dims, const int *prob_op, const double *x0,
              float *cand_param, int *cand_op, cudaStream_t stream);
 int nm_advance(const t2o_nm_state *st, int P, const float *l1_sum, float numel, float *cand_param, int *cand_op,
@@ -128,6 +129,11 @@ int t2o_score_candidates_masked(const float *states, int S, const float *targets
                                 int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
     return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, cand_mask, masks, n_masks,
                                  mask_ch, C, l1_sum, H, W, curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_topk_min(const float *values, const int32_t *seg_begin, int n_seg, int k, int32_t *out_idx, float *out_val,
+                 t2o_stream_t stream) {
+    return t2o::topk_min(values, seg_begin, n_seg, k, out_idx, out_val, (cudaStream_t)stream);
 }
 
 int t2o_nm_start(const t2o_nm_state *state, int P, const int32_t *n_dims, const int32_t *prob_op, const double *x0,

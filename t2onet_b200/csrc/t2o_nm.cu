@@ -301,6 +301,51 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NMArgs 
     if (lane == 0) { w.ctl[CTL_FCALLS] = w.fcalls; w.ctl[CTL_ITERS] = w.iters; }
 }
 
+// ---------------------------------------------------------------- top-k of the candidates' scores
+// The beam selection of a planner step (utils/beam_search.py:252-256: np.argsort of the candidates' distances, the first
+// beam_size kept) for many searches at once: segment s of `values` holds the candidates of search s; the k smallest come
+// out in ascending order, exact ties by the smaller index (numpy's kind='stable'; the reference's default quicksort leaves
+// the order of ties unspecified), NaN last.  One warp per segment: pass j picks the smallest (value, index) key that is
+// greater than the key picked in pass j - 1, so nothing is marked or moved.
+__global__ void __launch_bounds__(128) topk_min_kernel(const float *__restrict__ values, const int *__restrict__ seg_begin, int n_seg, int k,
+                                                       int *__restrict__ out_idx, float *__restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_seg) return;
+    const int b = seg_begin[s], e = seg_begin[s + 1];
+    float last_v = -CUDART_INF_F;
+    int last_i = -1;
+    for (int j = 0; j < k; ++j) {
+        float best_v = CUDART_INF_F;
+        int best_i = 0x7fffffff;
+        for (int i = b + lane; i < e; i += 32) {
+            float v = values[i];
+            if (isnan(v)) v = CUDART_INF_F;
+            const bool after = v > last_v || (v == last_v && i > last_i);
+            if (after && (v < best_v || (v == best_v && i < best_i))) { best_v = v; best_i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov < best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        }
+        const bool found = best_i != 0x7fffffff;
+        if (lane == 0) {
+            out_idx[(size_t)s * k + j] = found ? best_i : -1;
+            out_val[(size_t)s * k + j] = found ? values[best_i] : CUDART_INF_F;
+        }
+        if (!found) { last_v = CUDART_INF_F; last_i = 0x7fffffff; } else { last_v = best_v; last_i = best_i; }
+    }
+}
+
+int topk_min(const float *values, const int *seg_begin, int n_seg, int k, int *out_idx, float *out_val, cudaStream_t stream) {
+    if (!values || !seg_begin || !out_idx || !out_val || n_seg < 1 || k < 1) return T2O_ERR_INVALID_ARG;
+    topk_min_kernel<<<(n_seg + 3) / 4, 128, 0, stream>>>(values, seg_begin, n_seg, k, out_idx, out_val);
+    T2O_CUDA_OK(cudaGetLastError());
+    return T2O_OK;
+}
+
 static int nm_check(const t2o_nm_state *st, int P) {
     if (!st || P < 1) return T2O_ERR_INVALID_ARG;
     if (!st->sim || !st->fsim || !st->vec || !st->fxr || !st->perm || !st->ctl || !st->xbest || !st->fbest) return T2O_ERR_INVALID_ARG;

@@ -502,6 +502,20 @@ def score_candidates(states, targets, cand_state, cand_op, cand_param, state_tar
     return score_prepared(states, targets, cb, curve_steps)
 
 
+def topk_min(values, seg_begin, k):
+    """The k smallest values of every segment in ascending order (ties by the smaller index, NaN last): the argsort + [:beam_size]
+    of a planner step (utils/beam_search.py:252-256) for many searches at once, on the device.
+    values (C,) float32 CUDA; seg_begin (n_seg + 1,) ints.  -> (idx (n_seg, k) int32 into `values`, -1 padded; val (n_seg, k))."""
+    _lib.require_cuda(values)
+    values = values.detach().float().contiguous()
+    sb = torch.as_tensor(seg_begin, dtype=torch.int32).to(values.device).contiguous()
+    n_seg = sb.numel() - 1
+    idx = torch.empty(n_seg, k, dtype=torch.int32, device=values.device)
+    val = torch.empty(n_seg, k, dtype=torch.float32, device=values.device)
+    _lib.check(_lib.lib().t2o_topk_min(_lib.ptr(values), _lib.ptr(sb), n_seg, k, _lib.ptr(idx), _lib.ptr(val), _lib.stream_ptr(values.device)))
+    return idx, val
+
+
 class DeviceNelderMead:
     """P Nelder-Mead fits that live on the GPU (t2o_nm_start / t2o_nm_advance), each scored as candidate p of
     t2o_score_candidates: argmin_param L1(op(states[prob_state[p]]; param), its target) with scipy's defaults, as

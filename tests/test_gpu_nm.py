@@ -96,3 +96,30 @@ def test_entry_points_share_one_workspace_across_batch_sizes(T):
     torch.cuda.synchronize()
     ws = _lib.workspace(states.device, 1)
     assert not bool(ws[:65536 * 4].any())
+
+
+def test_topk_min_is_the_stable_argsort_prefix(T):
+    """t2o_topk_min == np.argsort(kind='stable')[:k] per segment (utils/beam_search.py:252-256), with ties, NaN, short and
+    empty segments."""
+    import t2onet_b200.functional as TF
+    g = torch.Generator().manual_seed(9)
+    sizes = [0, 1, 3, 8, 17, 64, 200, 1000]
+    vals = []
+    for n in sizes:
+        v = torch.rand(n, generator=g)
+        if n >= 8:
+            v[::3] = v[0]                                   # exact ties
+            v[5] = float('nan')
+        vals.append(v)
+    values = torch.cat(vals)
+    seg = np.concatenate([[0], np.cumsum(sizes)])
+    for k in (1, 8, 32):
+        idx, val = TF.topk_min(values.cuda(), seg, k)
+        idx, val = idx.cpu().numpy(), val.cpu().numpy()
+        for s, n in enumerate(sizes):
+            v = values[seg[s]:seg[s + 1]].numpy()
+            order = np.argsort(np.where(np.isnan(v), np.inf, v), kind='stable')[:k]
+            assert list(idx[s, :len(order)]) == [int(o) + int(seg[s]) for o in order], (k, s)
+            assert all(i == -1 for i in idx[s, len(order):]) and np.all(np.isinf(val[s, len(order):]))
+            got = val[s, :len(order)]
+            assert np.array_equal(np.isnan(got), np.isnan(v[order])) and np.array_equal(got[~np.isnan(got)], v[order][~np.isnan(v[order])])
