@@ -256,6 +256,25 @@ int t2o_nm_start(const t2o_nm_state *state /*host struct of device pointers*/, i
 int t2o_nm_advance(const t2o_nm_state *state /*host struct of device pointers*/, int P,
                    const float *l1_sum, float numel, float *cand_param, int32_t *cand_op, t2o_stream_t stream);
 
+/*
+ * Every fit of a planner step in ONE launch (replaces the thousands of get_dist calls scipy makes per fit,
+ * utils/beam_search.py:65-91): after t2o_nm_start, a cluster of CTAs (one per tile of the image) keeps a state and its target
+ * in shared memory for the whole life of the state's fits, the cluster's first CTA keeps the fits' simplices there too, and
+ * the cluster iterates score -> advance -- the same arithmetic as rounds of t2o_score_candidates + t2o_nm_advance, bit for
+ * bit, without re-staging the images or touching device memory between evaluations.
+ * fits_begin[s] .. fits_begin[s+1] are the fits of state s (S + 1 ints, at most 8 fits per state; fits sorted by state as for
+ * t2o_score_candidates); fit_mask / masks as in t2o_score_candidates_masked (NULL: none); host_fits_begin / host_fit_op are
+ * HOST copies of fits_begin and of the fits' operators (they size the launch's shared memory); max_rounds bounds the
+ * evaluations per fit (200 * 24 + 8 covers scipy's maxfev); fits it leaves unfinished can go on, here or in rounds.
+ * Returns T2O_ERR_UNSUPPORTED where the shape is not eligible (more than 8 tiles of 32 x 128 pixels per image, more than 8
+ * fits per state, W % 4 != 0, no TMA, fits too large for the shared memory): run the rounds instead.  workspace: >= 256 KiB.
+ */
+int t2o_nm_run_resident(const float *states, int S, const float *targets, int T, const int32_t *state_target,
+                        const int32_t *fits_begin, const int32_t *fit_mask, const float *masks, int n_masks, int mask_ch,
+                        const t2o_nm_state *state /*host struct of device pointers*/, int P, float numel,
+                        float *cand_param, int32_t *cand_op, const int32_t *host_fits_begin, const int32_t *host_fit_op,
+                        int H, int W, int curve_steps, int max_rounds, void *workspace, size_t workspace_bytes, t2o_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,9 @@ def _declare(lib):
     for name in ('t2o_img2tensor', 't2o_tensor2img'):
         getattr(lib, name).restype = ci
         getattr(lib, name).argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.t2o_nm_run_resident.restype = ci
+    lib.t2o_nm_run_resident.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, ci, ci, ctypes.POINTER(NMState), ci, ctypes.c_float, vp, vp,
+                                        vp, vp, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
     lib.t2o_topk_min.restype = ci
     lib.t2o_topk_min.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.t2o_nm_start.restype = ci
@@ -86,7 +89,7 @@ def _declare(lib):
 EXPORTS = ['t2o_version', 't2o_status_string', 't2o_last_cuda_error', 't2o_num_params', 't2o_workspace_bytes',
            't2o_score_workspace_bytes', 't2o_chain_forward', 't2o_chain_backward', 't2o_rows_forward',
            't2o_rows_backward', 't2o_l1_sum',
-           't2o_score_candidates', 't2o_score_candidates_masked', 't2o_topk_min', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
+           't2o_score_candidates', 't2o_score_candidates_masked', 't2o_topk_min', 't2o_nm_run_resident', 't2o_nm_start', 't2o_nm_advance', 't2o_ssim_workspace_bytes', 't2o_ssim_sum',
            't2o_u8_to_f32', 't2o_f32_to_u8', 't2o_img2tensor', 't2o_tensor2img']
 
 

@@ -15,9 +15,9 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libt2o_b200.so')
 SOURCES = ['t2o_chain.cu', 't2o_step.cu',
            't2o_score.cu', 't2o_nm.cu', 't2o_ssim.cu', 't2o_convert.cu', 't2o_cabi.cu']
-HEADERS = ['t2o_math.cuh', 't2o_common.cuh', 't2o_chain_kernels.cuh', 't2o_step_kernels.cuh', os.path.join('..', '..', 'include', 't2o.h')]
+HEADERS = ['t2o_math.cuh', 't2o_common.cuh', 't2o_nm_device.cuh', 't2o_chain_kernels.cuh', 't2o_step_kernels.cuh', os.path.join('..', '..', 'include', 't2o.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC']
+              '-Xcompiler', '-fPIC'] + os.environ.get('T2O_NVCC_EXTRA', '').split()     # (development probes: -DT2O_RES_PROBE)
 
 
 def nvcc_path():

@@ -28,6 +28,11 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
                      const int *cand_begin, const int *cand_op, const float *cand_param, const int *cand_mask,
                      const float *masks, int n_masks, int mask_ch, int C, float *l1_sum,
                      int H, int W, int L, void *ws, size_t ws_bytes, cudaStream_t stream);
+int nm_run_resident(const float *states, int S, const float *targets, int T, const int *state_target, const int *fits_begin,
+                    const int *cand_mask, const float *masks, int n_masks, int mask_ch,
+                    const t2o_nm_state *st, int P, float numel, float *cand_param, int *cand_op,
+                    const int *h_fits_begin, const int *h_fit_op,
+                    int H, int W, int L, int max_rounds, void *ws, size_t ws_bytes, cudaStream_t stream);
 int topk_min(const float *values, const int *seg_begin, int n_seg, int k, int *out_idx, float *out_val, cudaStream_t stream);
 int nm_start(const t2o_nm_state *st, int P, const int *n_dims, const int *prob_op, const double *x0,
              float *cand_param, int *cand_op, cudaStream_t stream);
@@ -129,6 +134,16 @@ int t2o_score_candidates_masked(const float *states, int S, const float *targets
                                 int H, int W, int curve_steps, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
     return t2o::score_candidates(states, S, targets, T, state_target, cand_begin, cand_op, cand_param, cand_mask, masks, n_masks,
                                  mask_ch, C, l1_sum, H, W, curve_steps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int t2o_nm_run_resident(const float *states, int S, const float *targets, int T, const int32_t *state_target,
+                        const int32_t *fits_begin, const int32_t *fit_mask, const float *masks, int n_masks, int mask_ch,
+                        const t2o_nm_state *state, int P, float numel, float *cand_param, int32_t *cand_op,
+                        const int32_t *host_fits_begin, const int32_t *host_fit_op,
+                        int H, int W, int curve_steps, int max_rounds, void *workspace, size_t workspace_bytes, t2o_stream_t stream) {
+    return t2o::nm_run_resident(states, S, targets, T, state_target, fits_begin, fit_mask, masks, n_masks, mask_ch, state, P, numel,
+                                cand_param, cand_op, host_fits_begin, host_fit_op, H, W, curve_steps, max_rounds, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
 }
 
 int t2o_topk_min(const float *values, const int32_t *seg_begin, int n_seg, int k, int32_t *out_idx, float *out_val,

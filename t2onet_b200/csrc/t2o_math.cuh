@@ -70,6 +70,7 @@ constexpr float BLUR_WC = 0.13080118596553802f, BLUR_WE = 0.11543164402246475f, 
 constexpr float TWO_PI_F = 6.283185307179586f;
 
 struct F2 { float a, b; };   // == float2 without needing vector_types.h on the host
+struct F4 { float a, b, c, d; };   // == float4
 
 // ---------------------------------------------------------------- scalar helpers
 T2O_HD float sat01(float z) {
@@ -157,41 +158,71 @@ T2O_HD float lum_rn(float r, float g, float b) {
 //              ct[CT_INVS] = 1/S, ct[CT_SCALE] = L/S
 // BWD: also set CT_INRANGE (only the backward kernels read it; the forward kernels and the scorer, which builds a table per
 // candidate and round, skip the 2 L evaluations)
+// One record of a curve table and the scalars every record needs.  Every product and sum is an explicitly rounded operation
+// (mul_rn / fmaf), so that the serial builder below and the lane-parallel one of the resident planner kernel (one lane per
+// record, t2o_score.cu) produce the same bits whatever the compiler would contract.
+struct CurveScalars { float S, scale, invL; };
+// (fixed trip counts with a predicate: the loops unroll, the loads of k[] issue together)
+T2O_HD CurveScalars curve_scalars(const float *k, int L) {
+    float S = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAX_L; ++i)
+        if (i < L) S += k[i];
+    S += CURVE_EPS;
+    return CurveScalars{S, (float)L / S, 1.0f / (float)L};
+}
+// prefix_j = sum_{i<j} k_i / L, accumulated in index order
+T2O_HD float curve_prefix(const float *k, int j, float invL) {
+    float prefix = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAX_L; ++i)
+        if (i < j) prefix = fmaf(k[i], invL, prefix);
+    return prefix;
+}
+// record j < L from prefix_j: (k'_j, Q_j, K_j, k'_j)
+T2O_HD F4 curve_record(const float *k, int L, int j, const CurveScalars &cs, float prefix) {
+    const float kp = mul_rn(k[j], cs.scale);
+    const float q = fmaf(-kp, mul_rn((float)j, cs.invL), mul_rn(prefix, cs.scale));
+    const float K = (j > 0) ? fmaf(k[j - 1], cs.scale, kp) : kp;
+    return F4{kp, q, K, kp};
+}
+// The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1, which would make the
+// output clamp swallow the gradient of every saturated (x == 1.0) pixel.  Pull the last segment back so that y(1) <= 1 (a
+// < 1e-6 shift; reference rounding there is platform dependent anyway).
+T2O_HD float curve_pull_back(float kp_last, float q_last) {
+    float q_end = q_last;
+    if (fmaf(kp_last, 1.0f, q_end) < 1.0f + 1e-5f)
+        for (int it = 0; it < 8; ++it) {
+            // one ulp of y(1) can be many ulps of a small Q: step by the excess, and by at least one ulp of Q
+            const float y1 = fmaf(kp_last, 1.0f, q_end);
+            if (!(y1 > 1.0f)) break;
+            q_end = fminf(nextafterf(q_end, -4.0f), q_end - (y1 - 1.0f));
+        }
+    return q_end;
+}
+
+// BWD: also set CT_INRANGE (only the backward kernels read it; the forward kernels and the scorer, which builds a table per
+// candidate and round, skip the 2 L evaluations)
 template <bool BWD = true>
 T2O_HD void build_curve(const float *k, int L, float *ct) {
-    float S = 0.0f;
-    for (int i = 0; i < L; ++i) S += k[i];
-    S += CURVE_EPS;
-    const float scale = (float)L / S;
-    const float invL = 1.0f / (float)L;
+    const CurveScalars cs = curve_scalars(k, L);
+    const float invL = cs.invL;
     float prefix = 0.0f;
     for (int j = 0; j < NBIN; ++j) {
-        float kp = 0.0f, q = 0.0f;
+        F4 r = F4{0.0f, 0.0f, 0.0f, 0.0f};
         if (j < L) {
-            kp = k[j] * scale;
-            q = prefix * scale - kp * ((float)j * invL);
-            prefix += k[j] * invL;
+            r = curve_record(k, L, j, cs, prefix);
+            prefix = fmaf(k[j], invL, prefix);
         }
-        ct[4 * j] = kp;
-        ct[4 * j + 1] = q;
-        ct[4 * j + 2] = (j > 0 && j < L) ? kp + k[j - 1] * scale : kp;
-        ct[4 * j + 3] = kp;
+        ct[4 * j] = r.a; ct[4 * j + 1] = r.b; ct[4 * j + 2] = r.c; ct[4 * j + 3] = r.d;
     }
-    // The curve maps 1 -> sum(k)/(sum(k)+1e-10) < 1, but the rounded table can land one ulp above 1,
-    // which would make the output clamp swallow the gradient of every saturated (x == 1.0) pixel.
-    // Pull the last segment back so that y(1) <= 1 (a < 1e-6 shift; reference rounding there is
-    // platform dependent anyway).
-    float q_end = ct[4 * (L - 1) + 1];
-    if (fmaf(ct[4 * (L - 1)], 1.0f, q_end) < 1.0f + 1e-5f) {
-        for (int it = 0; it < 8 && fmaf(ct[4 * (L - 1)], 1.0f, q_end) > 1.0f; ++it) q_end = nextafterf(q_end, -4.0f);
-        ct[4 * (L - 1) + 1] = q_end;
-    }
+    ct[4 * (L - 1) + 1] = curve_pull_back(ct[4 * (L - 1)], ct[4 * (L - 1) + 1]);
     ct[4 * L] = ct[4 * (L - 1)];
     ct[4 * L + 1] = ct[4 * (L - 1) + 1];
     ct[4 * L + 2] = ct[4 * (L - 1)];
     ct[4 * L + 3] = ct[4 * (L - 1)];
-    ct[CT_INVS] = 1.0f / S;
-    ct[CT_SCALE] = scale;
+    ct[CT_INVS] = 1.0f / cs.S;
+    ct[CT_SCALE] = cs.scale;
     // Does the output clamp ever cut this curve?  y is linear on a segment and fmaf is monotone in x, so it is enough to
     // evaluate both ends of every segment the way the kernels do.  All k_i >= 0 (every curve the Actor's regressors
     // produce) gives 1: the backward then skips the clamp gate of this curve.
@@ -302,7 +333,6 @@ T2O_HD void hue_y(const float *tab, float r, float g, float b, float &yr, float 
 // clamped, so j <= L always), no float->int conversion.  Every kernel keeps its operator tables in shared memory
 // (StepShared::tabs, ChainShared::tabs, the scorer's wtab).  The scaling by 2^-22 is exact, so tt == u - 2 exactly when
 // L xs is an integer (the knot test of the backward), and fma(tt, 2^22, -i) is the correctly rounded L xs - i.
-struct F4 { float a, b, c, d; };   // == float4
 constexpr float CURVE_TT = 1.0f / 4194304.0f, CURVE_TT_INV = 4194304.0f;   // 2^-22, 2^22
 // -> tt = L xs 2^-22, tfs = j 2^-22; seg = (k'_j, Q_j[, K_j, 0])
 T2O_HD F2 curve_seg2(const float *ct, float xs, int L, float &tt, float &tfs) {

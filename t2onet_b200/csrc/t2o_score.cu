@@ -17,7 +17,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "t2o_common.cuh"
+#include "t2o_nm_device.cuh"
 #include "../../include/t2o.h"
 
 namespace t2o {
@@ -55,6 +58,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// distributed shared memory: the address of `p` (this CTA's shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void *p, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+// one 32-bit word into another CTA's shared memory, completing 4 bytes of the transaction count of an mbarrier there: the
+// receiver that sees the barrier's phase complete sees the data (no fence, no cluster barrier)
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t value, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(value), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity) {
+    bool done = false;
+    for (int it = 0; it < (1 << 24) && !done; ++it) done = mbar_try_wait(bar, parity);
+    if (!done) __trap();                                         // a broken protocol must fail loudly, not hang the GPU
+}
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -69,10 +89,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, ui
 // HM: the launch carries masks (Operator.execute's out * mask + img * (1 - mask), models/operators.py:129): `mptr` points at
 // the group's first pixel in the candidate's mask (global memory, channels `mcs` floats apart; 0 for a 1-channel mask),
 // or is null for a candidate without a mask (mask = 1: blend(y, x, 1) == y to the bit).
+// (split in two so that the resident kernel loads a group once for all the fits of its state: xc / t are the group's centre
+// pixels of the state and its target pixels)
 template <int VEC, bool HM>
-__device__ __forceinline__ void score_group(float &sum, int op, const float *tab, int L, float p, const float *src, int spitch, int cs,
-                                            const float *tsrc, int ct, const float *mptr, size_t mcs) {
-    float x[3][VEC], t[3][VEC], m[3][VEC];
+__device__ __forceinline__ void score_group_loaded(float &sum, int op, const float *tab, int L, float p, const float (&xc)[3][VEC],
+                                                   const float (&t)[3][VEC], const float *src, int spitch, int cs,
+                                                   const float *mptr, size_t mcs) {
+    float x[3][VEC], m[3][VEC];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (HM && mptr) ld_vec<VEC>(mptr + c * mcs, m[c]);
@@ -85,38 +108,38 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float *row = src + c * cs;
-            float ctr[VEC], up[VEC], dn[VEC];
-            lds_vec<VEC>(row, ctr);
+            float up[VEC], dn[VEC];
             lds_vec<VEC>(row - spitch, up);
             lds_vec<VEC>(row + spitch, dn);
             const float lf = row[-1], rt = row[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float l = v > 0 ? ctr[v - 1] : lf;
-                const float r = v < VEC - 1 ? ctr[v + 1] : rt;
-                x[c][v] = sat01(blend<HM>(fmaf(p, laplace(ctr[v], up[v], dn[v], l, r), ctr[v]), ctr[v], m[c][v]));
+                const float l = v > 0 ? xc[c][v - 1] : lf;
+                const float r = v < VEC - 1 ? xc[c][v + 1] : rt;
+                x[c][v] = sat01(blend<HM>(fmaf(p, laplace(xc[c][v], up[v], dn[v], l, r), xc[c][v]), xc[c][v], m[c][v]));
             }
         }
     } else if (op == OP_BLUR) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float *row = src + c * cs, *ru = row - spitch, *rd = row + spitch;
-            float ctr[VEC], up[VEC], dn[VEC];
-            lds_vec<VEC>(row, ctr);
+            float up[VEC], dn[VEC];
             lds_vec<VEC>(ru, up);
             lds_vec<VEC>(rd, dn);
             const float lf = row[-1], rt = row[VEC], ul = ru[-1], ur = ru[VEC], dl = rd[-1], dr = rd[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float l = v > 0 ? ctr[v - 1] : lf, r = v < VEC - 1 ? ctr[v + 1] : rt;
+                const float l = v > 0 ? xc[c][v - 1] : lf, r = v < VEC - 1 ? xc[c][v + 1] : rt;
                 const float e = v > 0 ? up[v - 1] : ul, f = v < VEC - 1 ? up[v + 1] : ur;
                 const float g = v > 0 ? dn[v - 1] : dl, h = v < VEC - 1 ? dn[v + 1] : dr;
-                x[c][v] = sat01(blend<HM>(fmaf(p, blur_delta(ctr[v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), ctr[v]), ctr[v], m[c][v]));
+                x[c][v] = sat01(blend<HM>(fmaf(p, blur_delta(xc[c][v], (up[v] + dn[v]) + (l + r), (e + f) + (g + h)), xc[c][v]), xc[c][v], m[c][v]));
             }
         }
     } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) lds_vec<VEC>(src + c * cs, x[c]);
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x[c][v] = xc[c][v];
         switch (op) {
 #define T2O_CASE(OPC)                                                                                         \
     case OPC:                                                                                                 \
@@ -131,11 +154,21 @@ __device__ __forceinline__ void score_group(float &sum, int op, const float *tab
         }
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        lds_vec<VEC>(tsrc + c * ct, t[c]);
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) sum += fabsf(x[c][v] - t[c][v]);
+}
+
+template <int VEC, bool HM>
+__device__ __forceinline__ void score_group(float &sum, int op, const float *tab, int L, float p, const float *src, int spitch, int cs,
+                                            const float *tsrc, int ct, const float *mptr, size_t mcs) {
+    float xc[3][VEC], t[3][VEC];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lds_vec<VEC>(src + c * cs, xc[c]);
+        lds_vec<VEC>(tsrc + c * ct, t[c]);
     }
+    score_group_loaded<VEC, HM>(sum, op, tab, L, p, xc, t, src, spitch, cs, mptr, mcs);
 }
 
 // VEC = 4: W % 4 == 0, state rows padded by 4 floats each side (keeps 128-bit LDS aligned)
@@ -173,7 +206,9 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
 
     const bool coop = a.nsplit == 1 && cend - cbeg <= SCORE_NW;      // few candidates: all warps share each candidate's tile
 
-    float *sS = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
+    // (aligned by an offset into the array, not by integer arithmetic on the address: the pointers stay shared-memory pointers,
+    // so the tiles are read with LDS rather than generic loads)
+    float *sS = reinterpret_cast<float *>(dyn_raw + ((128u - (smem_u32(dyn_raw) & 127u)) & 127u));
     float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sS) + ((3 * srows * spitch * 4 + 127) & ~127));
     const size_t plane = (size_t)H * W;
 
@@ -283,6 +318,324 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------- resident Nelder-Mead
+// The fits of a planner step as ONE launch.  Round by round (t2o_score_candidates + t2o_nm_advance, thousands of times) every
+// round re-stages every state: a CTA per (state, tile) pays a candidate scan, a TMA round trip and an arrival-counter
+// epilogue for ~0.6 us of arithmetic, and the host pays a launch pair per round.  Here a CLUSTER of ntiles CTAs owns a state
+// for the whole life of its fits: each CTA stages its tile of the state and of the target ONCE; the leader (CTA 0) copies the
+// Nelder-Mead state of the state's fits (simplex, values, counters) from the caller's arrays into its shared memory, packed
+// by the fits' dimensions; then the cluster iterates
+//     leader: the fits' pending vertices -> every CTA's shared memory (st.async over distributed shared memory, completing
+//             the transaction count of the receiver's mbarrier `pbar`: no fence, no cluster barrier)
+//     every CTA: wait on pbar; tables of the live fits' vertices (one lane per curve record), |op(tile) - target tile| per
+//                fit (score_kernel's cooperative path), tile partials -> the leader's shared memory (st.async, `sbar`)
+//     leader: wait on sbar; one warp per fit consumes the score and proposes the next vertex (nm_advance_bound, on shared
+//             memory)
+// until every fit of the state is finished, writes the fits' state back and takes the next state (atomic work counter).
+// Vertices and scores never leave the SMs.  The arithmetic is the round-by-round path's, bit for bit: the same tiles, the
+// same groups per thread in the same order, the same warp / tile reduction order, the same Nelder-Mead code --
+// tests/test_gpu_nm.py compares the two exactly.
+namespace cg = cooperative_groups;
+constexpr int RES_MAXT = 8;      // tiles per state = cluster size (portable limit)
+
+struct ResidentShared {
+    float wsum[SCORE_NW][SCORE_NW];
+    float part[SCORE_NW][RES_MAXT];      // leader: tile partials of every fit, sent by the cluster's CTAs (completing sbar)
+    float cprm[SCORE_NW][NM_MAXN];       // pending vertex of every fit, sent by the leader to every CTA (completing pbar)
+    int cops[SCORE_NW];                  // its operator, T2O_OP_SKIP once the fit has finished (ditto)
+    float pend[SCORE_NW][NM_MAXN];       // leader: the vertex / operator the Nelder-Mead code proposes next (staging for cprm / cops)
+    int pop[SCORE_NW];
+    int cops0[SCORE_NW];                 // the fits' operators when the state was taken (table offsets)
+    int cmask[SCORE_NW];                 // the fits' masks
+    int nmoff[SCORE_NW];                 // leader: byte offset of fit c in the Nelder-Mead region, -1: not loaded
+    int nmN[SCORE_NW];                   // leader: its number of parameters
+    int toff[SCORE_NW];                  // offset of fit c's table (floats)
+    int next_state;                      // the state the cluster works on (written by the leader into every CTA)
+    uint64_t bar;                        // the tiles' TMA loads
+    uint64_t pbar;                       // a round's pending vertices have arrived (100 bytes per fit)
+    uint64_t sbar;                       // leader: a round's tile partials have arrived (4 bytes per fit and CTA)
+};
+
+// floats of an operator's table / bytes of a fit's Nelder-Mead state in shared memory (host and device agree on these)
+__host__ __device__ inline int res_tab_floats(int op) { return op == OP_COLOR ? 3 * CT : (op == OP_TONE ? CT : 8); }
+__host__ __device__ inline int res_nm_bytes(int N) { return (8 * (N * N + 5 * N + 2) + 4 * (N + 9) + 7) & ~7; }
+
+// fit c of the leader: views into the packed region [sim (N+1) x N | vec 3 x N | fsim N+1 | fxr | perm N+1 | ctl 8]
+__device__ __forceinline__ void res_bind(NMWarp &w, unsigned char *base, int N, const NMArgs &nm, int p, int lane, float *cprm, int *cop) {
+    double *d = reinterpret_cast<double *>(base);
+    w.sim = d; d += (N + 1) * N;
+    w.vec = d; d += 3 * N;
+    w.fsim = d; d += N + 1;
+    w.fxr = d; d += 1;
+    int *i = reinterpret_cast<int *>(d);
+    w.perm = i; i += N + 1;
+    w.ctl = i;
+    w.xbest = nm.st.xbest + (size_t)p * NM_MAXN;
+    w.fbest = nm.st.fbest + p;
+    w.cparam = cprm;
+    w.cop = cop;
+    w.ld = N;
+    w.lane = lane;
+    // (these views are shared memory: lets the Nelder-Mead code, written for generic pointers, use LDS / STS)
+    __builtin_assume(__isShared(w.sim)); __builtin_assume(__isShared(w.vec)); __builtin_assume(__isShared(w.fsim));
+    __builtin_assume(__isShared(w.fxr)); __builtin_assume(__isShared(w.perm)); __builtin_assume(__isShared(w.ctl));
+    __builtin_assume(__isShared(w.cparam)); __builtin_assume(__isShared(w.cop));
+}
+
+// lane-parallel table of one fit: one lane per curve record (3 L lanes of a color operator, L of a tone operator), lane 0
+// everything else -- the same functions in the same order as build_curve, so the same bits
+__device__ __forceinline__ void build_table_lanes(int op, int lane, const float *p, int L, float *tab) {
+    if (op == OP_COLOR || op == OP_TONE) {
+        const int part = lane / L, j = lane - part * L;
+        if (part < (op == OP_COLOR ? 3 : 1)) {
+            const float *k = p + part * L;
+            float *ct = tab + part * CT;
+            const CurveScalars cs = curve_scalars(k, L);
+            F4 r = curve_record(k, L, j, cs, curve_prefix(k, j, cs.invL));
+            if (j == L - 1) {
+                r.b = curve_pull_back(r.a, r.b);
+                *reinterpret_cast<float4 *>(ct + 4 * L) = make_float4(r.a, r.b, r.a, r.a);
+                ct[CT_INVS] = 1.0f / cs.S;
+                ct[CT_SCALE] = cs.scale;
+            }
+            *reinterpret_cast<float4 *>(ct + 4 * j) = make_float4(r.a, r.b, r.c, r.d);
+        }
+    } else if (lane == 0) {
+        build_table<false>(op, p, L, tab);
+    }
+}
+
+template <bool HM>
+__global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_constant__ CUtensorMap tm_state,
+                                                                 const __grid_constant__ CUtensorMap tm_target,
+                                                                 const __grid_constant__ ScoreArgs a, const __grid_constant__ NMArgs nm,
+                                                                 unsigned int *work_counter, int max_rounds, int tab_cap, int nm_cap,
+                                                                 unsigned long long *probe) {
+    constexpr int VEC = 4, HX = 4;
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    __shared__ __align__(16) ResidentShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();                  // = tile index
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W, TH = a.TH, TW = a.TW;
+    const int spitch = TW + 2 * HX, srows = TH + 2;
+    const int ty = rank / a.tiles_x, tx = rank - ty * a.tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    const int TWg = TW / VEC, ngroups = TH * TWg;
+    const int twg_magic = 65536 / TWg + 1;                       // gi / TWg == (gi * twg_magic) >> 16 for gi * TWg < 65536
+    const size_t plane = (size_t)H * W;
+    const size_t mcs = HM && a.mask_ch == 3 ? plane : 0;
+    // (aligned by an offset into the array, not by integer arithmetic on the address: the pointers stay shared-memory pointers,
+    // so the tiles are read with LDS rather than generic loads)
+    float *sS = reinterpret_cast<float *>(dyn_raw + ((128u - (smem_u32(dyn_raw) & 127u)) & 127u));
+    float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sS) + ((3 * srows * spitch * 4 + 127) & ~127));
+    float *tabs = sT + 3 * TH * TW;                                              // tab_cap floats (16-byte aligned)
+    unsigned char *nmreg = reinterpret_cast<unsigned char *>(tabs + tab_cap);      // nm_cap bytes (leader only)
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        mbar_init(&sh.pbar, 1);
+        mbar_init(&sh.sbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t bar_phase = 0, pphase = 0, sphase = 0;           // (the first cluster barrier below orders the initialisation)
+
+    for (;;) {
+        // ---- the cluster's next state
+        if (rank == 0 && tid == 0) {
+            const int nxt = (int)atomicAdd(work_counter, 1u);
+            for (int r = 0; r < a.ntiles; ++r) cluster.map_shared_rank(&sh, r)->next_state = nxt;
+        }
+        cluster.sync();
+        const int s = sh.next_state;
+        if (s >= a.S) break;
+        const int cbeg = a.cand_begin[s], cend = a.cand_begin[s + 1];
+        const int m = cend - cbeg;                               // <= SCORE_NW (checked by the host)
+        {
+            bool any = false;
+            for (int ci = cbeg; ci < cend; ++ci) any |= __ldcg(a.cand_op + ci) != OP_SKIP;
+            if (!any) continue;                                  // (every CTA of the cluster takes the same decision)
+        }
+        const int t_idx = a.state_target ? a.state_target[s] : s % a.T;
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(3 * srows * spitch + 3 * TH * TW) * 4u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&sh.bar, bytes);
+            tma_load_4d(sS, &tm_state, &sh.bar, x0 - HX, y0 - 1, 0, s);
+            tma_load_4d(sT, &tm_target, &sh.bar, x0, y0, 0, t_idx);
+        }
+        // ---- leader: the fits' Nelder-Mead state -> shared memory, their pending vertices -> every CTA
+        if (rank == 0 && warp < m) {
+            const int p = cbeg + warp;
+            // a state whose fits do not fit the shared memory the host sized is left alone (its fits stay unfinished)
+            int off = 0, N = 0, nm_total = 0, tab_total = 0;
+            for (int c = 0; c < m; ++c) {
+                const int Nc = __ldcg(nm.st.ctl + (size_t)(cbeg + c) * 8 + CTL_N);
+                if (c < warp) off += res_nm_bytes(Nc);
+                if (c == warp) N = Nc;
+                nm_total += res_nm_bytes(Nc);
+                tab_total += res_tab_floats(__ldcg(a.cand_op + cbeg + c));
+            }
+            const bool fits_ok = nm_total <= nm_cap && tab_total <= tab_cap;
+            const int op = fits_ok ? __ldcg(a.cand_op + p) : OP_SKIP;
+            const float prm = lane < NM_MAXN ? __ldcg(a.cand_param + (size_t)p * NM_MAXN + lane) : 0.0f;
+            const int mi = (HM && a.cand_mask) ? a.cand_mask[p] : -1;
+            if (op != OP_SKIP) {
+                NMWarp w;
+                res_bind(w, nmreg + off, N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
+                const double *gsim = nm.st.sim + (size_t)p * NM_ROWS * NM_MAXN, *gvec = nm.st.vec + (size_t)p * 3 * NM_MAXN;
+                if (lane < N) {
+                    for (int r = 0; r <= N; ++r) w.sim[r * N + lane] = __ldcg(gsim + r * NM_MAXN + lane);
+                    for (int r = 0; r < 3; ++r) w.vec[r * N + lane] = __ldcg(gvec + r * NM_MAXN + lane);
+                }
+                if (lane <= N) {
+                    w.fsim[lane] = __ldcg(nm.st.fsim + (size_t)p * NM_ROWS + lane);
+                    w.perm[lane] = __ldcg(nm.st.perm + (size_t)p * NM_ROWS + lane);
+                }
+                if (lane < 8) w.ctl[lane] = __ldcg(nm.st.ctl + (size_t)p * 8 + lane);
+                if (lane == 0) *w.fxr = __ldcg(nm.st.fxr + p);
+            }
+            if (lane == 0) { sh.nmoff[warp] = op != OP_SKIP ? off : -1; sh.nmN[warp] = N; sh.pop[warp] = op; }
+            if (lane < NM_MAXN) sh.pend[warp][lane] = prm;
+            for (int r = 0; r < a.ntiles; ++r) {
+                ResidentShared *dst = cluster.map_shared_rank(&sh, r);
+                if (lane == 0) { dst->cops0[warp] = op; dst->cmask[warp] = mi; }
+            }
+        }
+        cluster.sync();                                          // cops0 / cmask are in place (once per state)
+        {
+            bool done = false;
+            for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try_wait(&sh.bar, bar_phase);
+            if (!done) __trap();
+            bar_phase ^= 1u;
+        }
+        // ---- rounds
+#ifdef T2O_RES_PROBE
+        long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
+#define T2O_PROBE(i) { const long long now = clock64(); pc[i] += now - pt; pt = now; }
+#else
+#define T2O_PROBE(i)
+#endif
+        for (int round = 0; round < max_rounds; ++round) {
+#ifdef T2O_RES_PROBE
+            pt = clock64();
+#endif
+            // leader: the fits' pending vertices (or T2O_OP_SKIP) -> every CTA, itself included: 25 words per fit
+            if (rank == 0 && warp < m) {
+                __syncwarp();
+                const uint32_t v = lane < NM_MAXN ? __float_as_uint(sh.pend[warp][lane]) : (uint32_t)sh.pop[warp];
+                if (lane <= NM_MAXN)
+                    for (int r = 0; r < a.ntiles; ++r)
+                        st_async_u32(mapa_u32(lane < NM_MAXN ? (const void *)&sh.cprm[warp][lane] : (const void *)&sh.cops[warp], r), v,
+                                     mapa_u32(&sh.pbar, r));
+            }
+            if (tid == 0) mbar_expect_tx(&sh.pbar, (uint32_t)m * 4u * (NM_MAXN + 1));
+            mbar_wait_or_trap(&sh.pbar, pphase);
+            pphase ^= 1u;
+            T2O_PROBE(0)
+            int ops[SCORE_NW], toff[SCORE_NW];
+            bool any = false;
+            {
+                int o = 0;
+#pragma unroll
+                for (int c = 0; c < SCORE_NW; ++c) {
+                    ops[c] = c < m ? sh.cops[c] : OP_SKIP;
+                    toff[c] = o;
+                    o += c < m ? res_tab_floats(sh.cops0[c]) : 0;
+                    any |= ops[c] != OP_SKIP;
+                }
+            }
+            if (!any) break;
+            if (warp < m) {
+                int op = OP_SKIP, to = 0;
+#pragma unroll
+                for (int c = 0; c < SCORE_NW; ++c) { op = warp == c ? ops[c] : op; to = warp == c ? toff[c] : to; }
+                if (lane == 0) sh.toff[warp] = to;
+                if (op != OP_SKIP) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + to);
+            }
+            __syncthreads();
+            T2O_PROBE(1)
+            // fit by fit, all warps share the tile (score_kernel's cooperative path: thread tid takes groups tid, tid + 256, ...)
+#pragma unroll 1
+            for (int c = 0; c < m; ++c) {
+                const int op = sh.cops[c];
+                if (op == OP_SKIP) continue;
+                const float *tab = tabs + sh.toff[c];
+                const float p = tab[0];
+                const float *mimg = nullptr;
+                if (HM) { const int mi = sh.cmask[c]; if (mi >= 0) mimg = a.masks + (size_t)mi * a.mask_ch * plane; }
+                float sum = 0.0f;
+#pragma unroll 1
+                for (int gi = tid; gi < ngroups; gi += SCORE_NT) {
+                    const int ly = (gi * twg_magic) >> 16, lx = (gi - ly * TWg) * VEC;     // gi / TWg (exact: gi < 1024, TWg <= 32)
+                    if (y0 + ly >= H || x0 + lx >= W) continue;
+                    score_group<VEC, HM>(sum, op, tab, a.L, p, sS + (ly + 1) * spitch + HX + lx, spitch, srows * spitch,
+                                         sT + ly * TW + lx, TH * TW, mimg ? mimg + (size_t)(y0 + ly) * W + x0 + lx : nullptr, mcs);
+                }
+                sum = warp_sum(sum);
+                if (lane == 0) sh.wsum[c][warp] = sum;
+            }
+            __syncthreads();
+            T2O_PROBE(2)
+            if (tid < m) {
+                float v = 0.0f;
+#pragma unroll
+                for (int w = 0; w < SCORE_NW; ++w) v += sh.wsum[tid][w];
+                st_async_u32(mapa_u32(&sh.part[tid][rank], 0), __float_as_uint(sh.cops[tid] != OP_SKIP ? v : 0.0f), mapa_u32(&sh.sbar, 0));
+            }
+            if (rank == 0) {
+                if (tid == 0) mbar_expect_tx(&sh.sbar, (uint32_t)(a.ntiles * m) * 4u);
+                mbar_wait_or_trap(&sh.sbar, sphase);
+                sphase ^= 1u;
+            }
+            T2O_PROBE(3)
+            if (rank == 0 && warp < m) {
+                int op = OP_SKIP;
+#pragma unroll
+                for (int c = 0; c < SCORE_NW; ++c) op = warp == c ? ops[c] : op;
+                if (op != OP_SKIP) {
+                    float v = 0.0f;
+                    for (int t = lane; t < a.ntiles; t += 32) v += sh.part[warp][t];
+                    v = warp_sum(v);
+                    NMWarp w;
+                    unsigned char *base = nmreg + sh.nmoff[warp];
+                    // ctl sits behind (N+1) N + 3 N + N + 2 doubles and N + 1 ints: N is read through the leader's copy of it
+                    res_bind(w, base, sh.nmN[warp], nm, cbeg + warp, lane, sh.pend[warp], &sh.pop[warp]);
+                    nm_advance_bound(w, nm, v);
+                }
+            }
+            T2O_PROBE(4)
+#ifdef T2O_RES_PROBE
+            pc[5] += 1;
+#endif
+        }
+#ifdef T2O_RES_PROBE
+        // per-phase clocks of state 0's cluster: lane 0 of every warp of CTAs 0 and 1
+        if (probe && s == 0 && rank < 2 && lane == 0)
+            for (int i = 0; i < 6; ++i) probe[(rank * SCORE_NW + warp) * 6 + i] = (unsigned long long)pc[i];
+        if (probe && s == 0 && rank == 0 && tid < 12) probe[128 + tid] = g_nmp[tid];      // (running totals of the launch so far)
+#endif
+        // ---- leader: the fits' state back into the caller's arrays (finished, or stopped by max_rounds: the rounds can go on)
+        if (rank == 0 && warp < m && sh.nmoff[warp] >= 0) {
+            const int p = cbeg + warp, N = sh.nmN[warp];
+            NMWarp w;
+            res_bind(w, nmreg + sh.nmoff[warp], N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
+            double *gsim = nm.st.sim + (size_t)p * NM_ROWS * NM_MAXN, *gvec = nm.st.vec + (size_t)p * 3 * NM_MAXN;
+            if (lane < N) {
+                for (int r = 0; r <= N; ++r) gsim[r * NM_MAXN + lane] = w.sim[r * N + lane];
+                for (int r = 0; r < 3; ++r) gvec[r * NM_MAXN + lane] = w.vec[r * N + lane];
+            }
+            if (lane <= N) {
+                nm.st.fsim[(size_t)p * NM_ROWS + lane] = w.fsim[lane];
+                nm.st.perm[(size_t)p * NM_ROWS + lane] = w.perm[lane];
+            }
+            if (lane < 8) nm.st.ctl[(size_t)p * 8 + lane] = w.ctl[lane];
+            if (lane == 0) { nm.st.fxr[p] = *w.fxr; nm.cand_op[p] = sh.pop[warp]; }
+            if (lane < NM_MAXN) nm.cand_param[(size_t)p * NM_MAXN + lane] = sh.pend[warp][lane];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -384,6 +737,86 @@ int score_candidates(const float *states, int S, const float *targets, int T, co
     }
 #undef T2O_LAUNCH_SCORE
     T2O_CUDA_OK(cudaGetLastError());
+    return T2O_OK;
+}
+
+// Every fit of a planner step in one launch (see nm_resident_kernel).  T2O_ERR_UNSUPPORTED: the shape is not eligible (the
+// caller then runs the rounds itself).  fits_begin[s] .. fits_begin[s+1] are the fits of state s (at most 8); h_fits_begin and
+// h_fit_op are HOST copies of fits_begin and of the fits' operators: they size the shared memory of the launch.
+int nm_run_resident(const float *states, int S, const float *targets, int T, const int *state_target, const int *fits_begin,
+                    const int *cand_mask, const float *masks, int n_masks, int mask_ch,
+                    const t2o_nm_state *st, int P, float numel, float *cand_param, int *cand_op,
+                    const int *h_fits_begin, const int *h_fit_op,
+                    int H, int W, int L, int max_rounds, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!states || !targets || !fits_begin || !st || !cand_param || !cand_op || !h_fits_begin || !h_fit_op) return T2O_ERR_INVALID_ARG;
+    if (S < 1 || T < 1 || P < 1 || H < 1 || W < 1 || !(numel > 0.0f) || max_rounds < 1) return T2O_ERR_INVALID_ARG;
+    if (L < 1 || L > MAX_L) return T2O_ERR_UNSUPPORTED;
+    if (!ws || ws_bytes < COUNTER_REGION) return T2O_ERR_WORKSPACE;
+    const bool hm = masks != nullptr;
+    if (hm && (!cand_mask || n_masks < 1 || (mask_ch != 1 && mask_ch != 3))) return T2O_ERR_INVALID_ARG;
+    const bool aligned = ((uintptr_t)states % 16 == 0) && ((uintptr_t)targets % 16 == 0) && (!hm || (uintptr_t)masks % 16 == 0);
+    if (W % 4 != 0 || !aligned || get_encode_fn() == nullptr) return T2O_ERR_UNSUPPORTED;
+    // shared memory of a state's fits: operator tables and Nelder-Mead state, the largest need over the states
+    int tab_cap = 0, nm_cap = 0;
+    if (h_fits_begin[0] != 0 || h_fits_begin[S] != P) return T2O_ERR_INVALID_ARG;
+    for (int s = 0; s < S; ++s) {
+        const int b = h_fits_begin[s], e = h_fits_begin[s + 1];
+        if (e < b || e - b > SCORE_NW) return e < b ? T2O_ERR_INVALID_ARG : T2O_ERR_UNSUPPORTED;
+        int tf = 0, nb = 0;
+        for (int c = b; c < e; ++c) {
+            const int n = t2o_num_params(h_fit_op[c], L);
+            if (n < 1 || n > NM_MAXN) return T2O_ERR_INVALID_ARG;
+            tf += res_tab_floats(h_fit_op[c]);
+            nb += res_nm_bytes(n);
+        }
+        tab_cap = tf > tab_cap ? tf : tab_cap;
+        nm_cap = nb > nm_cap ? nb : nm_cap;
+    }
+    ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.states = states; a.targets = targets; a.cand_param = cand_param; a.state_target = state_target;
+    a.cand_begin = fits_begin; a.cand_op = cand_op;
+    a.masks = masks; a.cand_mask = hm ? cand_mask : nullptr; a.mask_ch = hm ? mask_ch : 0;
+    a.S = S; a.T = T; a.C = P; a.H = H; a.W = W; a.L = L;
+    a.TW = W < 128 ? W : 128;
+    a.TH = H < 32 ? H : 32;
+    a.tiles_x = (W + a.TW - 1) / a.TW;
+    a.ntiles = a.tiles_x * ((H + a.TH - 1) / a.TH);
+    a.nsplit = 1;
+    if (a.ntiles > RES_MAXT || a.TW + 8 > 256 || a.TH + 2 > 256) return T2O_ERR_UNSUPPORTED;
+    NMArgs nm;
+    memset(&nm, 0, sizeof(nm));
+    nm.st = *st; nm.P = P; nm.numel = numel; nm.cand_param = cand_param; nm.cand_op = cand_op;
+    nm.nonz_scale = 1 + 0.05; nm.zdelt = 0.00025; nm.xatol = 1e-4; nm.fatol = 1e-4;
+    const size_t s_floats = (size_t)3 * (a.TH + 2) * (a.TW + 8), t_floats = (size_t)3 * a.TH * a.TW;
+    const size_t smem = align_up(s_floats * 4, 128) + t_floats * 4 + (size_t)tab_cap * 4 + (size_t)nm_cap + 128;
+    auto kernel = hm ? nm_resident_kernel<true> : nm_resident_kernel<false>;
+    cudaFuncAttributes fa;
+    T2O_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+    if (smem + fa.sharedSizeBytes > (size_t)227 * 1024) return T2O_ERR_UNSUPPORTED;
+    CUtensorMap tms, tmt;
+    memset(&tms, 0, sizeof(tms)); memset(&tmt, 0, sizeof(tmt));
+    if (!make_map(&tms, states, S, H, W, a.TW + 8, a.TH + 2) || !make_map(&tmt, targets, T, H, W, a.TW, a.TH)) return T2O_ERR_NO_DEVICE;
+    // the work counter: the last word of the workspace's counter region (no entry point has 65 536 images or states); it is
+    // zero on entry and left at zero, like every other counter there
+    unsigned int *counter = (unsigned int *)ws + (COUNTER_REGION / sizeof(unsigned int) - 1);
+    T2O_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.ntiles; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(SCORE_NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)a.ntiles);
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) { (void)cudaGetLastError(); return T2O_ERR_UNSUPPORTED; }
+    if (nclusters > S) nclusters = S;
+    cfg.gridDim = dim3((unsigned)(nclusters * a.ntiles));
+    // (development builds with -DT2O_RES_PROBE leave per-phase clocks behind the counter region)
+    unsigned long long *probe = ws_bytes >= COUNTER_REGION + 4096 ? (unsigned long long *)((unsigned char *)ws + COUNTER_REGION) : nullptr;
+    T2O_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tms, tmt, a, nm, counter, max_rounds, tab_cap, nm_cap, probe));
+    T2O_CUDA_OK(cudaGetLastError());
+    T2O_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
     return T2O_OK;
 }
 

@@ -9,6 +9,7 @@ Mirrors the call pattern of the reference (file:line in /root/reference):
 All of them run the hand-written sm_100a kernels; there is no eager fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -443,7 +444,8 @@ class CandidateBatch:
         begin = torch.zeros(S + 1, dtype=torch.int64)
         if self.C:
             begin[1:] = torch.cumsum(torch.bincount(cs, minlength=S), 0)
-        self.begin = begin.to(torch.int32).to(device)
+        self.begin_host = begin.to(torch.int32).contiguous()          # (host copy: sizes the resident Nelder-Mead launch)
+        self.begin = self.begin_host.to(device)
         self.ops = torch.as_tensor(cand_op, dtype=torch.int32).to(device).contiguous()
         prm = torch.as_tensor(cand_param, dtype=torch.float32)
         if prm.dim() != 2 or prm.shape[0] != self.C or prm.shape[1] > _lib.MAX_OP_PARAMS:
@@ -545,7 +547,8 @@ class DeviceNelderMead:
             x0m[i, :n] = torch.as_tensor(v, dtype=torch.float64).flatten()[:n]
         self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target, masks, prob_mask)
         self.n_dims = torch.tensor(n_dims, dtype=torch.int32, device=dev)
-        self.prob_op = torch.as_tensor(prob_op, dtype=torch.int32).to(dev)
+        self.prob_op_host = torch.as_tensor(prob_op, dtype=torch.int32).cpu().contiguous()
+        self.prob_op = self.prob_op_host.to(dev)
         self.x0 = x0m.to(dev)
         f64 = dict(dtype=torch.float64, device=dev)
         self.sim = torch.empty(P, self.ROWS, _lib.MAX_OP_PARAMS, **f64)
@@ -586,7 +589,28 @@ class DeviceNelderMead:
         """Number of unfinished fits (synchronises)."""
         return int((self.ctl[:, 1] != 6).sum().item())
 
+    def run_resident(self, max_rounds=None):
+        """All rounds in one launch (t2o_nm_run_resident): the states and the fits' simplices stay in shared memory for the
+        life of the fits.  -> True, or False where the shape is not eligible (the caller runs the rounds)."""
+        limit = 200 * _lib.MAX_OP_PARAMS + 8 if max_rounds is None else max_rounds
+        lib, cb = _lib.lib(), self.cb
+        ws = _lib.workspace(self.dev, max(lib.t2o_score_workspace_bytes(self.S, self.P, self.H, self.W), 1 << 18))
+        m = cb.masks
+        st = lib.t2o_nm_run_resident(_lib.ptr(self.states), self.S, _lib.ptr(self.targets), self.targets.shape[0], _lib.ptr(cb.state_target),
+                                     _lib.ptr(cb.begin), _lib.ptr(cb.cand_mask), _lib.ptr(m), 0 if m is None else m.shape[0],
+                                     0 if m is None else m.shape[1], ctypes.byref(self.state), self.P, ctypes.c_float(self.numel),
+                                     _lib.ptr(cb.prm), _lib.ptr(cb.ops), cb.begin_host.data_ptr(), self.prob_op_host.data_ptr(),
+                                     self.H, self.W, self.L, limit, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.dev))
+        if st == 2:                                                 # T2O_ERR_UNSUPPORTED
+            return False
+        _lib.check(st)
+        self.rounds += limit
+        return True
+
     def run(self, check_every=64, use_graph=True, max_rounds=None):
+        if os.environ.get('T2O_NM_RESIDENT', '1') != '0' and self.rounds == 0 and self.run_resident(max_rounds):
+            if max_rounds is not None or self.active() == 0:
+                return self.result()
         limit = 200 * _lib.MAX_OP_PARAMS + 8 if max_rounds is None else max_rounds
         for _ in range(check_every):                               # eager warm-up (also sets the kernels' attributes)
             self._round()

@@ -4,6 +4,8 @@ driven by the same scorer (t2o_score_candidates), so equal function values must 
 final vertices, function values, iteration and evaluation counts are compared EXACTLY.  (The coroutine runs with
 stable=True: exact ties between fp32 function values are common, and scipy's tie order is numpy's unstable-quicksort
 implementation detail, which the device's stable rank sort does not imitate.)"""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -123,3 +125,57 @@ def test_topk_min_is_the_stable_argsort_prefix(T):
             assert all(i == -1 for i in idx[s, len(order):]) and np.all(np.isinf(val[s, len(order):]))
             got = val[s, :len(order)]
             assert np.array_equal(np.isnan(got), np.isnan(v[order])) and np.array_equal(got[~np.isnan(got)], v[order][~np.isnan(v[order])])
+
+
+@pytest.mark.parametrize('S,H,W,masked', [(5, 128, 128, False), (80, 128, 128, False), (6, 64, 96, True), (4, 32, 32, False),
+                                          (3, 40, 52, False), (2, 256, 256, False)])
+def test_resident_nelder_mead_equals_the_rounds_exactly(T, S, H, W, masked, monkeypatch):
+    """t2o_nm_run_resident (a cluster of CTAs keeps each state in shared memory for the life of its fits) against rounds of
+    t2o_score_candidates + t2o_nm_advance: fitted parameters, function values, iteration and evaluation counts identical,
+    with one to six fits per state, several tiles per image, ragged tiles and masks (256 x 256 has 16 tiles: the resident
+    path declines and the rounds run)."""
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    states, targets = _pairs(S, H, W, 31 + S)
+    ops = [0, 1, 2, 6] if S > 10 else GLOBAL_OPS
+    problems = [(s, op) for s in range(S) for op in ops[:1 + (s * 5) % len(ops)]]
+    kw = {}
+    if masked:
+        g = torch.Generator().manual_seed(3)
+        kw = dict(masks=(torch.rand(2, 1, H, W, generator=g) > 0.4).float().cuda(), prob_mask=[(i % 3) - 1 for i in range(len(problems))])
+    res = []
+    for env in ('0', '1'):
+        monkeypatch.setenv('T2O_NM_RESIDENT', env)
+        res.append(planner.fit_params_nelder_mead(states, targets, problems, ex, state_target=list(range(S)), **kw))
+    for (s, op), r0, r1 in zip(problems, *res):
+        assert r0.nfev == r1.nfev and r0.nit == r1.nit and r0.status == r1.status, (s, op, r0.nfev, r1.nfev)
+        assert np.array_equal(np.asarray(r0.x), np.asarray(r1.x)) and r0.fun == r1.fun, (s, op)
+    assert max(r.nfev for r in res[0]) >= (100 if S <= 10 else 20)
+
+
+def test_resident_nelder_mead_can_stop_and_go_on_in_rounds(T):
+    """max_rounds stops the resident launch early: the fits' state is written back, a second resident launch or the rounds carry
+    on from there, and the results equal an uninterrupted run exactly."""
+    from t2onet_b200 import planner, functional as TF
+    ex = T.Executor(T.default_options()).cuda()
+    S = 6
+    states, targets = _pairs(S, 128, 128, 77)
+    probs = [(s, op) for s in range(S) for op in GLOBAL_OPS]
+
+    def make():
+        return TF.DeviceNelderMead(states, targets, [p[0] for p in probs], [p[1] for p in probs],
+                                   [planner._param0(p[1], ex) for p in probs], state_target=list(range(S)))
+    ref = make()
+    assert ref.run_resident()
+    r0 = ref.result()
+    assert bool(r0['done'].all())
+    a = make()
+    assert a.run_resident(37) and a.active() > 0
+    assert a.run_resident(21)
+    os.environ['T2O_NM_RESIDENT'] = '0'
+    try:
+        r1 = a.run()
+    finally:
+        os.environ.pop('T2O_NM_RESIDENT', None)
+    for k in ('x', 'fun', 'nit', 'nfev', 'status'):
+        assert torch.equal(r0[k], r1[k]), k
