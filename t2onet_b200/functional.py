@@ -542,9 +542,11 @@ class DeviceNelderMead:
         n_dims = [num_params(int(o), curve_steps) for o in prob_op]
         if any(n < 1 or n > _lib.MAX_OP_PARAMS for n in n_dims):
             raise _lib.T2OError('Nelder-Mead fits need operators with 1..24 parameters')
-        x0m = torch.zeros(P, _lib.MAX_OP_PARAMS, dtype=torch.float64)
+        import numpy as np
+        x0h = np.zeros((P, _lib.MAX_OP_PARAMS), dtype=np.float64)
         for i, (v, n) in enumerate(zip(x0, n_dims)):
-            x0m[i, :n] = torch.as_tensor(v, dtype=torch.float64).flatten()[:n]
+            x0h[i, :n] = (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float64)).reshape(-1)[:n]
+        x0m = torch.from_numpy(x0h)
         self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target, masks, prob_mask)
         self.n_dims = torch.tensor(n_dims, dtype=torch.int32, device=dev)
         self.prob_op_host = torch.as_tensor(prob_op, dtype=torch.int32).cpu().contiguous()

@@ -18,6 +18,7 @@ Only the 'L1' distance is implemented: the discriminator branches of the referen
 names (utils/beam_search.py:42,55) and are dead code.
 """
 import os
+import threading
 import random
 
 import numpy as np
@@ -218,7 +219,7 @@ def get_param(I0, I1, txt, operation, executor, discriminator, dist_type, optimi
     return get_param_gd(I0, I1, txt, None, param0, executor, discriminator, operation, dist_type, optimizer)
 
 
-def _score_outputs(I_list, ops, params, I_gt_list, executor, mask_list=None):
+def _score_outputs(I_list, ops, params, I_gt_list, executor, mask_list=None, gather=None):
     """I_out and dist for every fitted candidate of a step (utils/beam_search.py:230,237): one per-row launch
     (every row its own state, operator, parameters, target and -- GIER -- mask), one device->host read of the distances."""
     if not I_list:
@@ -226,12 +227,19 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor, mask_list=None):
     L = getattr(executor.opt, 'curve_steps', 8)
     dev = I_list[0].device
     numel = float(I_gt_list[0].numel())
+    dev = torch.device(dev)
     outs, vals = [], []
     CH = 1024                                                       # rows per launch (bounds the temporaries)
     for c0 in range(0, len(I_list), CH):
         Is, Gs = I_list[c0:c0 + CH], I_gt_list[c0:c0 + CH]
-        img = torch.cat(Is, 0).contiguous()
-        tgt = torch.cat(Gs, 0).contiguous()
+        if gather is None:
+            img = torch.cat(Is, 0).contiguous()
+            tgt = torch.cat(Gs, 0).contiguous()
+        else:
+            # the rows are states[s_idx] / targets[pair]: two gathers instead of concatenating thousands of slices
+            st_all, s_idx, gt_all, p_idx = gather
+            img = st_all.index_select(0, torch.as_tensor(s_idx[c0:c0 + CH], dtype=torch.int64).to(dev))
+            tgt = gt_all.index_select(0, torch.as_tensor(p_idx[c0:c0 + CH], dtype=torch.int64).to(dev))
         prm = np.zeros((len(Is), 24), dtype=np.float32)
         for r, p in enumerate(params[c0:c0 + CH]):
             if isinstance(p, torch.Tensor):
@@ -373,12 +381,13 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
                             if oi < 0 or oi == operation:
                                 problems.append((s_idx, operation, m, j, k))
         # -- fit all of them (utils/beam_search.py:229)
+        states_cat = torch.cat(states, 0).contiguous() if problems else None
         if shard_fits and problems:
-            params, nfevs = _fit_sharded(torch.cat(states, 0).contiguous(), I_gt, problems, executor, state_pair, counter,
+            params, nfevs = _fit_sharded(states_cat, I_gt, problems, executor, state_pair, counter,
                                          numel, group)
         elif optimizer == 'Nelder-Mead' and problems:
             use_masks = masks is not None and masks_dev is not None
-            fits = fit_params_nelder_mead(torch.cat(states, 0).contiguous(), I_gt, [(s, op) for s, op, _, _, _ in problems],
+            fits = fit_params_nelder_mead(states_cat, I_gt, [(s, op) for s, op, _, _, _ in problems],
                                           executor, state_target=state_pair, counter=counter, numel=numel,
                                           masks=masks_dev if use_masks else None,
                                           prob_mask=[mask_gidx[m][k] for _, _, m, _, k in problems] if use_masks else None)
@@ -394,7 +403,10 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
         if masks is not None:
             mask_list = [None if mask_gidx[m][k] < 0 else masks_dev[mask_gidx[m][k]:mask_gidx[m][k] + 1] for _, _, m, _, k in problems]
         outs, dists = _score_outputs([states[s] for s, _, _, _, _ in problems], [op for _, op, _, _, _ in problems], params,
-                                     [I_gt[m:m + 1] for _, _, m, _, _ in problems], executor, mask_list)
+                                     [I_gt[m:m + 1] for _, _, m, _, _ in problems], executor, mask_list,
+                                     gather=None if not problems else (states_cat, [s for s, _, _, _, _ in problems],
+                                                                       I_gt if I_gt.dtype == torch.float32 else I_gt.float(),
+                                                                       [m for _, _, m, _, _ in problems]))
         # -- the reference's bookkeeping, pair by pair (utils/beam_search.py:239-259)
         minima = _step_minima_sharded(dists, problems, live, I_0.device, group) if shard_fits and problems else None
         by_pair = {m: [] for m in live}
@@ -455,13 +467,73 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
             S['sequences'], S['I_buff'] = seqs, [own(idx) for idx in buf_idx]
             if no_update_flag or finish_flag:
                 S['alive'] = False
+    # the reference returns CPU images (:236): every distinct kept image once, in a few large device -> host copies
+    # (sequences of a pair share their prefixes; ~1 400 separate .cpu() calls cost a 64-pair search 0.14 s)
+    uniq, order = {}, []
+    for m in range(M):
+        for seq in st[m]['sequences']:
+            for act in seq[0]:
+                if id(act[-1]) not in uniq:
+                    uniq[id(act[-1])] = len(order)
+                    order.append(act[-1])
+    host = []
+    CH = 512
+    for c0 in range(0, len(order), CH):
+        host.append(torch.cat(order[c0:c0 + CH], 0).cpu())
     results = []
     for m in range(M):
         seqs = st[m]['sequences']
         actions = [[act[:-1] for act in seq[0]] for seq in seqs]
-        Is = [[act[-1].cpu() for act in seq[0]] for seq in seqs]      # the reference returns CPU images (:236)
+        Is = [[host[uniq[id(act[-1])] // CH][uniq[id(act[-1])] % CH:uniq[id(act[-1])] % CH + 1] for act in seq[0]] for seq in seqs]
         results.append((actions, Is))
     return results
+
+
+def beam_search_pipelined(batches, executor, beam_size, operations, operation_names, max_step, err, workers=2, counter=None,
+                          **kwargs):
+    """`beam_search_batch` over a stream of batches -- the dataset loop of preprocess/gen_greedy_seqs_FiveK.py:44-64 -- with
+    `workers` batches in flight: each runs on its own thread and CUDA stream, so the host bookkeeping of one batch (selection,
+    records, result copies: about half of a batch's wall time) overlaps the device fits of another, and the resident
+    Nelder-Mead launches of two batches fill each other's tails.  Batches are independent, so every result equals the
+    sequential call's.  batches: an iterable of (I_0, I_gt) CUDA tensor pairs (consumed at most `workers` ahead);
+    returns the list of beam_search_batch results in order.  (Not for the eps-greedy variant, whose random draws are ordered.)"""
+    import concurrent.futures as cf
+    assert kwargs.get('_variant', 'default') != 'eps_greedy', 'eps-greedy draws from one ordered random stream'
+    if workers <= 1:
+        return [beam_search_batch(a, b, executor, beam_size, operations, operation_names, max_step, err, counter=counter, **kwargs)
+                for a, b in batches]
+    results, counts, pending = {}, {}, []
+    local = threading.local()
+
+    def work(k, I_0, I_gt, ready):
+        dev = I_0.device
+        torch.cuda.set_device(dev)                                  # (a new thread starts on device 0)
+        if not hasattr(local, 'stream'):
+            local.stream = torch.cuda.Stream(dev)
+        cnt = [0]
+        with torch.cuda.stream(local.stream):
+            local.stream.wait_event(ready)                          # the batch was produced on the caller's stream
+            res = beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, counter=cnt, **kwargs)
+            local.stream.synchronize()
+        I_0.record_stream(local.stream)
+        I_gt.record_stream(local.stream)
+        return k, res, cnt[0]
+
+    with cf.ThreadPoolExecutor(max_workers=workers) as pool:
+        def drain(fut):
+            k, res, c = fut.result()
+            results[k], counts[k] = res, c
+        for k, (I_0, I_gt) in enumerate(batches):
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(I_0.device))
+            pending.append(pool.submit(work, k, I_0, I_gt, ready))
+            if len(pending) >= workers + 1:
+                drain(pending.pop(0))
+        for fut in pending:
+            drain(fut)
+    if counter is not None:
+        counter[0] += sum(counts.values())
+    return [results[k] for k in range(len(results))]
 
 
 def beam_search(I_0, I_gt, txt, executor, discriminator, beam_size, operations, operation_names, max_step, err,

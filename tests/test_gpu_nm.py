@@ -76,6 +76,24 @@ def test_beam_search_batch_equals_single_pairs(T):
                 assert not x.is_cuda and torch.equal(x, y)
 
 
+def test_beam_search_pipelined_equals_sequential_batches(T):
+    """planner.beam_search_pipelined (batches in flight on two threads / CUDA streams) == one beam_search_batch per batch:
+    same sequences, parameters, distances, images and evaluation count."""
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    batches = [_pairs(3 + (k % 2), 32, 32, 40 + k) for k in range(5)]
+    c_seq, c_pipe = [0], [0]
+    seq = [planner.beam_search_batch(a, b, ex, 2, [0, 1, 3, 6], O.ACTION_NAMES, 2, 1e-3, counter=c_seq) for a, b in batches]
+    pipe = planner.beam_search_pipelined(iter(batches), ex, 2, [0, 1, 3, 6], O.ACTION_NAMES, 2, 1e-3, workers=2, counter=c_pipe)
+    assert c_seq[0] == c_pipe[0] and len(seq) == len(pipe)
+    for rs, rp in zip(seq, pipe):
+        assert len(rs) == len(rp)
+        for (acts, Is), (pacts, pIs) in zip(rs, rp):
+            assert acts == pacts
+            for xs, ys in zip(Is, pIs):
+                assert len(xs) == len(ys) and all(torch.equal(x, y) for x, y in zip(xs, ys))
+
+
 def test_entry_points_share_one_workspace_across_batch_sizes(T):
     """include/t2o.h: one workspace serves all entry points in turn, whatever the batch sizes -- the arrival counters
     live in a fixed region that no call's partial sums can reach (a scorer launch with few states followed by a
