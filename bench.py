@@ -711,25 +711,27 @@ def fused_scale(B, H, W, dev):
     return torch.full((B,), 1.0 / (B * 3 * H * W), device=dev, dtype=torch.float32)
 
 
-PLANNER_M = 64
+PLANNER_M = 256           # pairs per GPU: four lock-step batches of 64, two in flight (planner.beam_search_pipelined)
+PLANNER_BATCH = 64
 
 
 def planner_e2e_run(dev, seed, reps=3):
-    """beam_search_batch (= the reference's beam_search on every pair, utils/beam_search.py:196-264) over 64 synthetic pairs
-    of 3x128x128, beam 8, the six global operators, max 6 steps, Nelder-Mead fits resident on the device (BASELINE
-    config 3's shape; 1000 pairs = 16 such batches).  -> (best wall-clock seconds of reps - 1 timed repetitions,
+    """beam_search_batch (= the reference's beam_search on every pair, utils/beam_search.py:196-264) over 256 synthetic pairs
+    of 3x128x128 in lock-step batches of 64, two in flight, beam 8, the six global operators, max 6 steps, Nelder-Mead fits
+    resident on the device (BASELINE config 3's shape; its 1000 pairs are 16 such batches: --workload c3).  -> (best wall-clock seconds of reps - 1 timed repetitions,
     candidates scored, mean steps of the top sequences); the first repetition warms the kernels up."""
     import t2onet_b200 as T
     from t2onet_b200 import planner
     names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
     exe = T.Executor(T.default_options()).to(dev)
     img, tgt, _ = make_batch(PLANNER_M, 128, 128, seed, dev)
+    chunks = [(img[c:c + PLANNER_BATCH], tgt[c:c + PLANNER_BATCH]) for c in range(0, PLANNER_M, PLANNER_BATCH)]
     best = None
     for rep in range(reps):
         cnt = [0]
         torch.cuda.synchronize()
         t0 = time.time()
-        res = planner.beam_search_batch(img, tgt, exe, 8, CHAIN, names, 6, 1e-2, counter=cnt)
+        res = sum(planner.beam_search_pipelined(chunks, exe, 8, CHAIN, names, 6, 1e-2, workers=2, counter=cnt), [])
         torch.cuda.synchronize()
         dt = time.time() - t0
         if rep > 0 and (best is None or dt < best[0]):
@@ -780,7 +782,7 @@ def planner_e2e_line(seconds, candidates, mean_steps, n_gpus):
     return {'workload': '%d pairs of 3x128x128 per GPU, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, Nelder-Mead' % PLANNER_M,
             'n_gpus': n_gpus, 'seconds': seconds, 'pairs_per_s': pairs / seconds, 'candidates': candidates,
             'candidates_per_s': candidates / seconds, 'mean_steps': mean_steps,
-            'how': 'wall clock around beam_search_batch (host bookkeeping and result copies included), best of 2; N > 1: pairs sharded '
+            'how': 'wall clock around beam_search_pipelined (lock-step batches of 64 pairs, two in flight; host bookkeeping and result copies included), best of 2; N > 1: pairs sharded '
                    'by image, no communication during the search, slowest rank\'s time, candidates summed over ranks'}
 
 

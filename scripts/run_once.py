@@ -1,4 +1,4 @@
-"""Tiny drivers for profiler captures: python scripts/run_once.py {fwd_c4|bwd_c4|score|c2}"""
+"""Tiny drivers for profiler captures: python scripts/run_once.py {fwd_c4|bwd_c4|score|c2|resident}"""
 import os
 import sys
 
@@ -44,3 +44,19 @@ elif what == 'score':
         TF.score_prepared(states, targets, cb)
 torch.cuda.synchronize()
 print('done', what)
+
+if what == 'resident':
+    # every fit of a planner step in one launch: 132 states x the six FiveK operators (two waves of clusters)
+    import t2onet_b200 as T
+    from t2onet_b200 import planner
+    ex = T.Executor(T.default_options()).cuda()
+    S = 132
+    img, tgt, _ = bench.make_batch(S, 128, 128, 3015, dev)
+    probs = [(s, o) for s in range(S) for o in bench.CHAIN]
+    nm = TF.DeviceNelderMead(img, tgt, [p[0] for p in probs], [p[1] for p in probs], [planner._param0(p[1], ex) for p in probs],
+                             state_target=list(range(S)))
+    assert nm.run_resident()
+    torch.cuda.synchronize()
+    r = nm.result()
+    print('evaluations', int(r['nfev'].sum()), 'done', bool(r['done'].all()))
+torch.cuda.synchronize()
