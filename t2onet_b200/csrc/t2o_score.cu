@@ -70,9 +70,21 @@ __device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t valu
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(remote_addr), "r"(value), "r"(remote_bar) : "memory");
 }
+// wait for a phase with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 ms pass) instead of
+// re-issuing try_wait -- without the hint the waiting warps' polling was a quarter of all instructions the resident kernel
+// issued (ncu), taken from the arithmetic of the CTA next to them
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity) {
     bool done = false;
-    for (int it = 0; it < (1 << 24) && !done; ++it) done = mbar_try_wait(bar, parity);
+    for (int it = 0; it < (1 << 13) && !done; ++it) done = mbar_try_wait_sleep(bar, parity);
     if (!done) __trap();                                         // a broken protocol must fail loudly, not hang the GPU
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -516,6 +528,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
 #else
 #define T2O_PROBE(i)
 #endif
+        bool mylive = true;                                      // warp c < m: fit c has not finished (as far as this warp has seen)
         for (int round = 0; round < max_rounds; ++round) {
 #ifdef T2O_RES_PROBE
             pt = clock64();
@@ -529,31 +542,26 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                         st_async_u32(mapa_u32(lane < NM_MAXN ? (const void *)&sh.cprm[warp][lane] : (const void *)&sh.cops[warp], r), v,
                                      mapa_u32(&sh.pbar, r));
             }
+            // (only the warps that build a table wait for the vertices; the others go on to the barrier behind the tables, which
+            // costs no issue slots)
             if (tid == 0) mbar_expect_tx(&sh.pbar, (uint32_t)m * 4u * (NM_MAXN + 1));
-            mbar_wait_or_trap(&sh.pbar, pphase);
+            if (warp < m && mylive) mbar_wait_or_trap(&sh.pbar, pphase);
             pphase ^= 1u;
             T2O_PROBE(0)
-            int ops[SCORE_NW], toff[SCORE_NW];
-            bool any = false;
-            {
-                int o = 0;
-#pragma unroll
-                for (int c = 0; c < SCORE_NW; ++c) {
-                    ops[c] = c < m ? sh.cops[c] : OP_SKIP;
-                    toff[c] = o;
-                    o += c < m ? res_tab_floats(sh.cops0[c]) : 0;
-                    any |= ops[c] != OP_SKIP;
+            if (warp < m) {
+                int to = 0;
+                for (int c = 0; c < warp; ++c) to += res_tab_floats(sh.cops0[c]);
+                if (lane == 0) sh.toff[warp] = to;
+                if (mylive) {
+                    const int op = sh.cops[warp];
+                    mylive = op != OP_SKIP;
+                    if (mylive) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + to);
                 }
             }
+            __syncthreads();                                     // tables built <=> this round's vertices have arrived
+            bool any = false;
+            for (int c = 0; c < m; ++c) any |= sh.cops[c] != OP_SKIP;
             if (!any) break;
-            if (warp < m) {
-                int op = OP_SKIP, to = 0;
-#pragma unroll
-                for (int c = 0; c < SCORE_NW; ++c) { op = warp == c ? ops[c] : op; to = warp == c ? toff[c] : to; }
-                if (lane == 0) sh.toff[warp] = to;
-                if (op != OP_SKIP) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + to);
-            }
-            __syncthreads();
             T2O_PROBE(1)
             // fit by fit, all warps share the tile (score_kernel's cooperative path: thread tid takes groups tid, tid + 256, ...)
 #pragma unroll 1
@@ -585,15 +593,14 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             }
             if (rank == 0) {
                 if (tid == 0) mbar_expect_tx(&sh.sbar, (uint32_t)(a.ntiles * m) * 4u);
-                mbar_wait_or_trap(&sh.sbar, sphase);
+                // every publishing warp waits, live fit or not: the CTAs send their partials after they have consumed this round's
+                // vertices, so nothing of the next round can reach an mbarrier phase that is still open
+                if (warp < m) mbar_wait_or_trap(&sh.sbar, sphase);
                 sphase ^= 1u;
             }
             T2O_PROBE(3)
             if (rank == 0 && warp < m) {
-                int op = OP_SKIP;
-#pragma unroll
-                for (int c = 0; c < SCORE_NW; ++c) op = warp == c ? ops[c] : op;
-                if (op != OP_SKIP) {
+                if (mylive) {
                     float v = 0.0f;
                     for (int t = lane; t < a.ntiles; t += 32) v += sh.part[warp][t];
                     v = warp_sum(v);
