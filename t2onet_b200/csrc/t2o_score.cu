@@ -82,6 +82,15 @@ __device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t *bar, uint32_t pari
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
+// the same hand-over inside ONE CTA (an image of a single tile: a cluster of one block has no distributed shared memory to
+// address): a plain store, then a CTA fence, then the transaction bytes completed on the local mbarrier -- a release pattern
+// that the waiters' try_wait (acquire) pairs with.  (compute-sanitizer's racecheck does not model mbarrier ordering and
+// reports these stores against the waiters' reads; memcheck is clean.)
+__device__ __forceinline__ void st_local_u32(void *dst, uint32_t value, uint64_t *bar) {
+    *reinterpret_cast<volatile uint32_t *>(dst) = value;
+    __threadfence_block();
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(4u) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity) {
     bool done = false;
     for (int it = 0; it < (1 << 13) && !done; ++it) done = mbar_try_wait_sleep(bar, parity);
@@ -450,13 +459,16 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t bar_phase = 0, pphase = 0, sphase = 0;           // (the first cluster barrier below orders the initialisation)
+    uint32_t bar_phase = 0, pphase = 0, sphase = 0;
+    const bool single = a.ntiles == 1;
+    // every CTA of the cluster is running (and its mbarriers are initialised) before anyone writes into its shared memory
+    cluster.sync();
 
     for (;;) {
         // ---- the cluster's next state
         if (rank == 0 && tid == 0) {
             const int nxt = (int)atomicAdd(work_counter, 1u);
-            for (int r = 0; r < a.ntiles; ++r) cluster.map_shared_rank(&sh, r)->next_state = nxt;
+            for (int r = 0; r < a.ntiles; ++r) (a.ntiles == 1 ? &sh : cluster.map_shared_rank(&sh, r))->next_state = nxt;
         }
         cluster.sync();
         const int s = sh.next_state;
@@ -510,7 +522,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             if (lane == 0) { sh.nmoff[warp] = op != OP_SKIP ? off : -1; sh.nmN[warp] = N; sh.pop[warp] = op; }
             if (lane < NM_MAXN) sh.pend[warp][lane] = prm;
             for (int r = 0; r < a.ntiles; ++r) {
-                ResidentShared *dst = cluster.map_shared_rank(&sh, r);
+                ResidentShared *dst = single ? &sh : cluster.map_shared_rank(&sh, r);
                 if (lane == 0) { dst->cops0[warp] = op; dst->cmask[warp] = mi; }
             }
         }
@@ -537,10 +549,12 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             if (rank == 0 && warp < m) {
                 __syncwarp();
                 const uint32_t v = lane < NM_MAXN ? __float_as_uint(sh.pend[warp][lane]) : (uint32_t)sh.pop[warp];
-                if (lane <= NM_MAXN)
-                    for (int r = 0; r < a.ntiles; ++r)
-                        st_async_u32(mapa_u32(lane < NM_MAXN ? (const void *)&sh.cprm[warp][lane] : (const void *)&sh.cops[warp], r), v,
-                                     mapa_u32(&sh.pbar, r));
+                if (lane <= NM_MAXN) {
+                    void *dst = lane < NM_MAXN ? (void *)&sh.cprm[warp][lane] : (void *)&sh.cops[warp];
+                    if (single) st_local_u32(dst, v, &sh.pbar);
+                    else
+                        for (int r = 0; r < a.ntiles; ++r) st_async_u32(mapa_u32(dst, r), v, mapa_u32(&sh.pbar, r));
+                }
             }
             // (only the warps that build a table wait for the vertices; the others go on to the barrier behind the tables, which
             // costs no issue slots)
@@ -589,7 +603,9 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                 float v = 0.0f;
 #pragma unroll
                 for (int w = 0; w < SCORE_NW; ++w) v += sh.wsum[tid][w];
-                st_async_u32(mapa_u32(&sh.part[tid][rank], 0), __float_as_uint(sh.cops[tid] != OP_SKIP ? v : 0.0f), mapa_u32(&sh.sbar, 0));
+                const uint32_t pv = __float_as_uint(sh.cops[tid] != OP_SKIP ? v : 0.0f);
+                if (single) st_local_u32(&sh.part[tid][0], pv, &sh.sbar);
+                else st_async_u32(mapa_u32(&sh.part[tid][rank], 0), pv, mapa_u32(&sh.sbar, 0));
             }
             if (rank == 0) {
                 if (tid == 0) mbar_expect_tx(&sh.sbar, (uint32_t)(a.ntiles * m) * 4u);
@@ -624,6 +640,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
 #endif
         // ---- leader: the fits' state back into the caller's arrays (finished, or stopped by max_rounds: the rounds can go on)
         if (rank == 0 && warp < m && sh.nmoff[warp] >= 0) {
+            __syncwarp();                                        // (the lanes read what other lanes of the warp wrote in the last step)
             const int p = cbeg + warp, N = sh.nmN[warp];
             NMWarp w;
             res_bind(w, nmreg + sh.nmoff[warp], N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
