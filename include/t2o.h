@@ -266,7 +266,7 @@ int t2o_nm_advance(const t2o_nm_state *state /*host struct of device pointers*/,
  * t2o_score_candidates); fit_mask / masks as in t2o_score_candidates_masked (NULL: none); host_fits_begin / host_fit_op are
  * HOST copies of fits_begin and of the fits' operators (they size the launch's shared memory); max_rounds bounds the
  * evaluations per fit (200 * 24 + 8 covers scipy's maxfev); fits it leaves unfinished can go on, here or in rounds.
- * Returns T2O_ERR_UNSUPPORTED where the shape is not eligible (more than 8 tiles of 32 x 128 pixels per image, more than 8
+ * Returns T2O_ERR_UNSUPPORTED where the shape is not eligible (more than 16 tiles of 32 x 128 pixels per image, more than 8
  * fits per state, W % 4 != 0, no TMA, fits too large for the shared memory): run the rounds instead.  workspace: >= 256 KiB.
  */
 int t2o_nm_run_resident(const float *states, int S, const float *targets, int T, const int32_t *state_target,

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
 // same groups per thread in the same order, the same warp / tile reduction order, the same Nelder-Mead code --
 // tests/test_gpu_nm.py compares the two exactly.
 namespace cg = cooperative_groups;
-constexpr int RES_MAXT = 8;      // tiles per state = cluster size (portable limit)
+constexpr int RES_MAXT = 16;     // tiles per state = cluster size (8 is the portable limit; 9 .. 16 -- a 256 x 256 image -- are opted into)
 
 struct ResidentShared {
     float wsum[SCORE_NW][SCORE_NW];
@@ -825,6 +825,10 @@ int nm_run_resident(const float *states, int S, const float *targets, int T, con
     // zero on entry and left at zero, like every other counter there
     unsigned int *counter = (unsigned int *)ws + (COUNTER_REGION / sizeof(unsigned int) - 1);
     T2O_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.ntiles > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return T2O_ERR_UNSUPPORTED;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];

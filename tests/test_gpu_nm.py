@@ -146,12 +146,12 @@ def test_topk_min_is_the_stable_argsort_prefix(T):
 
 
 @pytest.mark.parametrize('S,H,W,masked', [(5, 128, 128, False), (80, 128, 128, False), (6, 64, 96, True), (4, 32, 32, False),
-                                          (3, 40, 52, False), (2, 256, 256, False)])
+                                          (3, 40, 52, False), (2, 256, 256, False), (2, 264, 320, True)])
 def test_resident_nelder_mead_equals_the_rounds_exactly(T, S, H, W, masked, monkeypatch):
     """t2o_nm_run_resident (a cluster of CTAs keeps each state in shared memory for the life of its fits) against rounds of
     t2o_score_candidates + t2o_nm_advance: fitted parameters, function values, iteration and evaluation counts identical,
-    with one to six fits per state, several tiles per image, ragged tiles and masks (256 x 256 has 16 tiles: the resident
-    path declines and the rounds run)."""
+    with one to six fits per state, several tiles per image, ragged tiles and masks (256 x 256 has 16 tiles: a cluster of 16;
+    264 x 320 has 27: the resident path declines and the rounds run)."""
     from t2onet_b200 import planner
     ex = T.Executor(T.default_options()).cuda()
     states, targets = _pairs(S, H, W, 31 + S)
