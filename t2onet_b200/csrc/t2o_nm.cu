@@ -33,10 +33,8 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NMArgs 
     if constexpr (START) {
         NMWarp w;
         nm_bind(w, a, p, lane);
-        double *fsim = a.st.fsim + (size_t)p * NM_ROWS;
-        int *perm = a.st.perm + (size_t)p * NM_ROWS;
         const int N = a.n_dims[p];
-        w.N = N; w.maxfun = 200 * N; w.fcalls = 0; w.iters = 0;
+        w.N = N; w.maxfun = 200 * N; w.fcalls = 0; w.iters = 0; w.status = 0; w.fxrv = 0.0;
         // sim[0] = x0; sim[k+1] = x0 with coordinate k stepped: (1 + nonzdelt) * y[k] if y[k] != 0 else zdelt
         const double x0d = lane < N ? a.x0[(size_t)p * NM_MAXN + lane] : 0.0;
         for (int k = 0; k <= N; ++k) {
@@ -46,14 +44,12 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NMArgs 
         }
         w.f = CUDART_INF; w.row = lane;
         if (lane == 0) {
-            w.ctl[CTL_N] = N; w.ctl[CTL_STATUS] = 0; w.ctl[CTL_OP] = a.prob_op[p]; w.ctl[CTL_RES] = 0;
+            w.ctl[CTL_N] = N; w.ctl[CTL_OP] = a.prob_op[p]; w.ctl[CTL_RES] = 0;
             *w.cop = a.prob_op[p];
         }
         __syncwarp();
         nm_propose(w, x0d, NM_INIT, 0);
-        __syncwarp();
-        if (lane <= w.N) { fsim[lane] = w.f; perm[lane] = w.row; }
-        if (lane == 0) { w.ctl[CTL_FCALLS] = w.fcalls; w.ctl[CTL_ITERS] = w.iters; }
+        nm_store(w);
     } else {
         nm_advance_fit(a, p, lane, a.l1_sum[p]);
     }

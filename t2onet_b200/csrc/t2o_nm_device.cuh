@@ -53,6 +53,10 @@ struct NMWarp {
     double f;
     int row;
     int fcalls, iters, maxfun;
+    // the step's control state (uniform over the lanes): what the pending vertex is (phase, k), scipy's status once finished,
+    // the value of the reflected vertex -- in registers between nm_load and nm_store
+    int phase, k, status;
+    double fxrv;
 };
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -136,7 +140,7 @@ __device__ __forceinline__ bool nm_propose(NMWarp &w, double x, int phase, int k
         w.cparam[w.lane] = w.lane < w.N ? (float)x : 0.0f;      // float64 -> float32, as torch.tensor([param], dtype=torch.float)
         if (w.lane < w.N) w.vec[VEC_PEND * w.ld + w.lane] = x;
     }
-    if (w.lane == 0) { w.ctl[CTL_PHASE] = phase; w.ctl[CTL_K] = k; }
+    w.phase = phase; w.k = k;
     return true;
 }
 
@@ -144,10 +148,10 @@ __device__ __forceinline__ void nm_finish(NMWarp &w, const NMArgs &a) {
     const int row0 = __shfl_sync(0xffffffffu, w.row, 0);
     const double f0 = shfl_d(w.f, 0);
     if (w.lane < NM_MAXN) w.xbest[w.lane] = w.lane < w.N ? w.sim[row0 * w.ld + w.lane] : 0.0;
+    w.phase = NM_DONE;
+    w.status = w.fcalls >= w.maxfun ? 1 : (w.iters >= w.maxfun ? 2 : 0);               // maxiter == maxfun == 200 N
     if (w.lane == 0) {
         *w.fbest = f0;
-        w.ctl[CTL_PHASE] = NM_DONE;
-        w.ctl[CTL_STATUS] = w.fcalls >= w.maxfun ? 1 : (w.iters >= w.maxfun ? 2 : 0);   // maxiter == maxfun == 200 N
         *w.cop = T2O_OP_SKIP;
     }
 }
@@ -261,27 +265,53 @@ __device__ __forceinline__ void nm_bind(NMWarp &w, const NMArgs &a, int p, int l
     w.lane = lane;
 }
 
-// One evaluation result for the fit `w` is bound to (l1 = the L1 sum of its pending vertex): consume it, move the simplex,
-// propose the next vertex (or finish).  Called by all 32 lanes of one warp; a finished fit returns at once.
-__device__ __forceinline__ void nm_advance_bound(NMWarp &w, const NMArgs &a, float l1) {
+// The fit's control state and sorted values: memory (the caller's arrays, or the resident kernel's shared memory) -> registers
+__device__ __forceinline__ void nm_load(NMWarp &w) {
     const int lane = w.lane;
-    double *fsim = w.fsim;
-    int *perm = w.perm;
+    const int N = w.ctl[CTL_N];
+    w.N = N; w.maxfun = 200 * N;
+    w.phase = w.ctl[CTL_PHASE]; w.k = w.ctl[CTL_K]; w.fcalls = w.ctl[CTL_FCALLS]; w.iters = w.ctl[CTL_ITERS];
+    w.status = w.ctl[CTL_STATUS];
+    w.f = lane <= N ? w.fsim[lane] : CUDART_INF;
+    w.row = lane <= N ? w.perm[lane] : lane;
+    w.fxrv = *w.fxr;
+}
+// ... and back
+__device__ __forceinline__ void nm_store(NMWarp &w) {
+    const int lane = w.lane;
+    __syncwarp();
+    if (lane <= w.N) { w.fsim[lane] = w.f; w.perm[lane] = w.row; }
+    if (lane == 0) {
+        w.ctl[CTL_PHASE] = w.phase; w.ctl[CTL_K] = w.k; w.ctl[CTL_FCALLS] = w.fcalls; w.ctl[CTL_ITERS] = w.iters;
+        w.ctl[CTL_STATUS] = w.status;
+        *w.fxr = w.fxrv;
+    }
+    __syncwarp();
+}
+
+// the same state as a value: what a warp that owns a fit for many steps keeps in registers between them
+struct NMRegs { double f, fxrv; int row, phase, k, fcalls, iters, status, N; };
+__device__ __forceinline__ NMRegs nm_regs(const NMWarp &w) { return NMRegs{w.f, w.fxrv, w.row, w.phase, w.k, w.fcalls, w.iters, w.status, w.N}; }
+__device__ __forceinline__ void nm_set_regs(NMWarp &w, const NMRegs &r) {
+    w.f = r.f; w.fxrv = r.fxrv; w.row = r.row; w.phase = r.phase; w.k = r.k; w.fcalls = r.fcalls; w.iters = r.iters;
+    w.status = r.status; w.N = r.N; w.maxfun = 200 * r.N;
+}
+
+// One evaluation result for the fit `w` holds (nm_load; l1 = the L1 sum of its pending vertex): consume it, move the simplex,
+// propose the next vertex (or finish).  Called by all 32 lanes of one warp; a finished fit returns at once.
+__device__ __forceinline__ void nm_step(NMWarp &w, const NMArgs &a, float l1) {
+    const int lane = w.lane;
     {
 #ifdef T2O_RES_PROBE
         w.pt = clock64();
 #endif
-        const int phase = w.ctl[CTL_PHASE];
+        const int phase = w.phase;
         if (phase == NM_DONE) return;
-        const int N = w.ctl[CTL_N], k = w.ctl[CTL_K];
-        w.N = N; w.maxfun = 200 * N; w.fcalls = w.ctl[CTL_FCALLS]; w.iters = w.ctl[CTL_ITERS];
-        w.f = lane <= N ? fsim[lane] : CUDART_INF;
-        w.row = lane <= N ? perm[lane] : lane;
+        const int N = w.N, k = w.k;
         // the value of the pending vertex, (x1 - x2).norm(1) / numel -> .item(): fp32, then widened.  torch's CUDA
         // division by a host scalar multiplies by the rounded reciprocal; so does this, to the bit
         const double fv = (double)__fmul_rn(l1, __frcp_rn(a.numel));
-        const double fxr = *w.fxr;
-        __syncwarp();
+        const double fxr = w.fxrv;
         const double f0 = shfl_d(w.f, 0), fN = shfl_d(w.f, N), fN1 = shfl_d(w.f, N >= 1 ? N - 1 : 0);
         T2O_NMP(0)
         // how the iteration ends: 0 not yet, 1 completed (full sort), 2 completed, only the worst vertex replaced (insertion),
@@ -299,7 +329,7 @@ __device__ __forceinline__ void nm_advance_bound(NMWarp &w, const NMArgs &a, flo
                 }
                 break;
             case NM_REFLECT:
-                if (lane == 0) *w.fxr = fv;
+                w.fxrv = fv;
                 if (nm_lt(fv, f0)) {
                     double xe = 0.0;
                     const int rowN = __shfl_sync(0xffffffffu, w.row, N);
@@ -350,20 +380,20 @@ __device__ __forceinline__ void nm_advance_bound(NMWarp &w, const NMArgs &a, flo
         T2O_NMP(1)
         if (fin) nm_end_iteration(w, a, fin == 3, fin == 2);
     }
-    __syncwarp();
-    if (lane <= w.N) { fsim[lane] = w.f; perm[lane] = w.row; }
-    if (lane == 0) { w.ctl[CTL_FCALLS] = w.fcalls; w.ctl[CTL_ITERS] = w.iters; }
     T2O_NMP(7)
 #ifdef T2O_RES_PROBE
     if (w.lane == 0 && w.N == NM_MAXN) atomicAdd(&g_nmp[8], 1ull);
 #endif
 }
 
-// the same on the caller's device arrays
+// load, step, store: the round-by-round driver's advance (state in the caller's device arrays)
 __device__ __forceinline__ void nm_advance_fit(const NMArgs &a, int p, int lane, float l1) {
     NMWarp w;
     nm_bind(w, a, p, lane);
-    nm_advance_bound(w, a, l1);
+    nm_load(w);
+    if (w.phase == NM_DONE) return;
+    nm_step(w, a, l1);
+    nm_store(w);
 }
 
 }  // namespace t2o

@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             tma_load_4d(sT, &tm_target, &sh.bar, x0, y0, 0, t_idx);
         }
         // ---- leader: the fits' Nelder-Mead state -> shared memory, their pending vertices -> every CTA
+        NMRegs nr = NMRegs{0.0, 0.0, 0, NM_DONE, 0, 0, 0, 0, 1};
         if (rank == 0 && warp < m) {
             const int p = cbeg + warp;
             // a state whose fits do not fit the shared memory the host sized is left alone (its fits stay unfinished)
@@ -518,6 +519,9 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                 }
                 if (lane < 8) w.ctl[lane] = __ldcg(nm.st.ctl + (size_t)p * 8 + lane);
                 if (lane == 0) *w.fxr = __ldcg(nm.st.fxr + p);
+                __syncwarp();
+                nm_load(w);
+                nr = nm_regs(w);                                 // (the warp keeps the fit's control state in registers from here on)
             }
             if (lane == 0) { sh.nmoff[warp] = op != OP_SKIP ? off : -1; sh.nmN[warp] = N; sh.pop[warp] = op; }
             if (lane < NM_MAXN) sh.pend[warp][lane] = prm;
@@ -541,6 +545,11 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
 #define T2O_PROBE(i)
 #endif
         bool mylive = true;                                      // warp c < m: fit c has not finished (as far as this warp has seen)
+        int my_to = 0;                                           // warp c < m: where fit c's table lives (the same in every CTA)
+        if (warp < m) {
+            for (int c = 0; c < warp; ++c) my_to += res_tab_floats(sh.cops0[c]);
+            if (lane == 0) sh.toff[warp] = my_to;                // (read behind the first round's block barrier)
+        }
         for (int round = 0; round < max_rounds; ++round) {
 #ifdef T2O_RES_PROBE
             pt = clock64();
@@ -562,15 +571,10 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             if (warp < m && mylive) mbar_wait_or_trap(&sh.pbar, pphase);
             pphase ^= 1u;
             T2O_PROBE(0)
-            if (warp < m) {
-                int to = 0;
-                for (int c = 0; c < warp; ++c) to += res_tab_floats(sh.cops0[c]);
-                if (lane == 0) sh.toff[warp] = to;
-                if (mylive) {
-                    const int op = sh.cops[warp];
-                    mylive = op != OP_SKIP;
-                    if (mylive) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + to);
-                }
+            if (warp < m && mylive) {
+                const int op = sh.cops[warp];
+                mylive = op != OP_SKIP;
+                if (mylive) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + my_to);
             }
             __syncthreads();                                     // tables built <=> this round's vertices have arrived
             bool any = false;
@@ -624,7 +628,9 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                     unsigned char *base = nmreg + sh.nmoff[warp];
                     // ctl sits behind (N+1) N + 3 N + N + 2 doubles and N + 1 ints: N is read through the leader's copy of it
                     res_bind(w, base, sh.nmN[warp], nm, cbeg + warp, lane, sh.pend[warp], &sh.pop[warp]);
-                    nm_advance_bound(w, nm, v);
+                    nm_set_regs(w, nr);
+                    nm_step(w, nm, v);
+                    nr = nm_regs(w);
                 }
             }
             T2O_PROBE(4)
@@ -644,6 +650,8 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             const int p = cbeg + warp, N = sh.nmN[warp];
             NMWarp w;
             res_bind(w, nmreg + sh.nmoff[warp], N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
+            nm_set_regs(w, nr);
+            nm_store(w);                                         // registers -> the shared-memory copy that goes back below
             double *gsim = nm.st.sim + (size_t)p * NM_ROWS * NM_MAXN, *gvec = nm.st.vec + (size_t)p * 3 * NM_MAXN;
             if (lane < N) {
                 for (int r = 0; r <= N; ++r) gsim[r * NM_MAXN + lane] = w.sim[r * N + lane];
