@@ -711,12 +711,12 @@ def fused_scale(B, H, W, dev):
     return torch.full((B,), 1.0 / (B * 3 * H * W), device=dev, dtype=torch.float32)
 
 
-PLANNER_M = 256           # pairs per GPU: four lock-step batches of 64, two in flight (planner.beam_search_pipelined)
+PLANNER_M = 512           # pairs per GPU: eight lock-step batches of 64, two in flight (planner.beam_search_pipelined)
 PLANNER_BATCH = 64
 
 
 def planner_e2e_run(dev, seed, reps=3):
-    """beam_search_batch (= the reference's beam_search on every pair, utils/beam_search.py:196-264) over 256 synthetic pairs
+    """beam_search_batch (= the reference's beam_search on every pair, utils/beam_search.py:196-264) over 512 synthetic pairs
     of 3x128x128 in lock-step batches of 64, two in flight, beam 8, the six global operators, max 6 steps, Nelder-Mead fits
     resident on the device (BASELINE config 3's shape; its 1000 pairs are 16 such batches: --workload c3).  -> (best wall-clock seconds of reps - 1 timed repetitions,
     candidates scored, mean steps of the top sequences); the first repetition warms the kernels up."""
