@@ -731,7 +731,7 @@ def planner_e2e_run(dev, seed, reps=3):
         cnt = [0]
         torch.cuda.synchronize()
         t0 = time.time()
-        res = sum(planner.beam_search_pipelined(chunks, exe, 8, CHAIN, names, 6, 1e-2, workers=2, counter=cnt), [])
+        res = sum(planner.beam_search_pipelined(chunks, exe, 8, CHAIN, names, 6, 1e-2, workers=2, counter=cnt, images='top'), [])
         torch.cuda.synchronize()
         dt = time.time() - t0
         if rep > 0 and (best is None or dt < best[0]):
@@ -782,7 +782,7 @@ def planner_e2e_line(seconds, candidates, mean_steps, n_gpus):
     return {'workload': '%d pairs of 3x128x128 per GPU, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, Nelder-Mead' % PLANNER_M,
             'n_gpus': n_gpus, 'seconds': seconds, 'pairs_per_s': pairs / seconds, 'candidates': candidates,
             'candidates_per_s': candidates / seconds, 'mean_steps': mean_steps,
-            'how': 'wall clock around beam_search_pipelined (lock-step batches of 64 pairs, two in flight; host bookkeeping and result copies included), best of 2; N > 1: pairs sharded '
+            'how': 'wall clock around beam_search_pipelined (lock-step batches of 64 pairs, two in flight; host bookkeeping and the copies of the top sequences\' images included), best of 2; N > 1: pairs sharded '
                    'by image, no communication during the search, slowest rank\'s time, candidates summed over ranks'}
 
 
@@ -1021,7 +1021,7 @@ def run_planner_c3(args):
     mine = list(range(rank, NPAIRS, world))
     # warm-up: two full batches through the pipelined driver (kernels, the allocator's pools of both worker streams)
     planner.beam_search_pipelined([make_batch(BATCH, 128, 128, 2000 + k, dev)[:2] for k in range(2)], exe, 8, CHAIN, names, 6, 1e-2,
-                                  workers=WORKERS)
+                                  workers=WORKERS, images='top')
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -1037,7 +1037,7 @@ def run_planner_c3(args):
             img, tgt, _ = make_batch(len(idx), 128, 128, 3010 + 7 * idx[0], dev)
             marks.append(time.time())
             yield img, tgt
-    for res in planner.beam_search_pipelined(batches(), exe, 8, CHAIN, names, 6, 1e-2, workers=WORKERS, counter=cnt):
+    for res in planner.beam_search_pipelined(batches(), exe, 8, CHAIN, names, 6, 1e-2, workers=WORKERS, counter=cnt, images='top'):
         steps += sum(len(r[0][0]) for r in res)
     per_batch = [round(b - a, 2) for a, b in zip(marks[:-1], marks[1:])]      # (hand-over times of the batches)
     torch.cuda.synchronize()
@@ -1053,7 +1053,8 @@ def run_planner_c3(args):
                           'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                           'seconds': sec, 'pairs_per_s': NPAIRS / sec, 'rank0_seconds_per_batch': per_batch, 'candidates': cand, 'mean_steps': t[2].item() / NPAIRS,
                           'config': {'workload': 'C3: 1000 pairs of 3x128x128, beam 8, ops [0,1,2,3,5,6], max_step 6, err 1e-2, '
-                                                 'Nelder-Mead; image-sharded, %d pairs in lock-step per call, %d calls in flight' % (BATCH, WORKERS)}}), flush=True)
+                                                 'Nelder-Mead; image-sharded, %d pairs in lock-step per call, %d calls in flight; the top sequence\'s images copied to the host '
+                                                 '(what the dataset driver writes, gen_greedy_seqs_FiveK.py:86-88)' % (BATCH, WORKERS)}}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -544,8 +544,12 @@ class DeviceNelderMead:
             raise _lib.T2OError('Nelder-Mead fits need operators with 1..24 parameters')
         import numpy as np
         x0h = np.zeros((P, _lib.MAX_OP_PARAMS), dtype=np.float64)
+        conv = {}                                                   # (the planner passes one start vector object per operator)
         for i, (v, n) in enumerate(zip(x0, n_dims)):
-            x0h[i, :n] = (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float64)).reshape(-1)[:n]
+            a = conv.get(id(v))
+            if a is None:
+                a = conv[id(v)] = (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float64)).reshape(-1)
+            x0h[i, :n] = a[:n]
         x0m = torch.from_numpy(x0h)
         self.cb = CandidateBatch(S, prob_state, prob_op, torch.zeros(P, _lib.MAX_OP_PARAMS), dev, state_target, masks, prob_mask)
         self.n_dims = torch.tensor(n_dims, dtype=torch.int32, device=dev)

@@ -131,8 +131,9 @@ def fit_params_nelder_mead(states, targets, problems, executor, state_target=Non
         return []
     L = getattr(executor.opt, 'curve_steps', 8)
     order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))       # the scorer wants candidates sorted by state
+    x0 = {op: _param0(op, executor) for op in set(p[1] for p in problems)}
     nm = TF.DeviceNelderMead(states, targets, [problems[i][0] for i in order], [problems[i][1] for i in order],
-                             [_param0(problems[i][1], executor) for i in order], state_target=state_target,
+                             [x0[problems[i][1]] for i in order], state_target=state_target,
                              curve_steps=L, numel=numel, masks=masks,
                              prob_mask=None if masks is None else [prob_mask[i] for i in order])
     r = nm.run()
@@ -140,10 +141,10 @@ def fit_params_nelder_mead(states, targets, problems, executor, state_target=Non
     if counter is not None:
         counter[0] += int(r['nfev'].sum())
     out = [None] * len(problems)
-    x, fun = r['x'].numpy(), r['fun'].numpy()
+    x, fun = r['x'].numpy(), r['fun'].tolist()
+    ns, nit, nfev, status = r['n'].tolist(), r['nit'].tolist(), r['nfev'].tolist(), r['status'].tolist()
     for pos, i in enumerate(order):
-        n = int(r['n'][pos])
-        out[i] = _Fit(x[pos, :n].copy(), float(fun[pos]), int(r['nit'][pos]), int(r['nfev'][pos]), int(r['status'][pos]))
+        out[i] = _Fit(x[pos, :ns[pos]].copy(), fun[pos], nit[pos], nfev[pos], status[pos])
     return out
 
 
@@ -256,7 +257,7 @@ def _score_outputs(I_list, ops, params, I_gt_list, executor, mask_list=None, gat
                               for mk in mask_list[c0:c0 + CH]], 0).contiguous()
         out, l1 = TF._rows_forward_raw(ops_dev, ops_host, img, mask, mask_ch, prm.to(dev), tgt, True, True, L)
         vals += (l1 / numel).tolist()
-        outs += [out[r:r + 1] for r in range(len(Is))]
+        outs += list(out.split(1))                                  # (views of the step's output tensor, one per row)
     return outs, vals
 
 
@@ -311,7 +312,7 @@ def _step_minima_sharded(dists, problems, live, device_, group):
 
 def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, dist_type='L1',
                       optimizer='Nelder-Mead', replace=False, _variant='default', _eps=0.05, counter=None, txt=None,
-                      trace=None, shard_fits=False, group=None, masks=None, mask_op_idx=None):
+                      trace=None, shard_fits=False, group=None, masks=None, mask_op_idx=None, images='all'):
     """`beam_search` (utils/beam_search.py:196-264) for M image pairs at once: I_0, I_gt (M,3,H,W).
 
     Every pair runs the reference's beam search unchanged; what is shared is the work: all (pair, beam state,
@@ -326,8 +327,12 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     chosen mask's position in the list is recorded as a fourth field of the action.
     `shard_fits` (inside an initialised process group, every rank calling with the SAME pairs): candidate-sharded mode --
     the fits of a step are split over the ranks, the table of fitted parameters is all-gathered and the step's best
-    candidate per pair is agreed with one all_reduce(MIN) (NCCL on GPUs); the result is the same for every rank count."""
+    candidate per pair is agreed with one all_reduce(MIN) (NCCL on GPUs); the result is the same for every rank count.
+    `images`: which edited images come back on the host -- 'all' (every beam's, as the reference returns them), 'top' (the
+    best sequence's only, which is what the dataset driver writes to disk, preprocess/gen_greedy_seqs_FiveK.py:86-88; the
+    other beams' image lists are empty) or 'none'."""
     assert dist_type == 'L1', 'only the L1 distance is implemented'
+    assert images in ('all', 'top', 'none')
     if shard_fits:
         import torch.distributed as _dist
         shard_fits = _dist.is_available() and _dist.is_initialized() and _dist.get_world_size(group) > 1
@@ -471,7 +476,9 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     # (sequences of a pair share their prefixes; ~1 400 separate .cpu() calls cost a 64-pair search 0.14 s)
     uniq, order = {}, []
     for m in range(M):
-        for seq in st[m]['sequences']:
+        for b, seq in enumerate(st[m]['sequences']):
+            if images == 'none' or (images == 'top' and b > 0):
+                continue
             for act in seq[0]:
                 if id(act[-1]) not in uniq:
                     uniq[id(act[-1])] = len(order)
@@ -484,7 +491,9 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     for m in range(M):
         seqs = st[m]['sequences']
         actions = [[act[:-1] for act in seq[0]] for seq in seqs]
-        Is = [[host[uniq[id(act[-1])] // CH][uniq[id(act[-1])] % CH:uniq[id(act[-1])] % CH + 1] for act in seq[0]] for seq in seqs]
+        Is = [[] if images == 'none' or (images == 'top' and b > 0) else
+              [host[uniq[id(act[-1])] // CH][uniq[id(act[-1])] % CH:uniq[id(act[-1])] % CH + 1] for act in seq[0]]
+              for b, seq in enumerate(seqs)]
         results.append((actions, Is))
     return results
 

@@ -85,6 +85,11 @@ def test_beam_search_pipelined_equals_sequential_batches(T):
     c_seq, c_pipe = [0], [0]
     seq = [planner.beam_search_batch(a, b, ex, 2, [0, 1, 3, 6], O.ACTION_NAMES, 2, 1e-3, counter=c_seq) for a, b in batches]
     pipe = planner.beam_search_pipelined(iter(batches), ex, 2, [0, 1, 3, 6], O.ACTION_NAMES, 2, 1e-3, workers=2, counter=c_pipe)
+    top = planner.beam_search_pipelined(iter(batches), ex, 2, [0, 1, 3, 6], O.ACTION_NAMES, 2, 1e-3, workers=2, images='top')
+    for rs, rt in zip(seq, top):
+        for (acts, Is), (tacts, tIs) in zip(rs, rt):
+            assert acts == tacts and len(tIs) == len(Is) and all(len(x) == 0 for x in tIs[1:])
+            assert len(tIs[0]) == len(Is[0]) and all(torch.equal(x, y) for x, y in zip(Is[0], tIs[0]))
     assert c_seq[0] == c_pipe[0] and len(seq) == len(pipe)
     for rs, rp in zip(seq, pipe):
         assert len(rs) == len(rp)
