@@ -1017,7 +1017,7 @@ def run_planner_c3(args):
     from t2onet_b200 import planner
     names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
     exe = T.Executor(T.default_options()).to(dev)
-    NPAIRS, BATCH, WORKERS = 1000, 64, int(os.environ.get('T2O_PLANNER_WORKERS', 2))
+    NPAIRS, BATCH, WORKERS = 1000, int(os.environ.get('T2O_PLANNER_BATCH', 64)), int(os.environ.get('T2O_PLANNER_WORKERS', 2))
     mine = list(range(rank, NPAIRS, world))
     # warm-up: two full batches through the pipelined driver (kernels, the allocator's pools of both worker streams)
     planner.beam_search_pipelined([make_batch(BATCH, 128, 128, 2000 + k, dev)[:2] for k in range(2)], exe, 8, CHAIN, names, 6, 1e-2,
