@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ F
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const bool raw = a.raw != 0;
 
-    if (tid < 3 * n) build_table_part<false>(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, tabs[tid / 3]);
+    for (int k = tid >> 5; k < n; k += NT / 32) build_table_lanes<false>(ch.op[k], tid & 31, a.params + (size_t)b * a.pstride + ch.poff[k], L, tabs[k]);
     __syncthreads();
 
     float l1 = 0.0f;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(NT, 4) chain_fwd_rows_kernel(const __grid_cons
 
     float *Xc = dyn_smem + (1 + lane) * VEC;
     for (int i = tid; i < RINGF; i += NT) dyn_smem[i] = 0.0f;
-    if (tid < 3 * n) build_table_part<false>(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, tabs[tid / 3]);
+    for (int k = tid >> 5; k < n; k += NT / 32) build_table_lanes<false>(ch.op[k], tid & 31, a.params + (size_t)b * a.pstride + ch.poff[k], L, tabs[k]);
 
     const int clamped = SP ? SPC : (ROWS ? chain_clamped_bits(ch.op, n) : a.clamped);
     float l1 = 0.0f;

@@ -281,6 +281,46 @@ T2O_HD void build_table_part(int op, int part, const float *p, int L, float *tab
     else if (part == 0) build_table<BWD>(op, p, L, tab);
 }
 
+#if defined(__CUDACC__)
+// One warp builds one operator's table: one lane per curve record (3 L lanes of a color operator, L of a tone operator),
+// lane 0 everything else -- the same functions in the same order as build_curve, so the same bits; the in-range flag is the
+// AND of the lanes' segment checks (a ballot).  Called by all 32 lanes of the warp.  The kernels give every operator of a
+// chain its own warp: the serial builders (three threads of one warp, one curve each, different operators one after the
+// other) kept a 128 x 128 step's other 250 threads at the first barrier for ~2 us.
+template <bool BWD = true>
+__device__ __forceinline__ void build_table_lanes(int op, int lane, const float *p, int L, float *tab) {
+    if (op == OP_COLOR || op == OP_TONE) {
+        const int part = lane / L, j = lane - part * L;
+        const bool active = part < (op == OP_COLOR ? 3 : 1);
+        bool ok = true;
+        if (active) {
+            const float *k = p + part * L;
+            float *ct = tab + part * CT;
+            const CurveScalars cs = curve_scalars(k, L);
+            F4 r = curve_record(k, L, j, cs, curve_prefix(k, j, cs.invL));
+            if (j == L - 1) {
+                r.b = curve_pull_back(r.a, r.b);
+                ct[4 * L] = r.a; ct[4 * L + 1] = r.b; ct[4 * L + 2] = r.a; ct[4 * L + 3] = r.a;
+                ct[CT_INVS] = 1.0f / cs.S;
+                ct[CT_SCALE] = cs.scale;
+            }
+            ct[4 * j] = r.a; ct[4 * j + 1] = r.b; ct[4 * j + 2] = r.c; ct[4 * j + 3] = r.d;
+            if (BWD) {
+                const float y0 = fmaf(r.a, (float)j * cs.invL, r.b), y1 = fmaf(r.a, (float)(j + 1) * cs.invL, r.b);
+                ok = y0 >= 0.0f && y0 <= 1.0f && y1 >= 0.0f && y1 <= 1.0f;
+            }
+        }
+        if (BWD) {
+            const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+            const unsigned int mine = ((1u << L) - 1u) << (part * L);           // the lanes of this lane's curve
+            if (active && j == 0) tab[part * CT + CT_INRANGE] = (bad & mine) ? 0.0f : 1.0f;
+        }
+    } else if (lane == 0) {
+        build_table<BWD>(op, p, L, tab);
+    }
+}
+#endif
+
 // ---------------------------------------------------------------- blend + clamp (models/operators.py:129-130)
 template <bool HM>
 T2O_HD float blend(float y, float x, float m) { return HM ? fmaf(y, m, x * (1.0f - m)) : y; }

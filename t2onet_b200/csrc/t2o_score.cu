@@ -403,29 +403,6 @@ __device__ __forceinline__ void res_bind(NMWarp &w, unsigned char *base, int N, 
     __builtin_assume(__isShared(w.cparam)); __builtin_assume(__isShared(w.cop));
 }
 
-// lane-parallel table of one fit: one lane per curve record (3 L lanes of a color operator, L of a tone operator), lane 0
-// everything else -- the same functions in the same order as build_curve, so the same bits
-__device__ __forceinline__ void build_table_lanes(int op, int lane, const float *p, int L, float *tab) {
-    if (op == OP_COLOR || op == OP_TONE) {
-        const int part = lane / L, j = lane - part * L;
-        if (part < (op == OP_COLOR ? 3 : 1)) {
-            const float *k = p + part * L;
-            float *ct = tab + part * CT;
-            const CurveScalars cs = curve_scalars(k, L);
-            F4 r = curve_record(k, L, j, cs, curve_prefix(k, j, cs.invL));
-            if (j == L - 1) {
-                r.b = curve_pull_back(r.a, r.b);
-                *reinterpret_cast<float4 *>(ct + 4 * L) = make_float4(r.a, r.b, r.a, r.a);
-                ct[CT_INVS] = 1.0f / cs.S;
-                ct[CT_SCALE] = cs.scale;
-            }
-            *reinterpret_cast<float4 *>(ct + 4 * j) = make_float4(r.a, r.b, r.c, r.d);
-        }
-    } else if (lane == 0) {
-        build_table<false>(op, p, L, tab);
-    }
-}
-
 template <bool HM>
 __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_constant__ CUtensorMap tm_state,
                                                                  const __grid_constant__ CUtensorMap tm_target,
@@ -574,7 +551,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             if (warp < m && mylive) {
                 const int op = sh.cops[warp];
                 mylive = op != OP_SKIP;
-                if (mylive) build_table_lanes(op, lane, sh.cprm[warp], a.L, tabs + my_to);
+                if (mylive) build_table_lanes<false>(op, lane, sh.cprm[warp], a.L, tabs + my_to);
             }
             __syncthreads();                                     // tables built <=> this round's vertices have arrived
             bool any = false;

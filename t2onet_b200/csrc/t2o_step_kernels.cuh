@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(NTH, 2) step_flat_kernel(const __grid_constant
     const float *mask_b = HM ? a.mask + (size_t)b * a.mask_ch * plane : nullptr;
     const float gl1 = a.grad_l1 ? a.grad_l1[b] : 0.0f;
 
-    if (tid < 3 * n) build_table_part(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, sh.tabs[tid / 3]);
+    // (a warp per operator, a lane per curve record)
+    for (int k = tid >> 5; k < n; k += SNT / 32) build_table_lanes<true>(ch.op[k], tid & 31, a.params + (size_t)b * a.pstride + ch.poff[k], L, sh.tabs[k]);
     __syncthreads();
 
     // dynamic shared memory: [staging slots: image 3 x SNT vectors, upstream 3 x SNT vectors][tape]
@@ -571,7 +572,8 @@ __global__ void __launch_bounds__(NTH, MINB) step_sharp_kernel(const __grid_cons
     const int ntp = sp > 1 ? sp - 1 : 0;
     V *tapeQ = reinterpret_cast<V *>(rings + NRING * RINGF) + ntp * RING * TSLOT + tid;      // [(k-sp-1)][c][SNT]
     for (int i = tid; i < NRING * RINGF; i += SNT) rings[i] = 0.0f;
-    if (tid < 3 * n) build_table_part(ch.op[tid / 3], tid % 3, a.params + (size_t)b * a.pstride + ch.poff[tid / 3], L, sh.tabs[tid / 3]);
+    // (a warp per operator, a lane per curve record)
+    for (int k = tid >> 5; k < n; k += SNT / 32) build_table_lanes<true>(ch.op[k], tid & 31, a.params + (size_t)b * a.pstride + ch.poff[k], L, sh.tabs[k]);
     __syncthreads();
 
     const float p = sh.tabs[sp][0];
