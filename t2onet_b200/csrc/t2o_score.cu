@@ -323,7 +323,12 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
             __syncwarp();
             if (lane == 0) build_table<false>(op, a.cand_param + (size_t)ci * T2O_MAX_OP_PARAMS, a.L, tab);
             __syncwarp();
-            const float sum = warp_sum(tile_sum(op, tab, lane, 32, cand_mask_img(ci)));
+            // one warp, the whole tile -- summed in the ORDER of the cooperative path (the share of each of its eight warps,
+            // reduced, then added in warp order), so that a candidate's score does not depend on how many candidates share
+            // its state: a fit is the same fit whether six or sixteen others run beside it
+            const float *mimg = cand_mask_img(ci);
+            float sum = 0.0f;
+            for (int vw = 0; vw < SCORE_NW; ++vw) sum += warp_sum(tile_sum(op, tab, vw * 32 + lane, SCORE_NT, mimg));
             if (lane == 0) a.part[(size_t)ci * a.ntiles + tile] = sum;
         }
     }

@@ -202,3 +202,26 @@ def test_resident_nelder_mead_can_stop_and_go_on_in_rounds(T):
         os.environ.pop('T2O_NM_RESIDENT', None)
     for k in ('x', 'fun', 'nit', 'nfev', 'status'):
         assert torch.equal(r0[k], r1[k]), k
+
+
+def test_resident_nelder_mead_declines_what_it_cannot_hold(T):
+    """More than eight fits on one state (or a state without fits next to it): run_resident() answers False / skips, run() falls
+    back to the rounds, and the results equal the host coroutine-checked round path."""
+    from t2onet_b200 import planner, functional as TF
+    ex = T.Executor(T.default_options()).cuda()
+    states, targets = _pairs(3, 32, 64, 5)
+    nine = [0, 1, 2, 6, 0, 1, 2, 6, 0]
+    probs = [(0, op) for op in nine] + [(2, 0)]                 # state 1 has no fit at all
+    nm = TF.DeviceNelderMead(states, targets, [p[0] for p in probs], [p[1] for p in probs],
+                             [planner._param0(p[1], ex) for p in probs], state_target=[0, 1, 2])
+    assert nm.run_resident() is False
+    r = nm.run()
+    assert bool(r['done'].all())
+    # the duplicated problems are the same fit
+    assert torch.equal(r['x'][0], r['x'][4]) and torch.equal(r['x'][0], r['x'][8]) and r['nfev'][0] == r['nfev'][4]
+    few = [(0, 0), (2, 6)]
+    nm2 = TF.DeviceNelderMead(states, targets, [p[0] for p in few], [p[1] for p in few], [planner._param0(p[1], ex) for p in few],
+                              state_target=[0, 1, 2])
+    assert nm2.run_resident() is True
+    r2 = nm2.result()
+    assert bool(r2['done'].all()) and torch.equal(r2['x'][0], r['x'][0]) and r2['fun'][0] == r['fun'][0]
