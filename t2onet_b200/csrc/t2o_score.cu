@@ -92,9 +92,17 @@ __device__ __forceinline__ void st_local_u32(void *dst, uint32_t value, uint64_t
     asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(4u) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity) {
-    bool done = false;
-    for (int it = 0; it < (1 << 13) && !done; ++it) done = mbar_try_wait_sleep(bar, parity);
-    if (!done) __trap();                                         // a broken protocol must fail loudly, not hang the GPU
+    if (mbar_try_wait_sleep(bar, parity)) return;
+    // a broken protocol must fail loudly, not hang the GPU: trap after 20 s of wall clock (a round takes microseconds; the
+    // bound is in time, not in polls, because how long one try_wait sleeps is up to the hardware)
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        for (int it = 0; it < 64; ++it)
+            if (mbar_try_wait_sleep(bar, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -513,12 +521,8 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             }
         }
         cluster.sync();                                          // cops0 / cmask are in place (once per state)
-        {
-            bool done = false;
-            for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try_wait(&sh.bar, bar_phase);
-            if (!done) __trap();
-            bar_phase ^= 1u;
-        }
+        mbar_wait_or_trap(&sh.bar, bar_phase);                   // the tiles
+        bar_phase ^= 1u;
         // ---- rounds
 #ifdef T2O_RES_PROBE
         long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
