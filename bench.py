@@ -739,13 +739,14 @@ def planner_e2e_run(dev, seed, reps=3):
     return best[0], best[1], sum(len(r[0][0]) for r in res) / PLANNER_M
 
 
-GIER_M = 16
+GIER_M = 64            # pairs per GPU: four lock-step batches of 16, two in flight
+GIER_BATCH = 16
 
 
 def planner_gier_run(dev, seed, reps=2):
     """BASELINE config 5's planner shape: GIER-shaped inputs (3x256x256 pairs, each with the global mask and two local masks that
     belong to brightness and saturation, preprocess/gen_greedy_seqs_GIER.py:36-62), beam 3 and err 1e-3 as that driver sets them,
-    the six global operators, Nelder-Mead; 16 pairs in lock-step.  -> (seconds, candidates, mean steps)"""
+    the six global operators, Nelder-Mead; 64 pairs in lock-step batches of 16, two in flight.  -> (seconds, candidates, mean steps)"""
     import t2onet_b200 as T
     from t2onet_b200 import planner
     names = ['brightness', 'contrast', 'saturation', 'color', 'inpaint', 'tone', 'sharpness', 'white']
@@ -757,12 +758,14 @@ def planner_gier_run(dev, seed, reps=2):
         m2 = torch.zeros(1, 1, 256, 256, device=dev); m2[..., 128:, 64 + 8 * (m % 3):] = 1.0
         masks.append([torch.ones(1, 1, 256, 256, device=dev), m1, m2])
         idx.append([-1, 0, 2])
+    chunks = [(img[c:c + GIER_BATCH], tgt[c:c + GIER_BATCH], {'masks': masks[c:c + GIER_BATCH], 'mask_op_idx': idx[c:c + GIER_BATCH]})
+              for c in range(0, GIER_M, GIER_BATCH)]
     best = None
     for rep in range(reps + 1):
         cnt = [0]
         torch.cuda.synchronize()
         t0 = time.time()
-        res = planner.beam_search_batch(img, tgt, exe, 3, CHAIN, names, 6, 1e-3, counter=cnt, masks=masks, mask_op_idx=idx)
+        res = sum(planner.beam_search_pipelined(chunks, exe, 3, CHAIN, names, 6, 1e-3, workers=2, counter=cnt, images='top'), [])
         torch.cuda.synchronize()
         dt = time.time() - t0
         if rep > 0 and (best is None or dt < best[0]):
@@ -774,7 +777,7 @@ def planner_gier_line(seconds, candidates, mean_steps, n_gpus):
     return {'workload': '%d GIER-shaped pairs of 3x256x256 per GPU (global mask + 2 local masks), beam 3, ops [0,1,2,3,5,6], max_step 6, '
                         'err 1e-3, Nelder-Mead' % GIER_M, 'n_gpus': n_gpus, 'seconds': seconds, 'pairs_per_s': GIER_M * n_gpus / seconds,
             'candidates': candidates, 'candidates_per_s': candidates / seconds, 'mean_steps': mean_steps,
-            'how': 'wall clock around beam_search_batch with masks, best of 2; N > 1: pairs sharded by image, slowest rank\'s time'}
+            'how': 'wall clock around beam_search_pipelined with masks (lock-step batches of 16 pairs, two in flight), best of 2; N > 1: pairs sharded by image, slowest rank\'s time'}
 
 
 def planner_e2e_line(seconds, candidates, mean_steps, n_gpus):

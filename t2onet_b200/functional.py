@@ -518,6 +518,10 @@ def topk_min(values, seg_begin, k):
     return idx, val
 
 
+import threading
+_CAPTURE_LOCK = threading.Lock()
+
+
 class DeviceNelderMead:
     """P Nelder-Mead fits that live on the GPU (t2o_nm_start / t2o_nm_advance), each scored as candidate p of
     t2o_score_candidates: argmin_param L1(op(states[prob_state[p]]; param), its target) with scipy's defaults, as
@@ -630,8 +634,10 @@ class DeviceNelderMead:
                 side = torch.cuda.Stream(self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.stream(side):                      # _round() launches on the capturing stream
-                    graph.capture_begin()
+                # (one capture at a time, in thread-local mode: planner.beam_search_pipelined runs batches on several threads, and
+                # a global-mode capture forbids the other threads' allocations and copies while it lasts)
+                with _CAPTURE_LOCK, torch.cuda.stream(side):       # _round() launches on the capturing stream
+                    graph.capture_begin(capture_error_mode='thread_local')
                     try:
                         for _ in range(check_every):
                             self._round()

@@ -504,17 +504,18 @@ def beam_search_pipelined(batches, executor, beam_size, operations, operation_na
     `workers` batches in flight: each runs on its own thread and CUDA stream, so the host bookkeeping of one batch (selection,
     records, result copies: about half of a batch's wall time) overlaps the device fits of another, and the resident
     Nelder-Mead launches of two batches fill each other's tails.  Batches are independent, so every result equals the
-    sequential call's.  batches: an iterable of (I_0, I_gt) CUDA tensor pairs (consumed at most `workers` ahead);
-    returns the list of beam_search_batch results in order.  (Not for the eps-greedy variant, whose random draws are ordered.)"""
+    sequential call's.  batches: an iterable of (I_0, I_gt) CUDA tensor pairs, or (I_0, I_gt, kwargs) with keyword arguments
+    of that batch alone (its masks / mask_op_idx) -- consumed at most `workers` ahead; returns the list of beam_search_batch
+    results in order.  (Not for the eps-greedy variant, whose random draws are ordered.)"""
     import concurrent.futures as cf
     assert kwargs.get('_variant', 'default') != 'eps_greedy', 'eps-greedy draws from one ordered random stream'
     if workers <= 1:
-        return [beam_search_batch(a, b, executor, beam_size, operations, operation_names, max_step, err, counter=counter, **kwargs)
-                for a, b in batches]
+        return [beam_search_batch(bt[0], bt[1], executor, beam_size, operations, operation_names, max_step, err, counter=counter,
+                                  **dict(kwargs, **(bt[2] if len(bt) > 2 else {}))) for bt in batches]
     results, counts, pending = {}, {}, []
     local = threading.local()
 
-    def work(k, I_0, I_gt, ready):
+    def work(k, I_0, I_gt, ready, kw):
         dev = I_0.device
         torch.cuda.set_device(dev)                                  # (a new thread starts on device 0)
         if not hasattr(local, 'stream'):
@@ -522,7 +523,7 @@ def beam_search_pipelined(batches, executor, beam_size, operations, operation_na
         cnt = [0]
         with torch.cuda.stream(local.stream):
             local.stream.wait_event(ready)                          # the batch was produced on the caller's stream
-            res = beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, counter=cnt, **kwargs)
+            res = beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, counter=cnt, **kw)
             local.stream.synchronize()
         I_0.record_stream(local.stream)
         I_gt.record_stream(local.stream)
@@ -532,10 +533,11 @@ def beam_search_pipelined(batches, executor, beam_size, operations, operation_na
         def drain(fut):
             k, res, c = fut.result()
             results[k], counts[k] = res, c
-        for k, (I_0, I_gt) in enumerate(batches):
+        for k, bt in enumerate(batches):
+            I_0, I_gt = bt[0], bt[1]
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(I_0.device))
-            pending.append(pool.submit(work, k, I_0, I_gt, ready))
+            pending.append(pool.submit(work, k, I_0, I_gt, ready, dict(kwargs, **(bt[2] if len(bt) > 2 else {}))))
             if len(pending) >= workers + 1:
                 drain(pending.pop(0))
         for fut in pending:

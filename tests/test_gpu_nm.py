@@ -76,10 +76,13 @@ def test_beam_search_batch_equals_single_pairs(T):
                 assert not x.is_cuda and torch.equal(x, y)
 
 
-def test_beam_search_pipelined_equals_sequential_batches(T):
+@pytest.mark.parametrize('resident', ['1', '0'])
+def test_beam_search_pipelined_equals_sequential_batches(T, resident, monkeypatch):
     """planner.beam_search_pipelined (batches in flight on two threads / CUDA streams) == one beam_search_batch per batch:
-    same sequences, parameters, distances, images and evaluation count."""
+    same sequences, parameters, distances, images and evaluation count -- with the resident Nelder-Mead launches and with the
+    round-by-round fallback (whose CUDA-graph captures must not collide between the threads)."""
     from t2onet_b200 import planner
+    monkeypatch.setenv('T2O_NM_RESIDENT', resident)
     ex = T.Executor(T.default_options()).cuda()
     batches = [_pairs(3 + (k % 2), 32, 32, 40 + k) for k in range(5)]
     c_seq, c_pipe = [0], [0]
