@@ -154,7 +154,7 @@ def test_topk_min_is_the_stable_argsort_prefix(T):
 
 
 @pytest.mark.parametrize('S,H,W,masked', [(5, 128, 128, False), (80, 128, 128, False), (6, 64, 96, True), (4, 32, 32, False),
-                                          (3, 40, 52, False), (2, 256, 256, False), (2, 264, 320, True)])
+                                          (3, 40, 52, False), (2, 256, 256, False), (2, 264, 320, True), (4, 64, 128, 3)])
 def test_resident_nelder_mead_equals_the_rounds_exactly(T, S, H, W, masked, monkeypatch):
     """t2o_nm_run_resident (a cluster of CTAs keeps each state in shared memory for the life of its fits) against rounds of
     t2o_score_candidates + t2o_nm_advance: fitted parameters, function values, iteration and evaluation counts identical,
@@ -168,7 +168,8 @@ def test_resident_nelder_mead_equals_the_rounds_exactly(T, S, H, W, masked, monk
     kw = {}
     if masked:
         g = torch.Generator().manual_seed(3)
-        kw = dict(masks=(torch.rand(2, 1, H, W, generator=g) > 0.4).float().cuda(), prob_mask=[(i % 3) - 1 for i in range(len(problems))])
+        kw = dict(masks=(torch.rand(2, 3 if masked == 3 else 1, H, W, generator=g) > 0.4).float().cuda(),
+                  prob_mask=[(i % 3) - 1 for i in range(len(problems))])
     res = []
     for env in ('0', '1'):
         monkeypatch.setenv('T2O_NM_RESIDENT', env)
