@@ -120,10 +120,12 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, ui
 // or is null for a candidate without a mask (mask = 1: blend(y, x, 1) == y to the bit).
 // (split in two so that the resident kernel loads a group once for all the fits of its state: xc / t are the group's centre
 // pixels of the state and its target pixels)
+// clamped_in: every value of the state tile lies in [0, 1] (true of every state a planner meets: images and clamped edits), so
+// the curve operators' input clamp is the identity and is skipped -- the same bits, one instruction per channel less
 template <int VEC, bool HM>
 __device__ __forceinline__ void score_group_loaded(float &sum, int op, const float *tab, int L, float p, const float (&xc)[3][VEC],
                                                    const float (&t)[3][VEC], const float *src, int spitch, int cs,
-                                                   const float *mptr, size_t mcs) {
+                                                   const float *mptr, size_t mcs, bool clamped_in = false) {
     float x[3][VEC], m[3][VEC];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -175,10 +177,21 @@ __device__ __forceinline__ void score_group_loaded(float &sum, int op, const flo
         _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                       \
             op_apply<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);                       \
         break;
-            T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE(OP_COLOR)
-            T2O_CASE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
+#define T2O_CASE_CURVE(OPC)                                                                                   \
+    case OPC:                                                                                                 \
+        if (clamped_in) {                                                                                     \
+            _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                   \
+                op_apply<HM, true>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);             \
+        } else {                                                                                              \
+            _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                   \
+                op_apply<HM>(OPC, tab, L, x[0][v], x[1][v], x[2][v], m[0][v], m[1][v], m[2][v]);                   \
+        }                                                                                                     \
+        break;
+            T2O_CASE(OP_BRIGHTNESS) T2O_CASE(OP_CONTRAST) T2O_CASE(OP_SATURATION) T2O_CASE_CURVE(OP_COLOR)
+            T2O_CASE_CURVE(OP_TONE) T2O_CASE(OP_WHITE) T2O_CASE(OP_EXPOSURE) T2O_CASE(OP_WHITEBALANCE)
             T2O_CASE(OP_BNW) T2O_CASE(OP_HUE)
 #undef T2O_CASE
+#undef T2O_CASE_CURVE
             default: break;
         }
     }
@@ -190,14 +203,14 @@ __device__ __forceinline__ void score_group_loaded(float &sum, int op, const flo
 
 template <int VEC, bool HM>
 __device__ __forceinline__ void score_group(float &sum, int op, const float *tab, int L, float p, const float *src, int spitch, int cs,
-                                            const float *tsrc, int ct, const float *mptr, size_t mcs) {
+                                            const float *tsrc, int ct, const float *mptr, size_t mcs, bool clamped_in = false) {
     float xc[3][VEC], t[3][VEC];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         lds_vec<VEC>(src + c * cs, xc[c]);
         lds_vec<VEC>(tsrc + c * ct, t[c]);
     }
-    score_group_loaded<VEC, HM>(sum, op, tab, L, p, xc, t, src, spitch, cs, mptr, mcs);
+    score_group_loaded<VEC, HM>(sum, op, tab, L, p, xc, t, src, spitch, cs, mptr, mcs, clamped_in);
 }
 
 // VEC = 4: W % 4 == 0, state rows padded by 4 floats each side (keeps 128-bit LDS aligned)
@@ -523,6 +536,10 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
         cluster.sync();                                          // cops0 / cmask are in place (once per state)
         mbar_wait_or_trap(&sh.bar, bar_phase);                   // the tiles
         bar_phase ^= 1u;
+        // is every value of the state tile (halo included; out-of-image zeros count) in [0, 1]?  One look per state.
+        bool clamped_in = true;
+        for (int i = tid; i < 3 * srows * spitch; i += SCORE_NT) clamped_in &= in01(sS[i]);
+        clamped_in = __syncthreads_and(clamped_in) != 0;
         // ---- rounds
 #ifdef T2O_RES_PROBE
         long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
@@ -582,7 +599,8 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                     const int ly = (gi * twg_magic) >> 16, lx = (gi - ly * TWg) * VEC;     // gi / TWg (exact: gi < 1024, TWg <= 32)
                     if (y0 + ly >= H || x0 + lx >= W) continue;
                     score_group<VEC, HM>(sum, op, tab, a.L, p, sS + (ly + 1) * spitch + HX + lx, spitch, srows * spitch,
-                                         sT + ly * TW + lx, TH * TW, mimg ? mimg + (size_t)(y0 + ly) * W + x0 + lx : nullptr, mcs);
+                                         sT + ly * TW + lx, TH * TW, mimg ? mimg + (size_t)(y0 + ly) * W + x0 + lx : nullptr, mcs,
+                                         clamped_in);
                 }
                 sum = warp_sum(sum);
                 if (lane == 0) sh.wsum[c][warp] = sum;
