@@ -46,6 +46,7 @@ struct NMWarp {
     double *sim, *vec, *fxr, *xbest, *fbest, *fsim;
     int *ctl, *perm;
     int ld;                         // doubles between the rows of sim / vec (NM_MAXN in the caller's arrays, N when packed in shared memory)
+    bool store_result;              // nm_finish writes xbest / fbest (false in the CTAs that only shadow a fit)
     float *cparam;
     int *cop;
     int N, lane;
@@ -147,11 +148,11 @@ __device__ __forceinline__ bool nm_propose(NMWarp &w, double x, int phase, int k
 __device__ __forceinline__ void nm_finish(NMWarp &w, const NMArgs &a) {
     const int row0 = __shfl_sync(0xffffffffu, w.row, 0);
     const double f0 = shfl_d(w.f, 0);
-    if (w.lane < NM_MAXN) w.xbest[w.lane] = w.lane < w.N ? w.sim[row0 * w.ld + w.lane] : 0.0;
+    if (w.store_result && w.lane < NM_MAXN) w.xbest[w.lane] = w.lane < w.N ? w.sim[row0 * w.ld + w.lane] : 0.0;
     w.phase = NM_DONE;
     w.status = w.fcalls >= w.maxfun ? 1 : (w.iters >= w.maxfun ? 2 : 0);               // maxiter == maxfun == 200 N
     if (w.lane == 0) {
-        *w.fbest = f0;
+        if (w.store_result) *w.fbest = f0;
         *w.cop = T2O_OP_SKIP;
     }
 }
@@ -263,6 +264,7 @@ __device__ __forceinline__ void nm_bind(NMWarp &w, const NMArgs &a, int p, int l
     w.perm = a.st.perm + (size_t)p * NM_ROWS;
     w.ld = NM_MAXN;
     w.lane = lane;
+    w.store_result = true;
 }
 
 // The fit's control state and sorted values: memory (the caller's arrays, or the resident kernel's shared memory) -> registers

@@ -370,15 +370,17 @@ __global__ void __launch_bounds__(SCORE_NT) score_kernel(const __grid_constant__
 // round re-stages every state: a CTA per (state, tile) pays a candidate scan, a TMA round trip and an arrival-counter
 // epilogue for ~0.6 us of arithmetic, and the host pays a launch pair per round.  Here a CLUSTER of ntiles CTAs owns a state
 // for the whole life of its fits: each CTA stages its tile of the state and of the target ONCE; the leader (CTA 0) copies the
-// Nelder-Mead state of the state's fits (simplex, values, counters) from the caller's arrays into its shared memory, packed
-// by the fits' dimensions; then the cluster iterates
-//     leader: the fits' pending vertices -> every CTA's shared memory (st.async over distributed shared memory, completing
-//             the transaction count of the receiver's mbarrier `pbar`: no fence, no cluster barrier)
-//     every CTA: wait on pbar; tables of the live fits' vertices (one lane per curve record), |op(tile) - target tile| per
-//                fit (score_kernel's cooperative path), tile partials -> the leader's shared memory (st.async, `sbar`)
-//     leader: wait on sbar; one warp per fit consumes the score and proposes the next vertex (nm_advance_bound, on shared
-//             memory)
-// until every fit of the state is finished, writes the fits' state back and takes the next state (atomic work counter).
+// Nelder-Mead state of the state's fits (simplex, values, counters) from the caller's arrays into shared memory, packed by the
+// fits' dimensions -- EVERY CTA of the cluster does, and every CTA steps every fit itself (warp c: fit c): the step is
+// deterministic, so all copies agree on the next vertex without a word exchanged, and only the tile partials travel:
+//     every CTA: tables of the live fits' vertices (one lane per curve record), |op(tile) - target tile| per fit
+//                (score_kernel's cooperative path), its tile partials -> every CTA's shared memory (st.async over distributed
+//                shared memory, completing the transaction count of the receiver's mbarrier: no fence, no cluster barrier)
+//     every CTA: the fit warps wait on that mbarrier, sum the partials in tile order, consume the score and propose the next
+//                vertex (nm_step, on shared memory and registers)
+// until every fit of the state is finished; the leader (CTA 0) writes results and the fits' state back, and the cluster takes
+// the next state (atomic work counter).  One hand-over per evaluation; two partial buffers / mbarriers alternate by round
+// parity, so a CTA that runs one round ahead can never complete a phase its neighbour still waits on.
 // Vertices and scores never leave the SMs.  The arithmetic is the round-by-round path's, bit for bit: the same tiles, the
 // same groups per thread in the same order, the same warp / tile reduction order, the same Nelder-Mead code --
 // tests/test_gpu_nm.py compares the two exactly.
@@ -387,20 +389,18 @@ constexpr int RES_MAXT = 16;     // tiles per state = cluster size (8 is the por
 
 struct ResidentShared {
     float wsum[SCORE_NW][SCORE_NW];
-    float part[SCORE_NW][RES_MAXT];      // leader: tile partials of every fit, sent by the cluster's CTAs (completing sbar)
-    float cprm[SCORE_NW][NM_MAXN];       // pending vertex of every fit, sent by the leader to every CTA (completing pbar)
-    int cops[SCORE_NW];                  // its operator, T2O_OP_SKIP once the fit has finished (ditto)
-    float pend[SCORE_NW][NM_MAXN];       // leader: the vertex / operator the Nelder-Mead code proposes next (staging for cprm / cops)
+    float part[2][SCORE_NW][RES_MAXT];   // tile partials of every fit, sent by every CTA of the cluster to every CTA (completing sbar);
+                                         // two buffers / barriers, by round parity: a CTA one round ahead cannot touch an open phase
+    float pend[SCORE_NW][NM_MAXN];       // the vertex / operator each fit evaluates next (written by this CTA's own Nelder-Mead step)
     int pop[SCORE_NW];
     int cops0[SCORE_NW];                 // the fits' operators when the state was taken (table offsets)
     int cmask[SCORE_NW];                 // the fits' masks
-    int nmoff[SCORE_NW];                 // leader: byte offset of fit c in the Nelder-Mead region, -1: not loaded
-    int nmN[SCORE_NW];                   // leader: its number of parameters
+    int nmoff[SCORE_NW];                 // byte offset of fit c in the Nelder-Mead region, -1: not loaded
+    int nmN[SCORE_NW];                   // its number of parameters
     int toff[SCORE_NW];                  // offset of fit c's table (floats)
     int next_state;                      // the state the cluster works on (written by the leader into every CTA)
     uint64_t bar;                        // the tiles' TMA loads
-    uint64_t pbar;                       // a round's pending vertices have arrived (100 bytes per fit)
-    uint64_t sbar;                       // leader: a round's tile partials have arrived (4 bytes per fit and CTA)
+    uint64_t sbar[2];                    // a round's tile partials have arrived (4 bytes per live fit and CTA)
 };
 
 // floats of an operator's table / bytes of a fit's Nelder-Mead state in shared memory (host and device agree on these)
@@ -408,7 +408,8 @@ __host__ __device__ inline int res_tab_floats(int op) { return op == OP_COLOR ? 
 __host__ __device__ inline int res_nm_bytes(int N) { return (8 * (N * N + 5 * N + 2) + 4 * (N + 9) + 7) & ~7; }
 
 // fit c of the leader: views into the packed region [sim (N+1) x N | vec 3 x N | fsim N+1 | fxr | perm N+1 | ctl 8]
-__device__ __forceinline__ void res_bind(NMWarp &w, unsigned char *base, int N, const NMArgs &nm, int p, int lane, float *cprm, int *cop) {
+__device__ __forceinline__ void res_bind(NMWarp &w, unsigned char *base, int N, const NMArgs &nm, int p, int lane, float *cprm, int *cop,
+                                         bool store_result) {
     double *d = reinterpret_cast<double *>(base);
     w.sim = d; d += (N + 1) * N;
     w.vec = d; d += 3 * N;
@@ -423,6 +424,7 @@ __device__ __forceinline__ void res_bind(NMWarp &w, unsigned char *base, int N, 
     w.cop = cop;
     w.ld = N;
     w.lane = lane;
+    w.store_result = store_result;
     // (these views are shared memory: lets the Nelder-Mead code, written for generic pointers, use LDS / STS)
     __builtin_assume(__isShared(w.sim)); __builtin_assume(__isShared(w.vec)); __builtin_assume(__isShared(w.fsim));
     __builtin_assume(__isShared(w.fxr)); __builtin_assume(__isShared(w.perm)); __builtin_assume(__isShared(w.ctl));
@@ -457,12 +459,13 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
     unsigned char *nmreg = reinterpret_cast<unsigned char *>(tabs + tab_cap);      // nm_cap bytes (leader only)
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
-        mbar_init(&sh.pbar, 1);
-        mbar_init(&sh.sbar, 1);
+        mbar_init(&sh.sbar[0], 1);
+        mbar_init(&sh.sbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t bar_phase = 0, pphase = 0, sphase = 0;
+    uint32_t bar_phase = 0, sphase0 = 0, sphase1 = 0;             // (parities of the tile barrier and of the two partial barriers)
+    unsigned int gr = 0;                                         // rounds this CTA has played (the same in every CTA of the cluster)
     const bool single = a.ntiles == 1;
     // every CTA of the cluster is running (and its mbarriers are initialised) before anyone writes into its shared memory
     cluster.sync();
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
         // ---- the cluster's next state
         if (rank == 0 && tid == 0) {
             const int nxt = (int)atomicAdd(work_counter, 1u);
-            for (int r = 0; r < a.ntiles; ++r) (a.ntiles == 1 ? &sh : cluster.map_shared_rank(&sh, r))->next_state = nxt;
+            for (int r = 0; r < a.ntiles; ++r) (single ? &sh : cluster.map_shared_rank(&sh, r))->next_state = nxt;
         }
         cluster.sync();
         const int s = sh.next_state;
@@ -491,26 +494,30 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             tma_load_4d(sS, &tm_state, &sh.bar, x0 - HX, y0 - 1, 0, s);
             tma_load_4d(sT, &tm_target, &sh.bar, x0, y0, 0, t_idx);
         }
-        // ---- leader: the fits' Nelder-Mead state -> shared memory, their pending vertices -> every CTA
+        // ---- EVERY CTA: the fits' Nelder-Mead state -> its own shared memory (warp c: fit c).  The CTAs of a cluster run the
+        // same deterministic step on the same numbers, so each knows every next vertex without being told: only the tile
+        // partials travel.  The leader's copy is the one that writes results and goes back to the caller's arrays.
         NMRegs nr = NMRegs{0.0, 0.0, 0, NM_DONE, 0, 0, 0, 0, 1};
-        if (rank == 0 && warp < m) {
+        int my_to = 0;                                           // warp c < m: where fit c's table lives
+        bool mylive = false;                                     // warp c < m: fit c has not finished
+        if (warp < m) {
             const int p = cbeg + warp;
             // a state whose fits do not fit the shared memory the host sized is left alone (its fits stay unfinished)
             int off = 0, N = 0, nm_total = 0, tab_total = 0;
             for (int c = 0; c < m; ++c) {
                 const int Nc = __ldcg(nm.st.ctl + (size_t)(cbeg + c) * 8 + CTL_N);
-                if (c < warp) off += res_nm_bytes(Nc);
+                const int tf = res_tab_floats(__ldcg(a.cand_op + cbeg + c));
+                if (c < warp) { off += res_nm_bytes(Nc); my_to += tf; }
                 if (c == warp) N = Nc;
                 nm_total += res_nm_bytes(Nc);
-                tab_total += res_tab_floats(__ldcg(a.cand_op + cbeg + c));
+                tab_total += tf;
             }
             const bool fits_ok = nm_total <= nm_cap && tab_total <= tab_cap;
             const int op = fits_ok ? __ldcg(a.cand_op + p) : OP_SKIP;
             const float prm = lane < NM_MAXN ? __ldcg(a.cand_param + (size_t)p * NM_MAXN + lane) : 0.0f;
-            const int mi = (HM && a.cand_mask) ? a.cand_mask[p] : -1;
             if (op != OP_SKIP) {
                 NMWarp w;
-                res_bind(w, nmreg + off, N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
+                res_bind(w, nmreg + off, N, nm, p, lane, sh.pend[warp], &sh.pop[warp], rank == 0);
                 const double *gsim = nm.st.sim + (size_t)p * NM_ROWS * NM_MAXN, *gvec = nm.st.vec + (size_t)p * 3 * NM_MAXN;
                 if (lane < N) {
                     for (int r = 0; r <= N; ++r) w.sim[r * N + lane] = __ldcg(gsim + r * NM_MAXN + lane);
@@ -525,21 +532,21 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
                 __syncwarp();
                 nm_load(w);
                 nr = nm_regs(w);                                 // (the warp keeps the fit's control state in registers from here on)
+                mylive = true;
             }
-            if (lane == 0) { sh.nmoff[warp] = op != OP_SKIP ? off : -1; sh.nmN[warp] = N; sh.pop[warp] = op; }
+            if (lane == 0) {
+                sh.nmoff[warp] = op != OP_SKIP ? off : -1; sh.nmN[warp] = N; sh.pop[warp] = op;
+                sh.toff[warp] = my_to; sh.cmask[warp] = (HM && a.cand_mask) ? a.cand_mask[p] : -1;
+            }
             if (lane < NM_MAXN) sh.pend[warp][lane] = prm;
-            for (int r = 0; r < a.ntiles; ++r) {
-                ResidentShared *dst = single ? &sh : cluster.map_shared_rank(&sh, r);
-                if (lane == 0) { dst->cops0[warp] = op; dst->cmask[warp] = mi; }
-            }
+            __syncwarp();
         }
-        cluster.sync();                                          // cops0 / cmask are in place (once per state)
         mbar_wait_or_trap(&sh.bar, bar_phase);                   // the tiles
         bar_phase ^= 1u;
         // is every value of the state tile (halo included; out-of-image zeros count) in [0, 1]?  One look per state.
         bool clamped_in = true;
         for (int i = tid; i < 3 * srows * spitch; i += SCORE_NT) clamped_in &= in01(sS[i]);
-        clamped_in = __syncthreads_and(clamped_in) != 0;
+        clamped_in = __syncthreads_and(clamped_in) != 0;         // (also: pop / toff / cmask of every warp are in place)
         // ---- rounds
 #ifdef T2O_RES_PROBE
         long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
@@ -547,47 +554,28 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
 #else
 #define T2O_PROBE(i)
 #endif
-        bool mylive = true;                                      // warp c < m: fit c has not finished (as far as this warp has seen)
-        int my_to = 0;                                           // warp c < m: where fit c's table lives (the same in every CTA)
-        if (warp < m) {
-            for (int c = 0; c < warp; ++c) my_to += res_tab_floats(sh.cops0[c]);
-            if (lane == 0) sh.toff[warp] = my_to;                // (read behind the first round's block barrier)
-        }
         for (int round = 0; round < max_rounds; ++round) {
 #ifdef T2O_RES_PROBE
             pt = clock64();
 #endif
-            // leader: the fits' pending vertices (or T2O_OP_SKIP) -> every CTA, itself included: 25 words per fit
-            if (rank == 0 && warp < m) {
-                __syncwarp();
-                const uint32_t v = lane < NM_MAXN ? __float_as_uint(sh.pend[warp][lane]) : (uint32_t)sh.pop[warp];
-                if (lane <= NM_MAXN) {
-                    void *dst = lane < NM_MAXN ? (void *)&sh.cprm[warp][lane] : (void *)&sh.cops[warp];
-                    if (single) st_local_u32(dst, v, &sh.pbar);
-                    else
-                        for (int r = 0; r < a.ntiles; ++r) st_async_u32(mapa_u32(dst, r), v, mapa_u32(&sh.pbar, r));
-                }
-            }
-            // (only the warps that build a table wait for the vertices; the others go on to the barrier behind the tables, which
-            // costs no issue slots)
-            if (tid == 0) mbar_expect_tx(&sh.pbar, (uint32_t)m * 4u * (NM_MAXN + 1));
-            if (warp < m && mylive) mbar_wait_or_trap(&sh.pbar, pphase);
-            pphase ^= 1u;
-            T2O_PROBE(0)
+            // the table of this warp's fit, from the vertex its own step proposed
             if (warp < m && mylive) {
-                const int op = sh.cops[warp];
+                const int op = sh.pop[warp];
                 mylive = op != OP_SKIP;
-                if (mylive) build_table_lanes<false>(op, lane, sh.cprm[warp], a.L, tabs + my_to);
+                if (mylive) build_table_lanes<false>(op, lane, sh.pend[warp], a.L, tabs + my_to);
             }
-            __syncthreads();                                     // tables built <=> this round's vertices have arrived
-            bool any = false;
-            for (int c = 0; c < m; ++c) any |= sh.cops[c] != OP_SKIP;
-            if (!any) break;
+            __syncthreads();
+            int nlive = 0;
+            for (int c = 0; c < m; ++c) nlive += sh.pop[c] != OP_SKIP ? 1 : 0;
+            if (nlive == 0) break;
+            const int pb = (int)(gr & 1u);
+            gr += 1u;
+            if (tid == 0) mbar_expect_tx(&sh.sbar[pb], (uint32_t)(a.ntiles * nlive) * 4u);
             T2O_PROBE(1)
             // fit by fit, all warps share the tile (score_kernel's cooperative path: thread tid takes groups tid, tid + 256, ...)
 #pragma unroll 1
             for (int c = 0; c < m; ++c) {
-                const int op = sh.cops[c];
+                const int op = sh.pop[c];
                 if (op == OP_SKIP) continue;
                 const float *tab = tabs + sh.toff[c];
                 const float p = tab[0];
@@ -607,36 +595,32 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             }
             __syncthreads();
             T2O_PROBE(2)
-            if (tid < m) {
+            // this tile's partial of every live fit -> every CTA of the cluster (st.async completing the receiver's mbarrier)
+            if (tid < m && sh.pop[tid] != OP_SKIP) {
                 float v = 0.0f;
 #pragma unroll
                 for (int w = 0; w < SCORE_NW; ++w) v += sh.wsum[tid][w];
-                const uint32_t pv = __float_as_uint(sh.cops[tid] != OP_SKIP ? v : 0.0f);
-                if (single) st_local_u32(&sh.part[tid][0], pv, &sh.sbar);
-                else st_async_u32(mapa_u32(&sh.part[tid][rank], 0), pv, mapa_u32(&sh.sbar, 0));
+                const uint32_t pv = __float_as_uint(v);
+                if (single) st_local_u32(&sh.part[pb][tid][0], pv, &sh.sbar[pb]);
+                else
+                    for (int r = 0; r < a.ntiles; ++r) st_async_u32(mapa_u32(&sh.part[pb][tid][rank], r), pv, mapa_u32(&sh.sbar[pb], r));
             }
-            if (rank == 0) {
-                if (tid == 0) mbar_expect_tx(&sh.sbar, (uint32_t)(a.ntiles * m) * 4u);
-                // every publishing warp waits, live fit or not: the CTAs send their partials after they have consumed this round's
-                // vertices, so nothing of the next round can reach an mbarrier phase that is still open
-                if (warp < m) mbar_wait_or_trap(&sh.sbar, sphase);
-                sphase ^= 1u;
+            // the warps that own a live fit wait for the cluster's partials, sum them in tile order and step their fit -- in
+            // every CTA alike; the others go on to the barrier behind the next tables (which costs no issue slots)
+            if (warp < m && mylive) {
+                mbar_wait_or_trap(&sh.sbar[pb], pb ? sphase1 : sphase0);
+                T2O_PROBE(3)
+                float v = 0.0f;
+                for (int t = lane; t < a.ntiles; t += 32) v += sh.part[pb][warp][t];
+                v = warp_sum(v);
+                NMWarp w;
+                res_bind(w, nmreg + sh.nmoff[warp], sh.nmN[warp], nm, cbeg + warp, lane, sh.pend[warp], &sh.pop[warp], rank == 0);
+                nm_set_regs(w, nr);
+                nm_step(w, nm, v);
+                nr = nm_regs(w);
+                __syncwarp();
             }
-            T2O_PROBE(3)
-            if (rank == 0 && warp < m) {
-                if (mylive) {
-                    float v = 0.0f;
-                    for (int t = lane; t < a.ntiles; t += 32) v += sh.part[warp][t];
-                    v = warp_sum(v);
-                    NMWarp w;
-                    unsigned char *base = nmreg + sh.nmoff[warp];
-                    // ctl sits behind (N+1) N + 3 N + N + 2 doubles and N + 1 ints: N is read through the leader's copy of it
-                    res_bind(w, base, sh.nmN[warp], nm, cbeg + warp, lane, sh.pend[warp], &sh.pop[warp]);
-                    nm_set_regs(w, nr);
-                    nm_step(w, nm, v);
-                    nr = nm_regs(w);
-                }
-            }
+            if (pb) sphase1 ^= 1u; else sphase0 ^= 1u;
             T2O_PROBE(4)
 #ifdef T2O_RES_PROBE
             pc[5] += 1;
@@ -653,7 +637,7 @@ __global__ void __launch_bounds__(SCORE_NT, 2) nm_resident_kernel(const __grid_c
             __syncwarp();                                        // (the lanes read what other lanes of the warp wrote in the last step)
             const int p = cbeg + warp, N = sh.nmN[warp];
             NMWarp w;
-            res_bind(w, nmreg + sh.nmoff[warp], N, nm, p, lane, sh.pend[warp], &sh.pop[warp]);
+            res_bind(w, nmreg + sh.nmoff[warp], N, nm, p, lane, sh.pend[warp], &sh.pop[warp], true);
             nm_set_regs(w, nr);
             nm_store(w);                                         // registers -> the shared-memory copy that goes back below
             double *gsim = nm.st.sim + (size_t)p * NM_ROWS * NM_MAXN, *gvec = nm.st.vec + (size_t)p * 3 * NM_MAXN;
