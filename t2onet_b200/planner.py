@@ -498,6 +498,10 @@ def beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_name
     return results
 
 
+_PIPE_LOCAL = threading.local()      # per worker thread: its CUDA stream
+_PIPE_POOLS = {}                     # workers -> the persistent thread pool
+
+
 def beam_search_pipelined(batches, executor, beam_size, operations, operation_names, max_step, err, workers=2, counter=None,
                           **kwargs):
     """`beam_search_batch` over a stream of batches -- the dataset loop of preprocess/gen_greedy_seqs_FiveK.py:44-64 -- with
@@ -513,26 +517,36 @@ def beam_search_pipelined(batches, executor, beam_size, operations, operation_na
         return [beam_search_batch(bt[0], bt[1], executor, beam_size, operations, operation_names, max_step, err, counter=counter,
                                   **dict(kwargs, **(bt[2] if len(bt) > 2 else {}))) for bt in batches]
     results, counts, pending = {}, {}, []
-    local = threading.local()
+    local = _PIPE_LOCAL
 
     def work(k, I_0, I_gt, ready, kw):
         dev = I_0.device
         torch.cuda.set_device(dev)                                  # (a new thread starts on device 0)
-        if not hasattr(local, 'stream'):
-            local.stream = torch.cuda.Stream(dev)
+        if not hasattr(local, 'streams'):
+            local.streams = {}
+        stream = local.streams.get(dev)
+        if stream is None:
+            stream = local.streams[dev] = torch.cuda.Stream(dev)
         cnt = [0]
-        with torch.cuda.stream(local.stream):
-            local.stream.wait_event(ready)                          # the batch was produced on the caller's stream
+        with torch.cuda.stream(stream):
+            stream.wait_event(ready)                                # the batch was produced on the caller's stream
             res = beam_search_batch(I_0, I_gt, executor, beam_size, operations, operation_names, max_step, err, counter=cnt, **kw)
-            local.stream.synchronize()
-        I_0.record_stream(local.stream)
-        I_gt.record_stream(local.stream)
+            stream.synchronize()
+        I_0.record_stream(stream)
+        I_gt.record_stream(stream)
         return k, res, cnt[0]
 
-    with cf.ThreadPoolExecutor(max_workers=workers) as pool:
-        def drain(fut):
-            k, res, c = fut.result()
-            results[k], counts[k] = res, c
+    # the worker threads (and with them their CUDA streams, the allocator's pools of those streams and the library's
+    # workspaces) live as long as the process: a fresh pool per call meant fresh streams, and a second or two of cudaMalloc
+    # at the start of every call
+    pool = _PIPE_POOLS.get(workers)
+    if pool is None:
+        pool = _PIPE_POOLS[workers] = cf.ThreadPoolExecutor(max_workers=workers, thread_name_prefix='t2o-planner')
+
+    def drain(fut):
+        k, res, c = fut.result()
+        results[k], counts[k] = res, c
+    try:
         for k, bt in enumerate(batches):
             I_0, I_gt = bt[0], bt[1]
             ready = torch.cuda.Event()
@@ -540,8 +554,14 @@ def beam_search_pipelined(batches, executor, beam_size, operations, operation_na
             pending.append(pool.submit(work, k, I_0, I_gt, ready, dict(kwargs, **(bt[2] if len(bt) > 2 else {}))))
             if len(pending) >= workers + 1:
                 drain(pending.pop(0))
-        for fut in pending:
-            drain(fut)
+        while pending:
+            drain(pending.pop(0))
+    finally:
+        for fut in pending:                                         # (an exception above: let the batches in flight finish)
+            try:
+                fut.result()
+            except Exception:
+                pass
     if counter is not None:
         counter[0] += sum(counts.values())
     return [results[k] for k in range(len(results))]
