@@ -259,8 +259,8 @@ int t2o_nm_advance(const t2o_nm_state *state /*host struct of device pointers*/,
 /*
  * Every fit of a planner step in ONE launch (replaces the thousands of get_dist calls scipy makes per fit,
  * utils/beam_search.py:65-91): after t2o_nm_start, a cluster of CTAs (one per tile of the image) keeps a state and its target
- * in shared memory for the whole life of the state's fits, the cluster's first CTA keeps the fits' simplices there too, and
- * the cluster iterates score -> advance -- the same arithmetic as rounds of t2o_score_candidates + t2o_nm_advance, bit for
+ * in shared memory for the whole life of the state's fits, every CTA keeps (and steps) the fits' simplices there too, and
+ * the cluster iterates score -> advance, exchanging only the tiles' partial sums -- the same arithmetic as rounds of t2o_score_candidates + t2o_nm_advance, bit for
  * bit, without re-staging the images or touching device memory between evaluations.
  * fits_begin[s] .. fits_begin[s+1] are the fits of state s (S + 1 ints, at most 8 fits per state; fits sorted by state as for
  * t2o_score_candidates); fit_mask / masks as in t2o_score_candidates_masked (NULL: none); host_fits_begin / host_fit_op are

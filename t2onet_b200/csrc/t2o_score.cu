@@ -393,7 +393,6 @@ struct ResidentShared {
                                          // two buffers / barriers, by round parity: a CTA one round ahead cannot touch an open phase
     float pend[SCORE_NW][NM_MAXN];       // the vertex / operator each fit evaluates next (written by this CTA's own Nelder-Mead step)
     int pop[SCORE_NW];
-    int cops0[SCORE_NW];                 // the fits' operators when the state was taken (table offsets)
     int cmask[SCORE_NW];                 // the fits' masks
     int nmoff[SCORE_NW];                 // byte offset of fit c in the Nelder-Mead region, -1: not loaded
     int nmN[SCORE_NW];                   // its number of parameters
