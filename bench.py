@@ -258,7 +258,7 @@ def measure_e2e(TF, dev, wl, batches, packed, steps, barrier, u8):
     from t2onet_b200 import visual_utils as V
     B, H, W = wl['B'], wl['H'], wl['W']
     px_step = B * H * W
-    NSLOT = 2
+    NSLOT = int(os.environ.get('T2O_E2E_SLOTS', 2))
     nh = min(2, len(batches))
     if u8:
         # image and target of a step sit back to back in ONE pinned buffer: one host -> device copy per step
