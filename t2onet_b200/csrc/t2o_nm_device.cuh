@@ -33,7 +33,7 @@ struct NMArgs {
 // development probe (-DT2O_RES_PROBE): clocks per stage of the advance of 24-parameter fits, summed over all of them
 #ifdef T2O_RES_PROBE
 static __device__ unsigned long long g_nmp[12];
-#define T2O_NMP(i) if (w.lane == 0 && w.N == NM_MAXN) { const long long now_ = clock64(); atomicAdd(&g_nmp[i], (unsigned long long)(now_ - w.pt)); w.pt = now_; }
+#define T2O_NMP(i) if (w.lane == 0 && w.N == NM_MAXN && w.store_result) { const long long now_ = clock64(); atomicAdd(&g_nmp[i], (unsigned long long)(now_ - w.pt)); w.pt = now_; }
 #else
 #define T2O_NMP(i)
 #endif
@@ -384,7 +384,7 @@ __device__ __forceinline__ void nm_step(NMWarp &w, const NMArgs &a, float l1) {
     }
     T2O_NMP(7)
 #ifdef T2O_RES_PROBE
-    if (w.lane == 0 && w.N == NM_MAXN) atomicAdd(&g_nmp[8], 1ull);
+    if (w.lane == 0 && w.N == NM_MAXN && w.store_result) atomicAdd(&g_nmp[8], 1ull);
 #endif
 }
 
