@@ -288,7 +288,16 @@ T2O_HD void build_table_part(int op, int part, const float *p, int L, float *tab
 // chain its own warp: the serial builders (three threads of one warp, one curve each, different operators one after the
 // other) kept a 128 x 128 step's other 250 threads at the first barrier for ~2 us.
 template <bool BWD = true>
+__device__ __forceinline__ void build_table_lanes_l(int op, int lane, const float *p, const int L, float *tab);
+// (curve_steps is 8 everywhere in the reference: with the constant the lane split is a shift, 1 / L and the loop predicates
+// fold -- the same operations on the same values)
+template <bool BWD = true>
 __device__ __forceinline__ void build_table_lanes(int op, int lane, const float *p, int L, float *tab) {
+    if (L == MAX_L) build_table_lanes_l<BWD>(op, lane, p, MAX_L, tab);
+    else build_table_lanes_l<BWD>(op, lane, p, L, tab);
+}
+template <bool BWD>
+__device__ __forceinline__ void build_table_lanes_l(int op, int lane, const float *p, const int L, float *tab) {
     if (op == OP_COLOR || op == OP_TONE) {
         const int part = lane / L, j = lane - part * L;
         const bool active = part < (op == OP_COLOR ? 3 : 1);
