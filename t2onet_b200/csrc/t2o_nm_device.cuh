@@ -61,12 +61,11 @@ struct NMWarp {
 };
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-// Double-precision compares and maxima through INTEGER instructions.  On this part a warp-wide FP64 instruction holds its pipe
-// for ~32 cycles (measured: the 4 FP64 instructions per vertex of the first version of the convergence test cost ~140 cycles
-// per vertex), and one warp per fit runs this code on the critical path of every evaluation -- so FP64 is kept for the
-// roundings scipy's arithmetic needs (sums, differences, the centroid) and everything that only ORDERS values works on bit
-// patterns: the pattern of |x| orders like |x|, a NaN's is above +inf's, and function values (L1 distances: >= +0, +inf or
-// NaN) order like their own patterns.
+// Double-precision compares and maxima through INTEGER instructions.  One warp per fit runs this code on the critical path of
+// every evaluation, so what counts is the latency of each dependent instruction, and FP64 compares / min-max / |x| are
+// multi-instruction, low-rate sequences -- FP64 is kept for the roundings scipy's arithmetic needs (sums, differences, the
+// centroid) and everything that only ORDERS values works on bit patterns: the pattern of |x| orders like |x|, a NaN's is
+// above +inf's, and function values (L1 distances: >= +0, +inf or NaN) order like their own patterns.
 constexpr long long NM_INF_BITS = 0x7ff0000000000000ll;
 __device__ __forceinline__ long long nm_abs_bits(double x) {
     // (through the two words: written as one 64-bit mask the compiler turns it back into an FP64 |x| instruction)
