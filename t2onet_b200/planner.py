@@ -130,7 +130,11 @@ def fit_params_nelder_mead(states, targets, problems, executor, state_target=Non
     if not problems:
         return []
     L = getattr(executor.opt, 'curve_steps', 8)
-    order = sorted(range(len(problems)), key=lambda i: (problems[i][0], i))       # the scorer wants candidates sorted by state
+    sts = [p[0] for p in problems]
+    if all(a <= b for a, b in zip(sts, sts[1:])):                                # (the planner lists its problems state by state)
+        order = list(range(len(problems)))
+    else:
+        order = sorted(range(len(problems)), key=lambda i: (sts[i], i))           # the scorer wants candidates sorted by state
     x0 = {op: _param0(op, executor) for op in set(p[1] for p in problems)}
     nm = TF.DeviceNelderMead(states, targets, [problems[i][0] for i in order], [problems[i][1] for i in order],
                              [x0[problems[i][1]] for i in order], state_target=state_target,
